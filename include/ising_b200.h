@@ -1,0 +1,186 @@
+/*
+ * ising_b200.h — C ABI of libising_b200.so, the B200 (sm_100a) implementation of the spin-update hot
+ * path of Wandao123/IsingModel.jl.
+ *
+ * The reference has no FFI of its own: its boundary for this path is the Julia method set
+ *   SingleSpinFlip.update!(ua, node, fluct)            src/SingleSpinFlip.jl:31,46,65
+ *   OnBipartiteGraph.update!(ua, Fv, Fh)               src/OnBipartiteGraph.jl:30,53
+ *   SamplingHelper.makeSampler!(ua, n; ...) step loops src/SamplingHelper.jl:28-51,110-133
+ *   calcEnergy / calcLocalMagneticField / calcLocalAuxiliaryBias   src/SpinSystems.jl:68-83,139-157
+ * Each entry point below names the reference lines it replaces; the Julia `ccall` stubs that bind
+ * them are in isingmodel.jl_b200/julia/IsingModelB200.jl and INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, opaque handles, int return code (0 = ISB_OK), never throws;
+ *   - every pointer argument is a HOST pointer owned by the caller for the duration of the call,
+ *     except in the *_dev entry points, which take device pointers on the handle's device;
+ *   - matrices are column-major with a leading dimension (Julia layout);
+ *   - site / unit indices are 0-based (the Julia shim subtracts 1);
+ *   - spins cross the boundary as int8 (+1 / -1), replica-major: replica r occupies
+ *     s[r*ld .. r*ld + N), i.e. a Julia Matrix{Int8}(N, R);
+ *   - an "ensemble" is R independent chains (replicas) of one model (the reference has one chain
+ *     per SpinSystem, src/SpinSystems.jl:14-17; R = 1 reproduces it);
+ *   - there is NO CPU fallback: every call needs a CUDA device and fails with ISB_ERR_CUDA otherwise.
+ */
+#ifndef ISING_B200_H
+#define ISING_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISB_VERSION 100 /* 0.1.0 */
+
+typedef struct isb_ctx isb_ctx;     /* one CUDA device + error slot            */
+typedef struct isb_model isb_model; /* immutable couplings resident in HBM     */
+typedef struct isb_ens isb_ens;     /* R replicas of spins (+ cached fields)   */
+
+/* return codes */
+enum {
+    ISB_OK = 0,
+    ISB_ERR_ARG = 1,      /* NULL pointer, bad enum, negative count                       */
+    ISB_ERR_SIZE = 2,     /* dimension mismatch (mirrors the error() calls of SpinSystems.jl:23,41,102-114) */
+    ISB_ERR_NONFINITE = 3,/* NaN / Inf in J, h, W, T or a fluctuation                      */
+    ISB_ERR_CUDA = 4,     /* CUDA runtime / driver failure, or no device                   */
+    ISB_ERR_UNSUPPORTED = 5, /* shape outside what the kernels are built for               */
+    ISB_ERR_NCCL = 6,
+    ISB_ERR_STATE = 7     /* call not valid for this kind of model / ensemble              */
+};
+
+/* single-spin rules — src/SingleSpinFlip.jl:12-17 (Hopfield), :38-44 (Glauber == heat bath), :57-63 (Metropolis) */
+enum { ISB_RULE_HOPFIELD = 0, ISB_RULE_GLAUBER = 1, ISB_RULE_METROPOLIS = 2 };
+/* bipartite rules — src/OnBipartiteGraph.jl:10-16 (SCA), :45-51 (MomentumAnnealing) */
+enum { ISB_BIP_SCA = 0, ISB_BIP_MA = 1 };
+/* site order of a single-spin run */
+enum {
+    ISB_ORDER_SEQUENTIAL = 0, /* node = (start + k) mod N                                        */
+    ISB_ORDER_LIST = 1,       /* node = nodes[k]   (SamplingHelper.jl:39 pre-drawn list)         */
+    ISB_ORDER_RANDOM = 2      /* node drawn by the library's Philox stream, shared by replicas    */
+};
+/* how an externally supplied fluctuation array is indexed */
+enum {
+    ISB_FLUCT_PHILOX = 0,     /* no array: library draws u by Philox4x32-10 and transforms it    */
+    ISB_FLUCT_SHARED = 1,     /* one stream for all replicas                                      */
+    ISB_FLUCT_PER_REPLICA = 2 /* replica r has its own stream                                     */
+};
+/* arithmetic of the field accumulators / storage of the couplings */
+enum {
+    ISB_PREC_F64 = 0, /* J and fields in double: bit-exact with the Float64 reference whenever
+                         every partial sum is exactly representable (integer / dyadic J), and
+                         equal up to decisions closer to zero than ~1e-13 otherwise             */
+    ISB_PREC_F32 = 1, /* J and fields in float; decisions still taken in double                 */
+    ISB_PREC_AUTO = 2,/* F64 fields; J stored as float iff that is lossless                      */
+    ISB_PREC_BF16X3 = 3, /* bipartite tensor path: W split into 3 bf16 terms, fp32 accumulation */
+    ISB_PREC_BF16X1 = 4  /* bipartite tensor path: W rounded to one bf16 term (exact when W is)  */
+};
+
+/* ------------------------------------------------------------------ context */
+int isb_version(void);
+int isb_device_count(void);
+int isb_create(int device, isb_ctx **out);
+void isb_destroy(isb_ctx *ctx);
+/* Last error text of this context (never NULL); isb_last_error(NULL) = last creation error. */
+const char *isb_last_error(const isb_ctx *ctx);
+/* Use an existing stream (a cudaStream_t passed as void*) for all ensembles created afterwards. */
+int isb_set_stream(isb_ctx *ctx, void *cuda_stream);
+int isb_synchronize(isb_ctx *ctx);
+
+/* ------------------------------------------------------------------ models */
+/* SpinSystem(s, J, h): src/SpinSystems.jl:19-51.  J is n x n column-major (leading dimension ld).
+ * As the reference does, a non-symmetric J is symmetrised from its upper triangle (:31-34) and the
+ * diagonal is zeroed (:35-38); *warn (may be NULL) receives bit 0 / bit 1 when that happened. */
+int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const double *h, int prec,
+                    int *warn, isb_model **out);
+/* SpinSystemOnBipartiteGraph(sigma, tau, W, h, b): src/SpinSystems.jl:97-118. W is nv x nh. */
+int isb_model_bipartite(isb_ctx *ctx, int nv, int nh, const double *W, int64_t ld,
+                        const double *h, const double *b, int prec, isb_model **out);
+void isb_model_destroy(isb_model *m);
+int isb_model_num_visible(const isb_model *m);
+int isb_model_num_hidden(const isb_model *m); /* 0 for a general-graph model */
+
+/* ------------------------------------------------------------------ ensembles */
+int isb_ens_create(isb_model *m, int R, isb_ens **out);
+void isb_ens_destroy(isb_ens *e);
+int isb_ens_replicas(const isb_ens *e);
+/* spinConfiguration get/set: src/SpinSystems.jl:61-62,128-129 */
+int isb_ens_set_spins(isb_ens *e, const int8_t *s, int64_t ld);
+int isb_ens_get_spins(isb_ens *e, int8_t *s, int64_t ld);
+/* hiddenLayer get/set: src/SpinSystems.jl:130-131 */
+int isb_ens_set_hidden(isb_ens *e, const int8_t *t, int64_t ld);
+int isb_ens_get_hidden(isb_ens *e, int8_t *t, int64_t ld);
+/* calcEnergy: src/SpinSystems.jl:68-73 / :139-145; E has R entries. */
+int isb_ens_energy(isb_ens *e, double *E);
+/* sum of the (visible) spins of each replica; M has R entries. */
+int isb_ens_magnetization(isb_ens *e, double *M);
+/* calcLocalMagneticField(ss): src/SpinSystems.jl:75-78 / :147-150; F is [R][ld], ld >= N(v). */
+int isb_ens_local_field(isb_ens *e, double *F, int64_t ld);
+/* calcLocalAuxiliaryBias: src/SpinSystems.jl:154-157; A is [R][ld], ld >= Nh. */
+int isb_ens_local_aux_bias(isb_ens *e, double *A, int64_t ld);
+
+/* ------------------------------------------------------------------ single-spin-flip runs */
+/*
+ * The step loop of makeSampler!(::SingleSpinUpdatingAlgorithm, n) (src/SamplingHelper.jl:45-49)
+ * with the accept/flip rules of src/SingleSpinFlip.jl:31-36,46-55,65-74, for all R replicas:
+ *   for k in 0..nsteps-1:  T <- Tsched[k / steps_per_T];  update!(ua, node_k, fluct_k)
+ *
+ *   order/nodes/start : see ISB_ORDER_*; nodes has nsteps entries (0-based) for ISB_ORDER_LIST.
+ *   fluct_mode/fluct  : ISB_FLUCT_SHARED: fluct[nsteps]; ISB_FLUCT_PER_REPLICA: fluct[R][nsteps];
+ *                       ISB_FLUCT_PHILOX: fluct ignored, (seed, step_offset) select the stream and
+ *                       fluct_k = log(u/(1-u)) (Glauber), -log(u) (Metropolis), unused (Hopfield).
+ *   Tsched            : nT temperatures, entry k / steps_per_T is used at step k (nT*steps_per_T >= nsteps).
+ *   trace_every       : if > 0, energies and magnetisations of every replica are recorded after
+ *                       each trace_every-th step into out_E / out_M ([nsteps/trace_every][R], either may be NULL).
+ *   out_flips         : R entries (or NULL): number of steps that changed the spin.
+ */
+int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *nodes, int start,
+                int fluct_mode, const double *fluct, uint64_t seed, uint64_t step_offset,
+                const double *Tsched, int64_t nT, int64_t steps_per_T, int64_t trace_every,
+                double *out_E, double *out_M, int64_t *out_flips);
+
+/* Fluctuations exactly as ISB_FLUCT_PHILOX generates them inside isb_ssf_run, for parity tests:
+ * out[r*nsteps + k], r in [r0, r0+nr). rule selects the transform. prec as the model's. */
+int isb_philox_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64_t step_offset,
+                     int r0, int nr, int64_t nsteps, double *out);
+/* Site list exactly as ISB_ORDER_RANDOM generates it. */
+int isb_philox_nodes(isb_ctx *ctx, int n, uint64_t seed, uint64_t step_offset, int64_t nsteps,
+                     int32_t *out);
+/* Raw Philox4x32-10 blocks (for known-answer tests): out[4*i..] = philox(ctr[4*i..], key). */
+int isb_philox_raw(isb_ctx *ctx, const uint32_t *ctr, const uint32_t key[2], int nblocks,
+                   uint32_t *out);
+
+/* ------------------------------------------------------------------ bipartite (block Gibbs) runs */
+/*
+ * The step loop of makeSampler!(::UpdatingAlgorithmOnBipartiteGraph, n) (src/SamplingHelper.jl:127-131)
+ * with update! of src/OnBipartiteGraph.jl:30-43 (SCA) / :53-66 (MomentumAnnealing):
+ *   hidden <- sgn+(2(W' sigma + b) - Fh*T [.* hidden]);  visible <- sgn+(2(W hidden + h) - Fv*T [.* visible])
+ *
+ *   fluct_mode SHARED: Fv[nsteps][nv], Fh[nsteps][nh]; PER_REPLICA: Fv[R][nsteps][nv], Fh[R][nsteps][nh];
+ *   PHILOX: drawn inside the kernel (logistic for SCA, exponential for MA).
+ *   out_E: [nsteps/trace_every][R] energies (may be NULL).
+ */
+int isb_bip_run(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *Fv,
+                const double *Fh, uint64_t seed, uint64_t step_offset, const double *Tsched,
+                int64_t nT, int64_t steps_per_T, int64_t trace_every, double *out_E);
+
+/* Fluctuations as ISB_FLUCT_PHILOX draws them in isb_bip_run: layer 0 = visible, 1 = hidden;
+ * out[(r - r0)][k][unit]. */
+int isb_philox_bip_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64_t step_offset,
+                         int layer, int nunits, int r0, int nr, int64_t nsteps, double *out);
+
+/* ------------------------------------------------------------------ instrumentation */
+/* Device time (ms, CUDA events on the ensemble's stream) of the kernels of the last *_run call,
+ * number of kernel launches it made, and bytes copied host->device / device->host by it. */
+int isb_ens_last_stats(const isb_ens *e, double *kernel_ms, int64_t *launches, int64_t *h2d_bytes,
+                       int64_t *d2h_bytes);
+/* Sum over replicas of accepted flips in the last isb_ssf_run (for the roofline's rows-fetched count). */
+int64_t isb_ens_last_flips(const isb_ens *e);
+/* Decisions of the last run whose |2h - fT| was below tie_eps (near-tie audit). */
+int64_t isb_ens_last_near_ties(const isb_ens *e);
+int isb_ens_set_tie_eps(isb_ens *e, double eps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISING_B200_H */

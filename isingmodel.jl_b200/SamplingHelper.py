@@ -1,0 +1,155 @@
+"""Host-side mirror of ``SamplingHelper`` (reference: src/SamplingHelper.jl) over the C ABI.
+
+``update_`` / ``makeSampler_`` keep the reference's contract (draw order, temperature applied before the
+step, n+1 yielded states that are the SAME mutable object).  ``run_`` is the batched form the library is
+built for: the whole step loop of ``makeSampler!`` executes inside one C-ABI call.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import MultiSpinFlip, OnBipartiteGraph, SingleSpinFlip, _lib
+from .SingleSpinFlip import SingleSpinUpdatingAlgorithm
+from .SpinSystems import UpdatingAlgorithmOnBipartiteGraph
+
+__all__ = ["update_", "makeSampler_", "run_"]
+
+
+def _rng(rng):
+    return rng if rng is not None else np.random.default_rng()
+
+
+def _bip(ua):
+    return ua.bipartite if isinstance(ua, MultiSpinFlip.MultiSpinUpdatingAlgorithm) else ua
+
+
+def update_(ua, rng=None):
+    """``update!(ua; rng)`` — src/SamplingHelper.jl:22-26 (single spin: node first, then the fluctuation),
+    :104-108 (bipartite: visible fluctuations first, then hidden)."""
+    rng = _rng(rng)
+    if isinstance(ua, SingleSpinUpdatingAlgorithm):
+        n = ua.spinSystem._host_spins.shape[1]
+        updatedNode = int(rng.integers(0, n))
+        fluctuation = float(ua.distribution.rand(rng))
+        return SingleSpinFlip.update_(ua, updatedNode, fluctuation)
+    b = _bip(ua)
+    ss = b.spinSystem
+    fv = b.distribution.rand(rng, ss._host_s.shape[1])
+    fh = b.distribution.rand(rng, ss._host_t.shape[1])
+    if b is ua:
+        return OnBipartiteGraph.update_(ua, fv, fh)
+    return MultiSpinFlip.update_(ua, fv, fh)
+
+
+def _schedule(ua, maxMCSteps, annealingSchedule):
+    """T[k] for k = 0..n: the reference sets T <- schedule(k) BEFORE step k (SamplingHelper.jl:43-46,128)."""
+    if not hasattr(ua, "temperature"):  # Hopfield: hasproperty(ua, :temperature) is false (:33)
+        return None
+    if annealingSchedule is None:
+        T0 = ua.temperature
+        return np.full(maxMCSteps + 1, T0, dtype=np.float64)
+    return np.array([float(annealingSchedule(k)) for k in range(maxMCSteps + 1)], dtype=np.float64)
+
+
+def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offset=0, order="random",
+         trace_every=0, per_replica_noise=True):
+    """The whole ``makeSampler!`` loop in one library call.  Returns a dict of traces.
+
+    rng given  -> site list and fluctuations are drawn on the host in the reference's order
+                  (SamplingHelper.jl:39-40 / :121-122) and shipped to the GPU;
+    rng None   -> drawn on the GPU by the counter RNG (Philox4x32-10, ``seed``/``step_offset``).
+    order      -> "random" (the reference's uniformly random site per step) or "sequential" (sweeps).
+    """
+    if maxMCSteps < 0:
+        warnings.warn(f"{maxMCSteps} is negative.")  # SamplingHelper.jl:29-31
+        maxMCSteps = 0
+    T = _schedule(ua, maxMCSteps, annealingSchedule)
+    Tsteps = None if T is None else T[1:] if maxMCSteps > 0 else T[:1]
+    if isinstance(ua, SingleSpinUpdatingAlgorithm):
+        ss = ua.spinSystem
+        ens = ss._ensemble()
+        R, n = ss._host_spins.shape
+        nodes = fluct = None
+        per_rep = False
+        if rng is not None:
+            if order == "random":
+                nodes = rng.integers(0, n, maxMCSteps)
+            if ua._rule != _lib.RULE_HOPFIELD:
+                per_rep = per_replica_noise and R > 1
+                fluct = ua.distribution.rand(rng, (R, maxMCSteps) if per_rep else maxMCSteps)
+        o = _lib.ORDER_SEQUENTIAL if order == "sequential" else (_lib.ORDER_LIST if nodes is not None else _lib.ORDER_RANDOM)
+        out = ens.ssf_run(ua._rule, maxMCSteps, order=o, nodes=nodes, fluct=fluct, fluct_per_replica=per_rep,
+                          seed=seed, step_offset=step_offset, T=Tsteps, trace_every=trace_every)
+        ss._dev_newer = True
+        if T is not None and maxMCSteps > 0:
+            ua.temperature = float(T[-1])
+        return out
+    b = _bip(ua)
+    ss = b.spinSystem
+    ens = ss._ensemble()
+    Fv = Fh = None
+    if rng is not None:
+        # reference layout: (units, steps) column-major == [steps][units] row-major
+        Fv = b.distribution.rand(rng, (maxMCSteps, ens.nv))
+        Fh = b.distribution.rand(rng, (maxMCSteps, ens.nh))
+    E = ens.bip_run(b._rule, maxMCSteps, Fv=Fv, Fh=Fh, seed=seed, step_offset=step_offset, T=Tsteps,
+                    trace_every=trace_every)
+    ss._dev_newer = True
+    if maxMCSteps > 0:
+        b.temperature = float(T[-1])
+    if b is not ua:
+        ua._sync_back()
+    return {"E": E}
+
+
+def makeSampler_(updatingAlgorithm, maxMCSteps, annealingSchedule=None, rng=None, *, stride=1):
+    """``makeSampler!(ua, n; annealingSchedule, rng)`` — src/SamplingHelper.jl:28-51, 69-91, 110-133.
+
+    A generator standing in for the Julia ``Channel``: yields ``updatingAlgorithm`` (the same mutable
+    object every time) once before the first step and then after every ``stride`` steps (reference:
+    stride = 1, n + 1 items).  All randomness is drawn up front in the reference's order.
+    """
+    ua = updatingAlgorithm
+    if maxMCSteps < 0:
+        warnings.warn(f"{maxMCSteps} is negative.")
+        maxMCSteps = 0
+    rng = _rng(rng)
+    T = _schedule(ua, maxMCSteps, annealingSchedule)
+    single = isinstance(ua, SingleSpinUpdatingAlgorithm)
+    if single:
+        n = ua.spinSystem._host_spins.shape[1]
+        updatedNodes = rng.integers(0, n, maxMCSteps)              # :39
+        fluctuations = ua.distribution.rand(rng, maxMCSteps)       # :40
+    else:
+        b = _bip(ua)
+        ens = b.spinSystem._ensemble()
+        Fv = b.distribution.rand(rng, (maxMCSteps, ens.nv))        # :121
+        Fh = b.distribution.rand(rng, (maxMCSteps, ens.nh))        # :122
+
+    def gen():
+        if T is not None:
+            ua.temperature = float(T[0])                           # :43
+        yield ua                                                   # :44
+        k = 0
+        while k < maxMCSteps:
+            m = min(stride, maxMCSteps - k)
+            if single:
+                ss = ua.spinSystem
+                ss._ensemble().ssf_run(ua._rule, m, nodes=updatedNodes[k:k + m],
+                                       fluct=None if ua._rule == _lib.RULE_HOPFIELD else fluctuations[k:k + m],
+                                       T=None if T is None else T[k + 1:k + 1 + m])
+                ss._dev_newer = True
+            else:
+                b = _bip(ua)
+                b.spinSystem._ensemble().bip_run(b._rule, m, Fv=Fv[k:k + m], Fh=Fh[k:k + m], T=T[k + 1:k + 1 + m])
+                b.spinSystem._dev_newer = True
+                if b is not ua:
+                    ua._sync_back()
+            k += m
+            if T is not None:
+                ua.temperature = float(T[k])                       # :46 / :128
+            yield ua                                               # :48 / :130
+
+    return gen()

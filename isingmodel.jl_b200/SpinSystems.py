@@ -1,0 +1,371 @@
+"""Host-side mirror of ``SpinSystems`` (reference: src/SpinSystems.jl) over the C ABI.
+
+Same type / function names and argument meaning as the Julia module; the arithmetic runs in
+``libising_b200.so`` on the GPU (no CPU path).  Extension over the reference: the spin
+configuration may be an ``(R, N)`` array, in which case the object is an ensemble of R independent
+chains sharing one J; a 1-D configuration is the reference's single chain (R = 1).
+
+Python conventions: site indices are 0-based (the Julia shim in ``julia/IsingModelB200.jl`` keeps the
+reference's 1-based indices), ``update!`` is spelled ``update_``.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["SpinSystem", "UpdatingAlgorithm", "getSpinConfiguration", "getCouplingCoefficients",
+           "getExternalMagneticField", "calcEnergy", "calcLocalMagneticField", "SpinSystemOnBipartiteGraph",
+           "UpdatingAlgorithmOnBipartiteGraph", "getHiddenLayer", "getAuxiliaryBias", "calcLocalAuxiliaryBias",
+           "setSpinConfiguration", "setCouplingCoefficients", "setExternalMagneticField", "setHiddenLayer",
+           "setAuxiliaryBias", "heaviside"]
+
+
+def _as_spins(x, name):
+    a = np.asarray(x)
+    if a.ndim not in (1, 2):
+        raise ValueError(f"{name} must be a vector (one chain) or an (R, N) array (R replicas)")
+    return a
+
+
+def _squeeze(self, arr):
+    """Reference objects hold one chain: return the vector / scalar when R == 1 and the input was 1-D."""
+    return arr[0] if self._single else arr
+
+
+class SpinSystem:
+    """src/SpinSystems.jl:14-52.  ``SpinSystem(spinConfiguration, couplingCoefficients, externalMagneticField)``."""
+
+    def __init__(self, spinConfiguration, couplingCoefficients, externalMagneticField, *, device=None,
+                 prec=_lib.PREC_AUTO):
+        s = _as_spins(spinConfiguration, "spinConfiguration")
+        self._single = s.ndim == 1
+        s = np.atleast_2d(s)
+        J = np.asarray(couplingCoefficients)
+        if hasattr(couplingCoefficients, "toarray"):  # scipy.sparse, as the reference tests pass `sparse(...)`
+            J = couplingCoefficients.toarray()
+        h = np.asarray(externalMagneticField)
+        numNodes = s.shape[1]
+        if J.ndim != 2 or J.shape[0] != J.shape[1]:
+            r, c = (J.shape + (0, 0))[:2]
+            raise ValueError(f"The coupling-coefficient matrix is not a square matrix: {r}rows ≠ {c}columns.")
+        row = J.shape[0]
+        if numNodes < row:      # :25-27
+            warnings.warn("The size of the spin-configuration vector is too smaller than the size of the "
+                          "coupling-coefficient matrix.  The incorresponding components of the "
+                          "coupling-coefficient matrix are ignored.")
+            J = J[:numNodes, :numNodes]
+        elif numNodes > row:    # :28-30
+            warnings.warn("The size of the spin-configuration vector is too bigger than the size of the "
+                          "coupling-coefficient matrix.  The incorresponding components of the "
+                          "spin-configuration vector are ignored.")
+            s = s[:, :row]
+        elif not np.array_equal(J, J.T):  # :31-33
+            warnings.warn("The coupling-coefficient matrix should be symmetric.  It is symmetrized by its "
+                          "upper-triangular components automatically.")
+            J = np.triu(J) + np.triu(J, 1).T
+        if np.any(np.diag(J) != 0):  # :35-38
+            warnings.warn("The diagonal components of the coupling-coefficient matrix should be zero.  Their "
+                          "non-zero components are ignored.")
+            J = J - np.diag(np.diag(J))
+        numBias = h.shape[0]
+        if row != numBias:      # :40-42
+            raise ValueError("The size of the coupling-coefficient matrix does not match the size of the "
+                             f"external-magnetic-field vector: {row} ≠ {numBias}.")
+        elif numNodes < numBias:  # :43-45
+            warnings.warn("The size of the spin-configuration vector is too smaller than the size of the "
+                          "external-magnetic-field vector.  The incorresponding components of the "
+                          "external-magnetic-field vector are ignored.")
+            h = h[:numNodes]
+        self._J = np.asarray(J, dtype=np.float64)       # float.(...) :50
+        self._h = np.asarray(h, dtype=np.float64)
+        self._host_spins = np.ascontiguousarray(s, dtype=np.int8)
+        if not np.all(np.abs(np.asarray(s, dtype=np.float64)) == 1.0):
+            raise ValueError("spins must be +1 / -1")
+        self._device, self._prec = device, prec
+        self._model = self._ens = None
+        self._dev_newer = False
+
+    # ---- device plumbing
+    @property
+    def replicas(self):
+        return self._host_spins.shape[0]
+
+    def _ensemble(self):
+        if self._ens is None:
+            ctx = _lib.context(self._device)
+            with warnings.catch_warnings():
+                self._model = _lib.Model.dense(ctx, self._J, self._h, self._prec)
+            self._ens = _lib.Ensemble(self._model, self.replicas)
+            self._ens.set_spins(self._host_spins)
+        return self._ens
+
+    def _invalidate_model(self):
+        s = self._spins2d()
+        self._host_spins = s
+        self._ens = self._model = None
+        self._dev_newer = False
+
+    def _spins2d(self):
+        if self._dev_newer:
+            self._host_spins = self._ens.get_spins()
+            self._dev_newer = False
+        return self._host_spins
+
+    # ---- reference fields
+    @property
+    def spinConfiguration(self):
+        return _squeeze(self, self._spins2d())
+
+    @spinConfiguration.setter
+    def spinConfiguration(self, value):
+        v = np.ascontiguousarray(np.atleast_2d(np.asarray(value)), dtype=np.int8)
+        if v.shape != self._host_spins.shape:
+            raise ValueError("spin configuration has the wrong shape")
+        self._host_spins = v
+        self._dev_newer = False
+        if self._ens is not None:
+            self._ens.set_spins(v)
+
+    @property
+    def couplingCoefficients(self):
+        return self._J
+
+    @couplingCoefficients.setter
+    def couplingCoefficients(self, J):
+        J = np.asarray(J, dtype=np.float64)
+        if J.shape != self._J.shape:
+            raise ValueError("coupling-coefficient matrix has the wrong shape")
+        self._invalidate_model()
+        self._J = J
+
+    @property
+    def externalMagneticField(self):
+        return self._h
+
+    @externalMagneticField.setter
+    def externalMagneticField(self, h):
+        h = np.asarray(h, dtype=np.float64)
+        if h.shape != self._h.shape:
+            raise ValueError("external-magnetic-field vector has the wrong shape")
+        self._invalidate_model()
+        self._h = h
+
+    def __deepcopy__(self, memo):
+        return SpinSystem(self.spinConfiguration.copy(), self._J.copy(), self._h.copy(), device=self._device,
+                          prec=self._prec)
+
+
+class UpdatingAlgorithm:
+    """src/SpinSystems.jl:54-59 — any subclass has a ``spinSystem`` field."""
+    spinSystem: SpinSystem
+
+
+class SpinSystemOnBipartiteGraph:
+    """src/SpinSystems.jl:90-119."""
+
+    def __init__(self, spinConfiguration, hiddenLayer, couplingCoefficients, externalMagneticField, auxiliaryBias,
+                 *, device=None, prec=_lib.PREC_F64):
+        s = _as_spins(spinConfiguration, "spinConfiguration")
+        t = _as_spins(hiddenLayer, "hiddenLayer")
+        self._single = s.ndim == 1
+        s, t = np.atleast_2d(s), np.atleast_2d(t)
+        W = couplingCoefficients.toarray() if hasattr(couplingCoefficients, "toarray") else np.asarray(couplingCoefficients)
+        h, b = np.asarray(externalMagneticField), np.asarray(auxiliaryBias)
+        nv, nh = s.shape[1], t.shape[1]
+        row, column = W.shape
+        if row != nv:
+            raise ValueError("The size of the coupling-coefficient matrix does not match the number of visible "
+                             f"and hidden nodes: {nv}nodes ≠ {row}rows.")
+        elif column != nh:
+            raise ValueError("The size of the coupling-coefficient matrix does not match the number of visible "
+                             f"and hidden nodes: {nh}nodes ≠ {column}columns.")
+        if h.shape[0] != nv:
+            raise ValueError("The size of the external-magnetic-field vector does not match the number of "
+                             f"visible nodes: {h.shape[0]} ≠ {nv}.")
+        elif b.shape[0] != nh:
+            raise ValueError("The size of the eauxiliary-bias vector does not match the number of hidden "
+                             f"nodes: {b.shape[0]} ≠ {nh}.")
+        if s.shape[0] != t.shape[0]:
+            raise ValueError("visible and hidden layers must hold the same number of replicas")
+        self._W = np.asarray(W, dtype=np.float64)
+        self._h = np.asarray(h, dtype=np.float64)
+        self._b = np.asarray(b, dtype=np.float64)
+        if not (np.all(np.abs(np.asarray(s, dtype=np.float64)) == 1.0)
+                and np.all(np.abs(np.asarray(t, dtype=np.float64)) == 1.0)):
+            raise ValueError("spins must be +1 / -1")
+        self._host_s = np.ascontiguousarray(s, dtype=np.int8)
+        self._host_t = np.ascontiguousarray(t, dtype=np.int8)
+        self._device, self._prec = device, prec
+        self._model = self._ens = None
+        self._dev_newer = False
+
+    @property
+    def replicas(self):
+        return self._host_s.shape[0]
+
+    def _ensemble(self):
+        if self._ens is None:
+            ctx = _lib.context(self._device)
+            self._model = _lib.Model.bipartite(ctx, self._W, self._h, self._b, self._prec)
+            self._ens = _lib.Ensemble(self._model, self.replicas)
+            self._ens.set_spins(self._host_s)
+            self._ens.set_hidden(self._host_t)
+        return self._ens
+
+    def _pull(self):
+        if self._dev_newer:
+            self._host_s = self._ens.get_spins()
+            self._host_t = self._ens.get_hidden()
+            self._dev_newer = False
+
+    def _invalidate_model(self):
+        self._pull()
+        self._ens = self._model = None
+
+    @property
+    def spinConfiguration(self):
+        self._pull()
+        return _squeeze(self, self._host_s)
+
+    @spinConfiguration.setter
+    def spinConfiguration(self, value):
+        self._pull()
+        v = np.ascontiguousarray(np.atleast_2d(np.asarray(value)), dtype=np.int8)
+        if v.shape != self._host_s.shape:
+            raise ValueError("spin configuration has the wrong shape")
+        self._host_s = v
+        if self._ens is not None:
+            self._ens.set_spins(v)
+
+    @property
+    def hiddenLayer(self):
+        self._pull()
+        return _squeeze(self, self._host_t)
+
+    @hiddenLayer.setter
+    def hiddenLayer(self, value):
+        self._pull()
+        v = np.ascontiguousarray(np.atleast_2d(np.asarray(value)), dtype=np.int8)
+        if v.shape != self._host_t.shape:
+            raise ValueError("hidden layer has the wrong shape")
+        self._host_t = v
+        if self._ens is not None:
+            self._ens.set_hidden(v)
+
+    @property
+    def couplingCoefficients(self):
+        return self._W
+
+    @couplingCoefficients.setter
+    def couplingCoefficients(self, W):
+        W = np.asarray(W, dtype=np.float64)
+        if W.shape != self._W.shape:
+            raise ValueError("coupling-coefficient matrix has the wrong shape")
+        self._invalidate_model()
+        self._W = W
+
+    @property
+    def externalMagneticField(self):
+        return self._h
+
+    @externalMagneticField.setter
+    def externalMagneticField(self, h):
+        self._invalidate_model()
+        self._h = np.asarray(h, dtype=np.float64)
+
+    @property
+    def auxiliaryBias(self):
+        return self._b
+
+    @auxiliaryBias.setter
+    def auxiliaryBias(self, b):
+        self._invalidate_model()
+        self._b = np.asarray(b, dtype=np.float64)
+
+    def __deepcopy__(self, memo):
+        return SpinSystemOnBipartiteGraph(self.spinConfiguration.copy(), self.hiddenLayer.copy(), self._W.copy(),
+                                          self._h.copy(), self._b.copy(), device=self._device, prec=self._prec)
+
+
+class UpdatingAlgorithmOnBipartiteGraph:
+    """src/SpinSystems.jl:121-126."""
+    spinSystem: SpinSystemOnBipartiteGraph
+
+
+def _ss(x):
+    return x.spinSystem if hasattr(x, "spinSystem") else x
+
+
+# getters / setters: src/SpinSystems.jl:61-66, 128-137
+def getSpinConfiguration(ua):
+    return _ss(ua).spinConfiguration
+
+
+def setSpinConfiguration(ua, spinConfiguration):
+    _ss(ua).spinConfiguration = spinConfiguration
+
+
+def getCouplingCoefficients(ua):
+    return _ss(ua).couplingCoefficients
+
+
+def setCouplingCoefficients(ua, couplingCoefficients):
+    _ss(ua).couplingCoefficients = couplingCoefficients
+
+
+def getExternalMagneticField(ua):
+    return _ss(ua).externalMagneticField
+
+
+def setExternalMagneticField(ua, externalMagneticField):
+    _ss(ua).externalMagneticField = externalMagneticField
+
+
+def getHiddenLayer(ua):
+    return _ss(ua).hiddenLayer
+
+
+def setHiddenLayer(ua, hiddenLayer):
+    _ss(ua).hiddenLayer = hiddenLayer
+
+
+def getAuxiliaryBias(ua):
+    return _ss(ua).auxiliaryBias
+
+
+def setAuxiliaryBias(ua, auxiliaryBias):
+    _ss(ua).auxiliaryBias = auxiliaryBias
+
+
+def calcEnergy(x):
+    """src/SpinSystems.jl:68-73 / :139-145 (on the GPU: isb_ens_energy)."""
+    ss = _ss(x)
+    E = ss._ensemble().energy()
+    return float(E[0]) if ss._single else E
+
+
+def calcLocalMagneticField(x, nodeIndex=None):
+    """src/SpinSystems.jl:75-86 / :147-152 (isb_ens_local_field); ``nodeIndex`` is 0-based."""
+    ss = _ss(x)
+    F = ss._ensemble().local_field()
+    if nodeIndex is not None:
+        if isinstance(ss, SpinSystemOnBipartiteGraph):
+            raise TypeError("calcLocalMagneticField(ss, i) is defined for SpinSystem only")
+        F = F[:, int(nodeIndex)]
+        return float(F[0]) if ss._single else F
+    return F[0] if ss._single else F
+
+
+def calcLocalAuxiliaryBias(x):
+    """src/SpinSystems.jl:154-159 (isb_ens_local_aux_bias)."""
+    ss = _ss(x)
+    A = ss._ensemble().local_aux_bias()
+    return A[0] if ss._single else A
+
+
+def heaviside(x, c=1.0):
+    """src/SpinSystems.jl:163-171 — host helper for documentation / tests; kernels implement it as !(x < 0)."""
+    return 1.0 if x > 0 else (0.0 if x < 0 else c)

@@ -1,0 +1,739 @@
+// api.cu — the extern "C" surface of libising_b200.so (include/ising_b200.h): contexts, models,
+// ensembles, host<->device staging and the run entry points.  No torch types, no CPU compute path:
+// every entry point that produces spins, fields or energies launches a CUDA kernel.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "handles.hpp"
+
+static thread_local std::string g_create_err = "";
+
+namespace isb {
+
+int fail(isb_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_create_err = buf;
+    return code;
+}
+
+int dev_reserve(isb_ctx *ctx, int slot, size_t bytes, void **out) {
+    isb_devbuf &b = ctx->scratch[slot];
+    if (bytes == 0) bytes = 16;
+    if (b.cap < bytes) {
+        if (b.p) {
+            ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ISB_CUDA(ctx, cudaFree(b.p));
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        const size_t cap = std::max(bytes, (size_t)4096);
+        ISB_CUDA(ctx, cudaMalloc(&b.p, cap));
+        b.cap = cap;
+    }
+    *out = b.p;
+    return ISB_OK;
+}
+
+}  // namespace isb
+
+using isb::fail;
+
+#define ISB_TRY(expr)            \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != ISB_OK) return _rc; \
+    } while (0)
+
+static bool all_finite(const double *p, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (!std::isfinite(p[i])) return false;
+    return true;
+}
+
+static int h2d(isb_ctx *ctx, void *dst, const void *src, size_t bytes, int64_t *acc) {
+    if (bytes == 0) return ISB_OK;
+    ISB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (acc) *acc += (int64_t)bytes;
+    return ISB_OK;
+}
+static int d2h(isb_ctx *ctx, void *dst, const void *src, size_t bytes, int64_t *acc) {
+    if (bytes == 0) return ISB_OK;
+    ISB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (acc) *acc += (int64_t)bytes;
+    return ISB_OK;
+}
+
+extern "C" {
+
+// ------------------------------------------------------------------ context
+int isb_version(void) { return ISB_VERSION; }
+
+int isb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int isb_create(int device, isb_ctx **out) {
+    if (!out) return fail(nullptr, ISB_ERR_ARG, "isb_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, ISB_ERR_CUDA,
+                    "isb_create: no CUDA device (%s); libising_b200 has no CPU fallback",
+                    ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+    }
+    if (device < 0 || device >= ndev)
+        return fail(nullptr, ISB_ERR_ARG, "isb_create: device %d out of range [0, %d)", device, ndev);
+    ISB_CUDA(nullptr, cudaSetDevice(device));
+    int major = 0, sms = 0, optin = 0;
+    ISB_CUDA(nullptr, cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    ISB_CUDA(nullptr, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    ISB_CUDA(nullptr, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (major != 10)
+        return fail(nullptr, ISB_ERR_CUDA, "isb_create: device %d is sm_%d0; this library is built for sm_100a only",
+                    device, major);
+    isb_ctx *ctx = new isb_ctx();
+    ctx->device = device;
+    ctx->num_sms = sms;
+    ctx->smem_optin = (size_t)optin;
+    ISB_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    ISB_CUDA(nullptr, cudaEventCreate(&ctx->ev0));
+    ISB_CUDA(nullptr, cudaEventCreate(&ctx->ev1));
+    *out = ctx;
+    return ISB_OK;
+}
+
+void isb_destroy(isb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->scratch)
+        if (b.p) cudaFree(b.p);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *isb_last_error(const isb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int isb_set_stream(isb_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return ISB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return ISB_OK;
+}
+
+int isb_synchronize(isb_ctx *ctx) {
+    if (!ctx) return ISB_ERR_ARG;
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+
+// ------------------------------------------------------------------ models
+static int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const double *h, int prec, int *warn,
+                    isb_model **out) {
+    if (!ctx) return ISB_ERR_ARG;
+    if (!out || !J) return fail(ctx, ISB_ERR_ARG, "isb_model_dense: NULL argument");
+    *out = nullptr;
+    if (warn) *warn = 0;
+    if (n <= 0) return fail(ctx, ISB_ERR_SIZE, "isb_model_dense: n = %d must be positive", n);
+    if (ld < n) return fail(ctx, ISB_ERR_SIZE, "isb_model_dense: leading dimension %lld < n = %d", (long long)ld, n);
+    if (prec != ISB_PREC_F64 && prec != ISB_PREC_F32 && prec != ISB_PREC_AUTO)
+        return fail(ctx, ISB_ERR_ARG, "isb_model_dense: prec must be ISB_PREC_F64, _F32 or _AUTO");
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    const bool fast = n <= 1024;
+    const int npl = fast ? next_pow2((n + 31) / 32) : 0;
+    const int npad = fast ? 32 * npl : ((n + 31) / 32) * 32;
+    std::vector<double> Jn((size_t)npad * npad, 0.0), hn((size_t)npad, 0.0);
+    // symmetry / diagonal handling of src/SpinSystems.jl:31-38
+    bool sym = true, diag = false;
+    for (int j = 0; j < n && sym; ++j)
+        for (int i = 0; i < j; ++i)
+            if (J[i + (int64_t)j * ld] != J[j + (int64_t)i * ld]) {
+                sym = false;
+                break;
+            }
+    for (int j = 0; j < n; ++j) {
+        for (int i = 0; i <= j; ++i) {
+            const double up = J[i + (int64_t)j * ld];                     // upper triangle element (i <= j)
+            const double lo = sym ? up : J[i + (int64_t)j * ld];          // Symmetric(J, :U)
+            if (!std::isfinite(up)) return fail(ctx, ISB_ERR_NONFINITE, "isb_model_dense: J[%d,%d] is not finite", i, j);
+            if (i == j) {
+                if (up != 0.0) diag = true;
+                continue;
+            }
+            Jn[(size_t)i * npad + j] = up;
+            Jn[(size_t)j * npad + i] = lo;
+        }
+    }
+    if (warn) *warn = (sym ? 0 : 1) | (diag ? 2 : 0);
+    if (h) {
+        if (!all_finite(h, (size_t)n)) return fail(ctx, ISB_ERR_NONFINITE, "isb_model_dense: h is not finite");
+        for (int i = 0; i < n; ++i) hn[i] = h[i];
+    }
+    bool lossless_f32 = true;
+    for (size_t k = 0; k < Jn.size() && lossless_f32; ++k) lossless_f32 = (double)(float)Jn[k] == Jn[k];
+
+    isb_model *m = new isb_model();
+    m->ctx = ctx;
+    m->kind = ISB_KIND_DENSE;
+    m->prec = prec == ISB_PREC_AUTO ? ISB_PREC_F64 : prec;
+    m->n = n;
+    m->npad = npad;
+    m->npl = npl;
+    m->fast_ok = fast;
+    m->j_is_f32 = prec == ISB_PREC_F32 || (prec == ISB_PREC_AUTO && lossless_f32);
+    const size_t nn = (size_t)npad * npad;
+    int rc = ISB_OK;
+    do {
+        if (cudaMalloc(&m->J64, nn * sizeof(double)) != cudaSuccess || cudaMalloc(&m->h64, npad * sizeof(double)) != cudaSuccess) {
+            rc = fail(ctx, ISB_ERR_CUDA, "isb_model_dense: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        cudaMemcpyAsync(m->J64, Jn.data(), nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(m->h64, hn.data(), npad * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        if (fast) {
+            // permuted copy for the sweep kernel: site k*32+lane -> position (k/VEC)*32*VEC + lane*VEC + k%VEC
+            const int jsz = m->j_is_f32 ? 4 : 8;
+            const int vec = std::min(16 / jsz, npl);
+            std::vector<unsigned char> Jp(nn * jsz);
+            for (int i = 0; i < npad; ++i)
+                for (int s = 0; s < npad; ++s) {
+                    const int k = s >> 5, lane = s & 31;
+                    const size_t pos = (size_t)i * npad + (size_t)(k / vec) * (32 * vec) + lane * vec + (k % vec);
+                    const double v = Jn[(size_t)i * npad + s];
+                    if (m->j_is_f32)
+                        reinterpret_cast<float *>(Jp.data())[pos] = (float)v;
+                    else
+                        reinterpret_cast<double *>(Jp.data())[pos] = v;
+                }
+            if (cudaMalloc(&m->Jperm, nn * jsz) != cudaSuccess) {
+                rc = fail(ctx, ISB_ERR_CUDA, "isb_model_dense: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+            cudaMemcpyAsync(m->Jperm, Jp.data(), nn * jsz, cudaMemcpyHostToDevice, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+        }
+        cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) rc = fail(ctx, ISB_ERR_CUDA, "isb_model_dense: upload failed: %s", cudaGetErrorString(ce));
+    } while (0);
+    if (rc) {
+        isb_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return ISB_OK;
+}
+
+int isb_model_bipartite(isb_ctx *ctx, int nv, int nh, const double *W, int64_t ld, const double *h, const double *b,
+                        int prec, isb_model **out) {
+    if (!ctx) return ISB_ERR_ARG;
+    if (!out || !W) return fail(ctx, ISB_ERR_ARG, "isb_model_bipartite: NULL argument");
+    *out = nullptr;
+    if (nv <= 0 || nh <= 0) return fail(ctx, ISB_ERR_SIZE, "isb_model_bipartite: nv = %d, nh = %d must be positive", nv, nh);
+    if (ld < nv) return fail(ctx, ISB_ERR_SIZE, "isb_model_bipartite: leading dimension %lld < nv = %d", (long long)ld, nv);
+    if (prec == ISB_PREC_AUTO) prec = ISB_PREC_F64;
+    if (prec != ISB_PREC_F64 && prec != ISB_PREC_BF16X3 && prec != ISB_PREC_BF16X1)
+        return fail(ctx, ISB_ERR_ARG, "isb_model_bipartite: prec must be ISB_PREC_F64, _BF16X3 or _BF16X1");
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<double> Wr((size_t)nv * nh), Wt((size_t)nv * nh), hn((size_t)nv, 0.0), bn((size_t)nh, 0.0);
+    for (int j = 0; j < nh; ++j)
+        for (int i = 0; i < nv; ++i) {
+            const double v = W[i + (int64_t)j * ld];
+            if (!std::isfinite(v)) return fail(ctx, ISB_ERR_NONFINITE, "isb_model_bipartite: W[%d,%d] is not finite", i, j);
+            Wr[(size_t)i * nh + j] = v;
+            Wt[(size_t)j * nv + i] = v;
+        }
+    if (h) {
+        if (!all_finite(h, nv)) return fail(ctx, ISB_ERR_NONFINITE, "isb_model_bipartite: h is not finite");
+        std::copy(h, h + nv, hn.begin());
+    }
+    if (b) {
+        if (!all_finite(b, nh)) return fail(ctx, ISB_ERR_NONFINITE, "isb_model_bipartite: b is not finite");
+        std::copy(b, b + nh, bn.begin());
+    }
+    isb_model *m = new isb_model();
+    m->ctx = ctx;
+    m->kind = ISB_KIND_BIPARTITE;
+    m->prec = prec;
+    m->nv = nv;
+    m->nh = nh;
+    int rc = ISB_OK;
+    do {
+        const size_t nn = (size_t)nv * nh * sizeof(double);
+        if (cudaMalloc(&m->W64, nn) != cudaSuccess || cudaMalloc(&m->Wt64, nn) != cudaSuccess ||
+            cudaMalloc(&m->hb64, nv * sizeof(double)) != cudaSuccess || cudaMalloc(&m->bb64, nh * sizeof(double)) != cudaSuccess) {
+            rc = fail(ctx, ISB_ERR_CUDA, "isb_model_bipartite: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        cudaMemcpyAsync(m->W64, Wr.data(), nn, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(m->Wt64, Wt.data(), nn, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(m->hb64, hn.data(), nv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(m->bb64, bn.data(), nh * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) {
+            rc = fail(ctx, ISB_ERR_CUDA, "isb_model_bipartite: upload failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+        if (prec != ISB_PREC_F64) rc = isb::bip_tc_model_init(m, Wr.data());
+    } while (0);
+    if (rc) {
+        isb_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return ISB_OK;
+}
+
+void isb_model_destroy(isb_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    if (m->tc) isb::bip_tc_model_free(m);
+    cudaFree(m->J64);
+    cudaFree(m->Jperm);
+    cudaFree(m->h64);
+    cudaFree(m->W64);
+    cudaFree(m->Wt64);
+    cudaFree(m->hb64);
+    cudaFree(m->bb64);
+    delete m;
+}
+
+int isb_model_num_visible(const isb_model *m) { return !m ? 0 : (m->kind == ISB_KIND_DENSE ? m->n : m->nv); }
+int isb_model_num_hidden(const isb_model *m) { return !m ? 0 : (m->kind == ISB_KIND_DENSE ? 0 : m->nh); }
+
+// ------------------------------------------------------------------ ensembles
+int isb_ens_create(isb_model *m, int R, isb_ens **out) {
+    if (!m) return ISB_ERR_ARG;
+    isb_ctx *ctx = m->ctx;
+    if (!out) return fail(ctx, ISB_ERR_ARG, "isb_ens_create: out is NULL");
+    *out = nullptr;
+    if (R <= 0) return fail(ctx, ISB_ERR_SIZE, "isb_ens_create: R = %d must be positive", R);
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    isb_ens *e = new isb_ens();
+    e->model = m;
+    e->R = R;
+    int rc = ISB_OK;
+    do {
+        cudaError_t ce;
+        if (m->kind == ISB_KIND_DENSE) {
+            e->lds = m->npad;
+            ce = cudaMalloc(&e->spins, (size_t)R * e->lds);
+            if (ce == cudaSuccess) ce = cudaMemsetAsync(e->spins, 1, (size_t)R * e->lds, ctx->stream);
+            if (ce == cudaSuccess && m->fast_ok) ce = cudaMalloc(&e->fields, (size_t)R * m->npad * isb::ssf_field_elem_size(m));
+        } else {
+            e->lds = (m->nv + 15) / 16 * 16;
+            e->ldh = (m->nh + 15) / 16 * 16;
+            ce = cudaMalloc(&e->spins, (size_t)R * e->lds);
+            if (ce == cudaSuccess) ce = cudaMalloc(&e->hidden, (size_t)R * e->ldh);
+            if (ce == cudaSuccess) ce = cudaMemsetAsync(e->spins, 1, (size_t)R * e->lds, ctx->stream);
+            if (ce == cudaSuccess) ce = cudaMemsetAsync(e->hidden, 1, (size_t)R * e->ldh, ctx->stream);
+        }
+        if (ce == cudaSuccess) ce = cudaMalloc(&e->d_flips, (size_t)R * sizeof(unsigned long long));
+        if (ce == cudaSuccess) ce = cudaMalloc(&e->d_counters, 4 * sizeof(unsigned long long));
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) {
+            rc = fail(ctx, ISB_ERR_CUDA, "isb_ens_create: allocation failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+        if (m->kind == ISB_KIND_BIPARTITE && m->prec != ISB_PREC_F64) rc = isb::bip_tc_ens_init(e);
+    } while (0);
+    if (rc) {
+        isb_ens_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return ISB_OK;
+}
+
+void isb_ens_destroy(isb_ens *e) {
+    if (!e) return;
+    cudaSetDevice(e->model->ctx->device);
+    cudaStreamSynchronize(e->model->ctx->stream);
+    if (e->tc) isb::bip_tc_ens_free(e);
+    cudaFree(e->spins);
+    cudaFree(e->hidden);
+    cudaFree(e->fields);
+    cudaFree(e->d_flips);
+    cudaFree(e->d_counters);
+    delete e;
+}
+
+int isb_ens_replicas(const isb_ens *e) { return e ? e->R : 0; }
+
+static int copy_spins_in(isb_ens *e, int8_t *dst, int64_t ldd, int n, const int8_t *s, int64_t ld, const char *who) {
+    isb_ctx *ctx = e->model->ctx;
+    if (!s) return fail(ctx, ISB_ERR_ARG, "%s: NULL spin array", who);
+    if (ld < n) return fail(ctx, ISB_ERR_SIZE, "%s: leading dimension %lld < %d units", who, (long long)ld, n);
+    for (int r = 0; r < e->R; ++r)
+        for (int i = 0; i < n; ++i) {
+            const int8_t v = s[(int64_t)r * ld + i];
+            if (v != 1 && v != -1)
+                return fail(ctx, ISB_ERR_ARG, "%s: spin [%d, replica %d] = %d is not +1 / -1", who, i, r, (int)v);
+        }
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ISB_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)ldd, s, (size_t)ld, (size_t)n, (size_t)e->R, cudaMemcpyHostToDevice,
+                                    ctx->stream));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    e->fields_rule_sign = 0;
+    return ISB_OK;
+}
+static int copy_spins_out(isb_ens *e, const int8_t *src, int64_t lds, int n, int8_t *s, int64_t ld, const char *who) {
+    isb_ctx *ctx = e->model->ctx;
+    if (!s) return fail(ctx, ISB_ERR_ARG, "%s: NULL spin array", who);
+    if (ld < n) return fail(ctx, ISB_ERR_SIZE, "%s: leading dimension %lld < %d units", who, (long long)ld, n);
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ISB_CUDA(ctx, cudaMemcpy2DAsync(s, (size_t)ld, src, (size_t)lds, (size_t)n, (size_t)e->R, cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+
+int isb_ens_set_spins(isb_ens *e, const int8_t *s, int64_t ld) {
+    if (!e) return ISB_ERR_ARG;
+    const isb_model *m = e->model;
+    return copy_spins_in(e, e->spins, e->lds, m->kind == ISB_KIND_DENSE ? m->n : m->nv, s, ld, "isb_ens_set_spins");
+}
+int isb_ens_get_spins(isb_ens *e, int8_t *s, int64_t ld) {
+    if (!e) return ISB_ERR_ARG;
+    const isb_model *m = e->model;
+    return copy_spins_out(e, e->spins, e->lds, m->kind == ISB_KIND_DENSE ? m->n : m->nv, s, ld, "isb_ens_get_spins");
+}
+int isb_ens_set_hidden(isb_ens *e, const int8_t *t, int64_t ld) {
+    if (!e) return ISB_ERR_ARG;
+    if (e->model->kind != ISB_KIND_BIPARTITE) return fail(e->model->ctx, ISB_ERR_STATE, "isb_ens_set_hidden: not a bipartite ensemble");
+    return copy_spins_in(e, e->hidden, e->ldh, e->model->nh, t, ld, "isb_ens_set_hidden");
+}
+int isb_ens_get_hidden(isb_ens *e, int8_t *t, int64_t ld) {
+    if (!e) return ISB_ERR_ARG;
+    if (e->model->kind != ISB_KIND_BIPARTITE) return fail(e->model->ctx, ISB_ERR_STATE, "isb_ens_get_hidden: not a bipartite ensemble");
+    return copy_spins_out(e, e->hidden, e->ldh, e->model->nh, t, ld, "isb_ens_get_hidden");
+}
+
+int isb_ens_energy(isb_ens *e, double *E) {
+    if (!e) return ISB_ERR_ARG;
+    isb_ctx *ctx = e->model->ctx;
+    if (!E) return fail(ctx, ISB_ERR_ARG, "isb_ens_energy: E is NULL");
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *dE;
+    ISB_TRY(isb::dev_reserve(ctx, isb::SCR_OUT, (size_t)e->R * sizeof(double), (void **)&dE));
+    ISB_TRY(e->model->kind == ISB_KIND_DENSE ? isb::dense_energy_device(e, dE) : isb::bip_energy_device(e, dE));
+    ISB_TRY(d2h(ctx, E, dE, (size_t)e->R * sizeof(double), nullptr));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+
+int isb_ens_magnetization(isb_ens *e, double *M) {
+    if (!e) return ISB_ERR_ARG;
+    isb_ctx *ctx = e->model->ctx;
+    if (!M) return fail(ctx, ISB_ERR_ARG, "isb_ens_magnetization: M is NULL");
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *dM;
+    ISB_TRY(isb::dev_reserve(ctx, isb::SCR_OUT, (size_t)e->R * sizeof(double), (void **)&dM));
+    ISB_TRY(isb::magnetization_device(e, dM));
+    ISB_TRY(d2h(ctx, M, dM, (size_t)e->R * sizeof(double), nullptr));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+
+static int field_common(isb_ens *e, int layer, double *F, int64_t ld, const char *who) {
+    isb_model *m = e->model;
+    isb_ctx *ctx = m->ctx;
+    const int nout = m->kind == ISB_KIND_DENSE ? m->n : (layer == 0 ? m->nv : m->nh);
+    if (!F) return fail(ctx, ISB_ERR_ARG, "%s: output is NULL", who);
+    if (ld < nout) return fail(ctx, ISB_ERR_SIZE, "%s: leading dimension %lld < %d", who, (long long)ld, nout);
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *dF;
+    ISB_TRY(isb::dev_reserve(ctx, isb::SCR_OUT, (size_t)e->R * nout * sizeof(double), (void **)&dF));
+    if (m->kind == ISB_KIND_DENSE)
+        ISB_TRY(isb::dense_field_device(e, dF, nout));
+    else
+        ISB_TRY(isb::bip_field_device(e, layer, dF, nout));
+    ISB_CUDA(ctx, cudaMemcpy2DAsync(F, (size_t)ld * sizeof(double), dF, (size_t)nout * sizeof(double),
+                                    (size_t)nout * sizeof(double), (size_t)e->R, cudaMemcpyDeviceToHost, ctx->stream));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+int isb_ens_local_field(isb_ens *e, double *F, int64_t ld) {
+    if (!e) return ISB_ERR_ARG;
+    return field_common(e, 0, F, ld, "isb_ens_local_field");
+}
+int isb_ens_local_aux_bias(isb_ens *e, double *A, int64_t ld) {
+    if (!e) return ISB_ERR_ARG;
+    if (e->model->kind != ISB_KIND_BIPARTITE)
+        return fail(e->model->ctx, ISB_ERR_STATE, "isb_ens_local_aux_bias: not a bipartite ensemble");
+    return field_common(e, 1, A, ld, "isb_ens_local_aux_bias");
+}
+
+// ------------------------------------------------------------------ runs
+static int check_schedule(isb_ctx *ctx, const char *who, const double *Tsched, int64_t nT, int64_t steps_per_T,
+                          int64_t nsteps) {
+    if (!Tsched || nT <= 0) return fail(ctx, ISB_ERR_ARG, "%s: a temperature schedule is required", who);
+    if (steps_per_T <= 0) return fail(ctx, ISB_ERR_ARG, "%s: steps_per_T must be positive", who);
+    if ((nsteps + steps_per_T - 1) / steps_per_T > nT)
+        return fail(ctx, ISB_ERR_SIZE, "%s: schedule of %lld entries x %lld steps is shorter than %lld steps", who,
+                    (long long)nT, (long long)steps_per_T, (long long)nsteps);
+    if (!all_finite(Tsched, (size_t)nT)) return fail(ctx, ISB_ERR_NONFINITE, "%s: non-finite temperature", who);
+    return ISB_OK;
+}
+
+static void begin_stats(isb_ens *e) {
+    e->last_ms = 0.0;
+    e->last_launches = e->last_h2d = e->last_d2h = 0;
+    e->last_flips = e->last_near_ties = 0;
+}
+
+int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *nodes, int start, int fluct_mode,
+                const double *fluct, uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT,
+                int64_t steps_per_T, int64_t trace_every, double *out_E, double *out_M, int64_t *out_flips) {
+    if (!e) return ISB_ERR_ARG;
+    isb_model *m = e->model;
+    isb_ctx *ctx = m->ctx;
+    const char *who = "isb_ssf_run";
+    if (m->kind != ISB_KIND_DENSE) return fail(ctx, ISB_ERR_STATE, "%s: not a general-graph ensemble", who);
+    if (rule < ISB_RULE_HOPFIELD || rule > ISB_RULE_METROPOLIS) return fail(ctx, ISB_ERR_ARG, "%s: unknown rule %d", who, rule);
+    if (nsteps < 0) return fail(ctx, ISB_ERR_ARG, "%s: nsteps = %lld is negative", who, (long long)nsteps);
+    if (order < ISB_ORDER_SEQUENTIAL || order > ISB_ORDER_RANDOM) return fail(ctx, ISB_ERR_ARG, "%s: unknown order %d", who, order);
+    if (fluct_mode < ISB_FLUCT_PHILOX || fluct_mode > ISB_FLUCT_PER_REPLICA)
+        return fail(ctx, ISB_ERR_ARG, "%s: unknown fluct_mode %d", who, fluct_mode);
+    if (trace_every < 0) return fail(ctx, ISB_ERR_ARG, "%s: trace_every is negative", who);
+    const bool stochastic = rule != ISB_RULE_HOPFIELD;
+    if (!stochastic) fluct_mode = ISB_FLUCT_PHILOX;  // the fluctuation is a dummy (SingleSpinFlip.jl:31)
+    if (order == ISB_ORDER_LIST) {
+        if (!nodes && nsteps > 0) return fail(ctx, ISB_ERR_ARG, "%s: ISB_ORDER_LIST needs a node list", who);
+        for (int64_t k = 0; k < nsteps; ++k)
+            if (nodes[k] < 0 || nodes[k] >= m->n)
+                return fail(ctx, ISB_ERR_ARG, "%s: nodes[%lld] = %d outside [0, %d)", who, (long long)k, nodes[k], m->n);
+    } else if (order == ISB_ORDER_SEQUENTIAL) {
+        if (start < 0 || start >= m->n) return fail(ctx, ISB_ERR_ARG, "%s: start = %d outside [0, %d)", who, start, m->n);
+    }
+    if (fluct_mode != ISB_FLUCT_PHILOX) {
+        if (!fluct && nsteps > 0) return fail(ctx, ISB_ERR_ARG, "%s: fluctuation array is NULL", who);
+        const size_t nf = (size_t)nsteps * (fluct_mode == ISB_FLUCT_PER_REPLICA ? (size_t)e->R : 1);
+        if (!all_finite(fluct, nf)) return fail(ctx, ISB_ERR_NONFINITE, "%s: non-finite fluctuation", who);
+    }
+    const double zeroT = 0.0;
+    if (stochastic) {
+        ISB_TRY(check_schedule(ctx, who, Tsched, nT, steps_per_T, nsteps));
+    } else {
+        Tsched = &zeroT;
+        nT = 1;
+        steps_per_T = std::max<int64_t>(nsteps, 1);
+    }
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    begin_stats(e);
+    if (nsteps == 0) {
+        if (out_flips) std::fill(out_flips, out_flips + e->R, (int64_t)0);
+        return ISB_OK;
+    }
+
+    int32_t *d_nodes = nullptr;
+    double *d_fluct = nullptr, *d_T = nullptr, *d_E = nullptr, *d_M = nullptr;
+    if (order != ISB_ORDER_SEQUENTIAL) {
+        ISB_TRY(isb::dev_reserve(ctx, isb::SCR_NODES, (size_t)nsteps * sizeof(int32_t), (void **)&d_nodes));
+        if (order == ISB_ORDER_LIST)
+            ISB_TRY(h2d(ctx, d_nodes, nodes, (size_t)nsteps * sizeof(int32_t), &e->last_h2d));
+    }
+    if (fluct_mode != ISB_FLUCT_PHILOX) {
+        const size_t nf = (size_t)nsteps * (fluct_mode == ISB_FLUCT_PER_REPLICA ? (size_t)e->R : 1);
+        ISB_TRY(isb::dev_reserve(ctx, isb::SCR_FLUCT, nf * sizeof(double), (void **)&d_fluct));
+        ISB_TRY(h2d(ctx, d_fluct, fluct, nf * sizeof(double), &e->last_h2d));
+    }
+    ISB_TRY(isb::dev_reserve(ctx, isb::SCR_T, (size_t)nT * sizeof(double), (void **)&d_T));
+    ISB_TRY(h2d(ctx, d_T, Tsched, (size_t)nT * sizeof(double), &e->last_h2d));
+    const int64_t ntr = trace_every > 0 ? nsteps / trace_every : 0;
+    if (ntr > 0 && out_E) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_E, (size_t)ntr * e->R * sizeof(double), (void **)&d_E));
+    if (ntr > 0 && out_M) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_M, (size_t)ntr * e->R * sizeof(double), (void **)&d_M));
+    ISB_CUDA(ctx, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+
+    ISB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (order == ISB_ORDER_RANDOM) {
+        ISB_TRY(isb::philox_nodes_device(ctx, m->n, seed, step_offset, nsteps, d_nodes));
+        e->last_launches += 1;
+    }
+    ISB_TRY(isb::ssf_run_device(e, rule, nsteps, order, d_nodes, start, fluct_mode, d_fluct, seed, step_offset, d_T,
+                                steps_per_T, (d_E || d_M) ? trace_every : 0, d_E, d_M));
+    ISB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+
+    std::vector<unsigned long long> fl((size_t)e->R);
+    unsigned long long counters[4] = {0, 0, 0, 0};
+    ISB_TRY(d2h(ctx, fl.data(), e->d_flips, (size_t)e->R * sizeof(unsigned long long), &e->last_d2h));
+    ISB_TRY(d2h(ctx, counters, e->d_counters, sizeof counters, &e->last_d2h));
+    if (d_E) ISB_TRY(d2h(ctx, out_E, d_E, (size_t)ntr * e->R * sizeof(double), &e->last_d2h));
+    if (d_M) ISB_TRY(d2h(ctx, out_M, d_M, (size_t)ntr * e->R * sizeof(double), &e->last_d2h));
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) return fail(ctx, ISB_ERR_CUDA, "%s: kernel failed: %s", who, cudaGetErrorString(ce));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    e->last_ms = ms;
+    for (int r = 0; r < e->R; ++r) {
+        e->last_flips += (int64_t)fl[r];
+        if (out_flips) out_flips[r] = (int64_t)fl[r];
+    }
+    e->last_near_ties = (int64_t)counters[0];
+    return ISB_OK;
+}
+
+int isb_philox_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64_t step_offset, int r0, int nr,
+                     int64_t nsteps, double *out) {
+    (void)prec;
+    if (!ctx) return ISB_ERR_ARG;
+    if (!out || nr < 0 || nsteps < 0 || r0 < 0) return fail(ctx, ISB_ERR_ARG, "isb_philox_fluct: bad argument");
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *d;
+    const size_t bytes = (size_t)nr * nsteps * sizeof(double);
+    ISB_TRY(isb::dev_reserve(ctx, isb::SCR_OUT, bytes, (void **)&d));
+    ISB_TRY(isb::philox_fluct_device(ctx, rule, seed, step_offset, r0, nr, nsteps, d));
+    ISB_TRY(d2h(ctx, out, d, bytes, nullptr));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+
+int isb_philox_nodes(isb_ctx *ctx, int n, uint64_t seed, uint64_t step_offset, int64_t nsteps, int32_t *out) {
+    if (!ctx) return ISB_ERR_ARG;
+    if (!out || n <= 0 || nsteps < 0) return fail(ctx, ISB_ERR_ARG, "isb_philox_nodes: bad argument");
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int32_t *d;
+    ISB_TRY(isb::dev_reserve(ctx, isb::SCR_OUT, (size_t)nsteps * sizeof(int32_t), (void **)&d));
+    ISB_TRY(isb::philox_nodes_device(ctx, n, seed, step_offset, nsteps, d));
+    ISB_TRY(d2h(ctx, out, d, (size_t)nsteps * sizeof(int32_t), nullptr));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+
+int isb_philox_raw(isb_ctx *ctx, const uint32_t *ctr, const uint32_t key[2], int nblocks, uint32_t *out) {
+    if (!ctx) return ISB_ERR_ARG;
+    if (!ctr || !key || !out || nblocks < 0) return fail(ctx, ISB_ERR_ARG, "isb_philox_raw: bad argument");
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t *dc, *dout;
+    const size_t bytes = (size_t)nblocks * 4 * sizeof(uint32_t);
+    ISB_TRY(isb::dev_reserve(ctx, isb::SCR_TMP, bytes, (void **)&dc));
+    ISB_TRY(isb::dev_reserve(ctx, isb::SCR_OUT, bytes, (void **)&dout));
+    ISB_TRY(h2d(ctx, dc, ctr, bytes, nullptr));
+    ISB_TRY(isb::philox_raw_device(ctx, dc, key[0], key[1], nblocks, dout));
+    ISB_TRY(d2h(ctx, out, dout, bytes, nullptr));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+
+int isb_bip_run(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *Fv, const double *Fh,
+                uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT, int64_t steps_per_T,
+                int64_t trace_every, double *out_E) {
+    if (!e) return ISB_ERR_ARG;
+    isb_model *m = e->model;
+    isb_ctx *ctx = m->ctx;
+    const char *who = "isb_bip_run";
+    if (m->kind != ISB_KIND_BIPARTITE) return fail(ctx, ISB_ERR_STATE, "%s: not a bipartite ensemble", who);
+    if (rule != ISB_BIP_SCA && rule != ISB_BIP_MA) return fail(ctx, ISB_ERR_ARG, "%s: unknown rule %d", who, rule);
+    if (nsteps < 0) return fail(ctx, ISB_ERR_ARG, "%s: nsteps = %lld is negative", who, (long long)nsteps);
+    if (fluct_mode < ISB_FLUCT_PHILOX || fluct_mode > ISB_FLUCT_PER_REPLICA)
+        return fail(ctx, ISB_ERR_ARG, "%s: unknown fluct_mode %d", who, fluct_mode);
+    if (trace_every < 0) return fail(ctx, ISB_ERR_ARG, "%s: trace_every is negative", who);
+    ISB_TRY(check_schedule(ctx, who, Tsched, nT, steps_per_T, nsteps));
+    const size_t rep = fluct_mode == ISB_FLUCT_PER_REPLICA ? (size_t)e->R : 1;
+    const size_t nfv = (size_t)nsteps * m->nv * rep, nfh = (size_t)nsteps * m->nh * rep;
+    if (fluct_mode != ISB_FLUCT_PHILOX && nsteps > 0) {
+        if (!Fv || !Fh) return fail(ctx, ISB_ERR_ARG, "%s: fluctuation arrays are NULL", who);
+        if (!all_finite(Fv, nfv) || !all_finite(Fh, nfh)) return fail(ctx, ISB_ERR_NONFINITE, "%s: non-finite fluctuation", who);
+    }
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    begin_stats(e);
+    if (nsteps == 0) return ISB_OK;
+    double *d_Fv = nullptr, *d_Fh = nullptr, *d_T = nullptr, *d_E = nullptr;
+    if (fluct_mode != ISB_FLUCT_PHILOX) {
+        ISB_TRY(isb::dev_reserve(ctx, isb::SCR_FLUCT, nfv * sizeof(double), (void **)&d_Fv));
+        ISB_TRY(isb::dev_reserve(ctx, isb::SCR_FLUCT2, nfh * sizeof(double), (void **)&d_Fh));
+        ISB_TRY(h2d(ctx, d_Fv, Fv, nfv * sizeof(double), &e->last_h2d));
+        ISB_TRY(h2d(ctx, d_Fh, Fh, nfh * sizeof(double), &e->last_h2d));
+    }
+    ISB_TRY(isb::dev_reserve(ctx, isb::SCR_T, (size_t)nT * sizeof(double), (void **)&d_T));
+    ISB_TRY(h2d(ctx, d_T, Tsched, (size_t)nT * sizeof(double), &e->last_h2d));
+    const int64_t ntr = (trace_every > 0 && out_E) ? nsteps / trace_every : 0;
+    if (ntr > 0) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_E, (size_t)ntr * e->R * sizeof(double), (void **)&d_E));
+
+    ISB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (m->prec == ISB_PREC_F64)
+        ISB_TRY(isb::bip_run_exact_device(e, rule, nsteps, fluct_mode, d_Fv, d_Fh, seed, step_offset, d_T, steps_per_T,
+                                          trace_every, d_E));
+    else
+        ISB_TRY(isb::bip_run_tc_device(e, rule, nsteps, fluct_mode, d_Fv, d_Fh, seed, step_offset, d_T, steps_per_T,
+                                       trace_every, d_E));
+    ISB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    if (d_E) ISB_TRY(d2h(ctx, out_E, d_E, (size_t)ntr * e->R * sizeof(double), &e->last_d2h));
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) return fail(ctx, ISB_ERR_CUDA, "%s: kernel failed: %s", who, cudaGetErrorString(ce));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    e->last_ms = ms;
+    return ISB_OK;
+}
+
+int isb_philox_bip_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64_t step_offset, int layer, int nunits,
+                         int r0, int nr, int64_t nsteps, double *out) {
+    (void)prec;
+    if (!ctx) return ISB_ERR_ARG;
+    if (!out || nr < 0 || nsteps < 0 || r0 < 0 || nunits <= 0 || (layer != 0 && layer != 1))
+        return fail(ctx, ISB_ERR_ARG, "isb_philox_bip_fluct: bad argument");
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *d;
+    const size_t bytes = (size_t)nr * nsteps * nunits * sizeof(double);
+    ISB_TRY(isb::dev_reserve(ctx, isb::SCR_OUT, bytes, (void **)&d));
+    ISB_TRY(isb::philox_bip_fluct_device(ctx, rule, seed, step_offset, layer, nunits, r0, nr, nsteps, d));
+    ISB_TRY(d2h(ctx, out, d, bytes, nullptr));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+
+// ------------------------------------------------------------------ instrumentation
+int isb_ens_last_stats(const isb_ens *e, double *kernel_ms, int64_t *launches, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (!e) return ISB_ERR_ARG;
+    if (kernel_ms) *kernel_ms = e->last_ms;
+    if (launches) *launches = e->last_launches;
+    if (h2d_bytes) *h2d_bytes = e->last_h2d;
+    if (d2h_bytes) *d2h_bytes = e->last_d2h;
+    return ISB_OK;
+}
+int64_t isb_ens_last_flips(const isb_ens *e) { return e ? e->last_flips : 0; }
+int64_t isb_ens_last_near_ties(const isb_ens *e) { return e ? e->last_near_ties : 0; }
+int isb_ens_set_tie_eps(isb_ens *e, double eps) {
+    if (!e) return ISB_ERR_ARG;
+    if (!(eps >= 0.0)) return fail(e->model->ctx, ISB_ERR_ARG, "isb_ens_set_tie_eps: eps must be >= 0");
+    e->tie_eps = eps;
+    return ISB_OK;
+}
+
+}  // extern "C"

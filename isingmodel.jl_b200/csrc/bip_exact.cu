@@ -1,0 +1,222 @@
+// bip_exact.cu — Float64 block-Gibbs path for SpinSystemOnBipartiteGraph ensembles (ISB_PREC_F64).
+//
+// Replaces, for R chains at once,
+//   OnBipartiteGraph.update!(::StochasticCellularAutomata, Fv, Fh)   src/OnBipartiteGraph.jl:30-43
+//   OnBipartiteGraph.update!(::MomentumAnnealing, Fv, Fh)            src/OnBipartiteGraph.jl:53-66
+//   calcLocalAuxiliaryBias  W' sigma + b                              src/SpinSystems.jl:154-157
+//   calcLocalMagneticField  W tau + h                                 src/SpinSystems.jl:147-150
+//   calcEnergy              -sigma' W tau - h' sigma - b' tau         src/SpinSystems.jl:139-143
+//
+// This is the bit-exact path: every output unit sums its W column sequentially over ascending input
+// index in double (the order of the reference's generic mat-vec and of the CPU test oracle), so the
+// decision quantity 2*(W's + b) - F*T is bit-identical to the Float64 reference for ANY W, not only
+// for integer / dyadic couplings.  The tensor-core path (bip_tc.cu) is the throughput path.
+//
+// Layout: one thread per output unit, CH chains per CTA.  The CH input spin vectors are packed into a
+// shared-memory bit mask per input unit, so one coalesced read of a W row serves CH chains.
+#include "common.cuh"
+#include "handles.hpp"
+
+namespace isb {
+
+constexpr int BIPX_CH = 8;        // chains per CTA
+constexpr int BIPX_THREADS = 128; // output units per CTA
+
+struct BipHalfParams {
+    const double *Wm;    // [nin][ldw]: element (input i, output j) at i*ldw + j
+    int64_t ldw;
+    const double *bias;  // [nout]
+    const int8_t *in;    // [R][ldin]
+    int64_t ldin;
+    int nin;
+    int8_t *out;         // [R][ldout]  (also the unit's own previous value for MomentumAnnealing)
+    int64_t ldout;
+    int nout;
+    int R;
+    int rule;            // ISB_BIP_SCA / ISB_BIP_MA
+    int fluct_mode;
+    const double *F;     // SHARED: [nsteps][nout]; PER_REPLICA: [R][nsteps][nout]
+    int64_t nsteps, k;   // step index within this run
+    const double *Tsched;
+    int64_t steps_per_T;
+    uint64_t seed, step_abs;  // Philox: absolute step = step_offset + k
+    uint32_t domain;
+    double *field_out;   // FIELD mode: [R][ldf]
+    int64_t ldf;
+};
+
+template <bool FIELD>
+__global__ void __launch_bounds__(BIPX_THREADS) bip_half_kernel(const BipHalfParams p) {
+    extern __shared__ unsigned char smask[];  // [nin] bit c = spin of chain c is +1
+    const int r0 = blockIdx.y * BIPX_CH;
+    const int nch = min(BIPX_CH, p.R - r0);
+    for (int i = threadIdx.x; i < p.nin; i += blockDim.x) {
+        unsigned m = 0;
+        for (int c = 0; c < nch; ++c) m |= (p.in[(int64_t)(r0 + c) * p.ldin + i] > 0 ? 1u : 0u) << c;
+        smask[i] = (unsigned char)m;
+    }
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.nout) return;
+    double acc[BIPX_CH];
+#pragma unroll
+    for (int c = 0; c < BIPX_CH; ++c) acc[c] = 0.0;
+    const double *wp = p.Wm + j;
+    for (int i = 0; i < p.nin; ++i) {
+        const double w = __ldg(wp + (int64_t)i * p.ldw);
+        const unsigned m = smask[i];
+#pragma unroll
+        for (int c = 0; c < BIPX_CH; ++c) acc[c] = __dadd_rn(acc[c], ((m >> c) & 1u) ? w : -w);
+    }
+    const double bj = p.bias[j];
+    if constexpr (FIELD) {
+        for (int c = 0; c < nch; ++c) p.field_out[(int64_t)(r0 + c) * p.ldf + j] = __dadd_rn(acc[c], bj);
+        return;
+    }
+    const double T = p.Tsched[p.k / p.steps_per_T];
+    for (int c = 0; c < nch; ++c) {
+        const int r = r0 + c;
+        double f;
+        if (p.fluct_mode == ISB_FLUCT_PHILOX) {
+            const Philox4 blk = philox_unit_block(p.seed, p.domain, (uint32_t)r, p.step_abs, (uint32_t)(j >> 2));
+            const uint32_t w = philox_pick(blk, (uint32_t)(j & 3));
+            f = p.rule == ISB_BIP_SCA ? logistic_from_word(w) : exponential_from_word(w);
+        } else if (p.fluct_mode == ISB_FLUCT_SHARED) {
+            f = p.F[p.k * p.nout + j];
+        } else {
+            f = p.F[((int64_t)r * p.nsteps + p.k) * p.nout + j];
+        }
+        int8_t *o = p.out + (int64_t)r * p.ldout + j;
+        double ft = __dmul_rn(f, T);
+        if (p.rule == ISB_BIP_MA) ft = __dmul_rn(ft, (double)*o);
+        const double x = __dsub_rn(__dmul_rn(2.0, __dadd_rn(acc[c], bj)), ft);
+        *o = (x < 0.0) ? (int8_t)-1 : (int8_t)1;  // heaviside(0) = 1, src/SpinSystems.jl:163-171
+    }
+}
+
+// E_r = -sum_i sigma_i (sum_j W_ij tau_j) - sum_i h_i sigma_i - sum_j b_j tau_j ; one CTA per chain.
+__global__ void bip_energy_kernel(const double *__restrict__ Wt /*[nh][nv]*/, const double *__restrict__ h,
+                                  const double *__restrict__ b, const int8_t *sig, int64_t lds, const int8_t *tau,
+                                  int64_t ldh, int nv, int nh, double *E) {
+    extern __shared__ int8_t tsh[];  // [nh]
+    __shared__ double red[32];
+    const int r = blockIdx.x;
+    for (int j = threadIdx.x; j < nh; j += blockDim.x) tsh[j] = tau[(int64_t)r * ldh + j];
+    __syncthreads();
+    double part = 0.0;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        double row = 0.0;
+        for (int j = 0; j < nh; ++j) row += Wt[(int64_t)j * nv + i] * (double)tsh[j];
+        const double si = (double)sig[(int64_t)r * lds + i];
+        part -= si * row + h[i] * si;
+    }
+    for (int j = threadIdx.x; j < nh; j += blockDim.x) part -= b[j] * (double)tsh[j];
+    part = warp_sum(part);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) red[w] = part;
+    __syncthreads();
+    if (w == 0) {
+        const int nwarp = blockDim.x >> 5;
+        part = lane < nwarp ? red[lane] : 0.0;
+        part = warp_sum(part);
+        if (lane == 0) E[r] = part;
+    }
+}
+
+__global__ void philox_bip_fluct_kernel(int rule, uint64_t seed, uint64_t step_offset, uint32_t domain, int nunits,
+                                        int r0, int nr, int64_t nsteps, double *out) {
+    const int64_t total = (int64_t)nr * nsteps * nunits;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % nunits);
+        const int64_t k = (idx / nunits) % nsteps;
+        const int rr = (int)(idx / ((int64_t)nunits * nsteps));
+        const Philox4 blk =
+            philox_unit_block(seed, domain, (uint32_t)(r0 + rr), step_offset + (uint64_t)k, (uint32_t)(j >> 2));
+        const uint32_t w = philox_pick(blk, (uint32_t)(j & 3));
+        out[idx] = rule == ISB_BIP_SCA ? logistic_from_word(w) : exponential_from_word(w);
+    }
+}
+
+int philox_bip_fluct_device(isb_ctx *ctx, int rule, uint64_t seed, uint64_t step_offset, int layer, int nunits,
+                            int r0, int nr, int64_t nsteps, double *d_out) {
+    const int64_t total = (int64_t)nr * nsteps * nunits;
+    if (total == 0) return ISB_OK;
+    const int64_t g = (total + 255) / 256;
+    philox_bip_fluct_kernel<<<(int)(g < 148 * 16 ? g : 148 * 16), 256, 0, ctx->stream>>>(
+        rule, seed, step_offset, layer == 0 ? DOM_BIP_VISIBLE : DOM_BIP_HIDDEN, nunits, r0, nr, nsteps, d_out);
+    ISB_CUDA(ctx, cudaGetLastError());
+    return ISB_OK;
+}
+
+int bip_energy_device(isb_ens *e, double *d_E) {
+    isb_model *m = e->model;
+    bip_energy_kernel<<<e->R, 256, m->nh, m->ctx->stream>>>(m->Wt64, m->hb64, m->bb64, e->spins, e->lds, e->hidden,
+                                                            e->ldh, m->nv, m->nh, d_E);
+    ISB_CUDA(m->ctx, cudaGetLastError());
+    return ISB_OK;
+}
+
+static void fill_half(BipHalfParams &p, isb_ens *e, int layer) {
+    isb_model *m = e->model;
+    if (layer == 1) {  // hidden from visible: sum_i W[i][j] sigma_i + b_j
+        p.Wm = m->W64; p.ldw = m->nh; p.bias = m->bb64;
+        p.in = e->spins; p.ldin = e->lds; p.nin = m->nv;
+        p.out = e->hidden; p.ldout = e->ldh; p.nout = m->nh;
+        p.domain = DOM_BIP_HIDDEN;
+    } else {           // visible from hidden: sum_j W[i][j] tau_j + h_i
+        p.Wm = m->Wt64; p.ldw = m->nv; p.bias = m->hb64;
+        p.in = e->hidden; p.ldin = e->ldh; p.nin = m->nh;
+        p.out = e->spins; p.ldout = e->lds; p.nout = m->nv;
+        p.domain = DOM_BIP_VISIBLE;
+    }
+    p.R = e->R;
+}
+
+int bip_field_device(isb_ens *e, int layer, double *d_out, int64_t ld) {
+    isb_model *m = e->model;
+    BipHalfParams p{};
+    fill_half(p, e, layer);
+    p.field_out = d_out;
+    p.ldf = ld;
+    dim3 grid((p.nout + BIPX_THREADS - 1) / BIPX_THREADS, (e->R + BIPX_CH - 1) / BIPX_CH);
+    bip_half_kernel<true><<<grid, BIPX_THREADS, p.nin, m->ctx->stream>>>(p);
+    ISB_CUDA(m->ctx, cudaGetLastError());
+    return ISB_OK;
+}
+
+int bip_run_exact_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv,
+                         const double *d_Fh, uint64_t seed, uint64_t step_offset, const double *d_T,
+                         int64_t steps_per_T, int64_t trace_every, double *d_E) {
+    isb_model *m = e->model;
+    isb_ctx *ctx = m->ctx;
+    int64_t ntr = 0;
+    for (int64_t k = 0; k < nsteps; ++k) {
+        for (int layer = 1; layer >= 0; --layer) {  // hidden first (from the OLD visible), then visible
+            BipHalfParams p{};
+            fill_half(p, e, layer);
+            p.rule = rule;
+            p.fluct_mode = fluct_mode;
+            p.F = layer == 1 ? d_Fh : d_Fv;
+            p.nsteps = nsteps;
+            p.k = k;
+            p.Tsched = d_T;
+            p.steps_per_T = steps_per_T;
+            p.seed = seed;
+            p.step_abs = step_offset + (uint64_t)k;
+            dim3 grid((p.nout + BIPX_THREADS - 1) / BIPX_THREADS, (e->R + BIPX_CH - 1) / BIPX_CH);
+            bip_half_kernel<false><<<grid, BIPX_THREADS, p.nin, ctx->stream>>>(p);
+            ISB_CUDA(ctx, cudaGetLastError());
+            e->last_launches += 1;
+        }
+        if (d_E && trace_every > 0 && (k + 1) % trace_every == 0) {
+            int rc = bip_energy_device(e, d_E + ntr * e->R);
+            if (rc) return rc;
+            e->last_launches += 1;
+            ++ntr;
+        }
+    }
+    return ISB_OK;
+}
+
+}  // namespace isb

@@ -1,0 +1,139 @@
+// common.cuh — device helpers shared by the sm_100a kernels of libising_b200.so:
+// mbarrier / bulk-copy (TMA) PTX wrappers, warp reductions, Philox4x32-10 and the
+// uniform -> fluctuation transforms that replace Distributions.jl's samplers
+// (reference call sites: src/SamplingHelper.jl:24,40,105-106,121-122).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace isb {
+
+// ------------------------------------------------------------------ mbarrier + bulk async copy
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    // make the initialised barriers visible to the async (TMA) proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (context error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ------------------------------------------------------------------ warp helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------ Philox4x32-10
+// Salmon, Moraes, Dror, Shaw, SC'11.  Checked word for word against oracle/ (tests/test_philox.py).
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+__host__ __device__ __forceinline__ uint32_t philox_pick(const Philox4 &p, uint32_t w) {
+    return w == 0 ? p.x : (w == 1 ? p.y : (w == 2 ? p.z : p.w));
+}
+
+// Stream domains (top 4 bits of counter word 3).
+enum : uint32_t { DOM_SSF_FLUCT = 1, DOM_SSF_NODES = 2, DOM_BIP_VISIBLE = 3, DOM_BIP_HIDDEN = 4 };
+
+// Word assigned to step `step` of replica `replica` in a single-spin run:
+// counter = (lo(step>>2), hi(step>>2), replica, domain<<28), key = seed, word = step & 3.
+__host__ __device__ __forceinline__ uint32_t philox_step_word(uint64_t seed, uint32_t domain, uint32_t replica,
+                                                              uint64_t step) {
+    const uint64_t q = step >> 2;
+    const Philox4 p = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), replica, domain << 28, (uint32_t)seed,
+                                    (uint32_t)(seed >> 32));
+    return philox_pick(p, (uint32_t)(step & 3));
+}
+// Block of 4 words for units 4*uq .. 4*uq+3 of one layer at step `step` of replica `replica`
+// (bipartite runs): counter = (lo(step), hi(step), replica, domain<<28 | uq).
+__host__ __device__ __forceinline__ Philox4 philox_unit_block(uint64_t seed, uint32_t domain, uint32_t replica,
+                                                              uint64_t step, uint32_t uq) {
+    return philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), replica, (domain << 28) | uq, (uint32_t)seed,
+                         (uint32_t)(seed >> 32));
+}
+
+// u in (0,1): (w + 1/2) 2^-32 — exactly representable, never 0 or 1.
+__device__ __forceinline__ double u_from_word(uint32_t w) {
+    return __dmul_rn(__dadd_rn((double)w, 0.5), 2.3283064365386962890625e-10);
+}
+// Logistic(0,1) by inversion: log(u / (1-u))   (GlauberDynamics / SCA: SingleSpinFlip.jl:43, OnBipartiteGraph.jl:15)
+__device__ __forceinline__ double logistic_from_word(uint32_t w) {
+    const double u = u_from_word(w);
+    return log(__ddiv_rn(u, __dsub_rn(1.0, u)));
+}
+// Exponential(1) by inversion: -log(u)         (MetropolisMethod / MomentumAnnealing: SingleSpinFlip.jl:62, OnBipartiteGraph.jl:50)
+__device__ __forceinline__ double exponential_from_word(uint32_t w) { return -log(u_from_word(w)); }
+
+// fluctuation of a rule from a word: rule ids follow ising_b200.h (0 Hopfield, 1 Glauber, 2 Metropolis)
+__device__ __forceinline__ double ssf_fluct_from_word(int rule, uint32_t w) {
+    return rule == 1 ? logistic_from_word(w) : (rule == 2 ? exponential_from_word(w) : 0.0);
+}
+
+// Uniform site in [0, n): high half of w * n (SamplingHelper.jl:23,39 draw rand(rng, 1:N)).
+__host__ __device__ __forceinline__ int32_t node_from_word(uint32_t w, int n) {
+    return (int32_t)(((uint64_t)w * (uint64_t)(uint32_t)n) >> 32);
+}
+
+}  // namespace isb

@@ -1,0 +1,116 @@
+// handles.hpp — host-side objects behind the opaque handles of include/ising_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/ising_b200.h"
+
+struct isb_devbuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct isb_ctx {
+    int device = 0;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    isb_devbuf scratch[12];      // grow-only device staging buffers (see isb::dev_reserve)
+};
+
+enum { ISB_KIND_DENSE = 0, ISB_KIND_BIPARTITE = 1 };
+
+struct isb_model {
+    isb_ctx *ctx = nullptr;
+    int kind = ISB_KIND_DENSE;
+    int prec = ISB_PREC_F64;
+    // ---- dense: N sites, padded to Npad = 32*NPL (NPL a power of two) for the sweep kernel
+    int n = 0, npad = 0, npl = 0;
+    bool fast_ok = false;        // N <= 1024: register-resident sweep kernel applies
+    bool j_is_f32 = false;       // storage type of the permuted copy used by the sweep kernel
+    double *J64 = nullptr;       // natural layout [npad][npad] (row i contiguous; symmetric)
+    void *Jperm = nullptr;       // permuted columns, double or float, [npad][npad]
+    double *h64 = nullptr;       // [npad]
+    // ---- bipartite: nv visible, nh hidden
+    int nv = 0, nh = 0;
+    double *W64 = nullptr;       // [nv][nh]  (row i = visible unit i; contiguous over hidden)
+    double *Wt64 = nullptr;      // [nh][nv]
+    double *hb64 = nullptr;      // visible bias [nv]
+    double *bb64 = nullptr;      // hidden bias  [nh]
+    // tensor-core operands (bf16 split terms, K-major, padded) — filled by bip_tc.cu when prec is BF16X*
+    void *tc = nullptr;
+};
+
+struct isb_ens {
+    isb_model *model = nullptr;
+    int R = 0;
+    int8_t *spins = nullptr;     // [R][npad]   (dense)  or  [R][nvpad] (bipartite visible)
+    int8_t *hidden = nullptr;    // [R][nhpad]
+    int64_t lds = 0, ldh = 0;    // row strides of the two arrays (bytes == elements)
+    void *fields = nullptr;      // cached local fields [R][npad], double or float
+    int fields_rule_sign = 0;    // 0 = invalid, +1 = J s + h (Glauber/Metropolis), -1 = J s - h (Hopfield)
+    unsigned long long *d_flips = nullptr;   // [R]
+    unsigned long long *d_counters = nullptr; // [0] near ties
+    double tie_eps = 0.0;
+    // last-run statistics
+    double last_ms = 0.0;
+    int64_t last_launches = 0, last_h2d = 0, last_d2h = 0, last_flips = 0, last_near_ties = 0;
+    void *tc = nullptr;          // tensor-core path state (bf16 spin matrices), owned by bip_tc.cu
+};
+
+namespace isb {
+
+int fail(isb_ctx *ctx, int code, const char *fmt, ...);
+// Grow-only device scratch buffer `slot` of the context, at least `bytes` long.
+int dev_reserve(isb_ctx *ctx, int slot, size_t bytes, void **out);
+enum { SCR_NODES = 0, SCR_FLUCT = 1, SCR_T = 2, SCR_E = 3, SCR_M = 4, SCR_FLUCT2 = 5, SCR_OUT = 6, SCR_TMP = 7,
+       SCR_TC0 = 8, SCR_TC1 = 9 };
+
+#define ISB_CUDA(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return isb::fail((ctx), ISB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                                \
+    } while (0)
+
+// ssf.cu
+int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *d_nodes, int start,
+                   int fluct_mode, const double *d_fluct, uint64_t seed, uint64_t step_offset,
+                   const double *d_T, int64_t steps_per_T, int64_t trace_every, double *d_E, double *d_M);
+int ssf_ensure_fields(isb_ens *e, int sign);
+size_t ssf_field_elem_size(const isb_model *m);
+int philox_fluct_device(isb_ctx *ctx, int rule, uint64_t seed, uint64_t step_offset, int r0, int nr,
+                        int64_t nsteps, double *d_out);
+int philox_nodes_device(isb_ctx *ctx, int n, uint64_t seed, uint64_t step_offset, int64_t nsteps,
+                        int32_t *d_out);
+int philox_raw_device(isb_ctx *ctx, const uint32_t *d_ctr, uint32_t k0, uint32_t k1, int nblocks,
+                      uint32_t *d_out);
+int dense_energy_device(isb_ens *e, double *d_E);
+int dense_field_device(isb_ens *e, double *d_F, int64_t ld);  // natural J s + h in double
+int magnetization_device(isb_ens *e, double *d_M);
+
+// bip_exact.cu
+int bip_run_exact_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv,
+                         const double *d_Fh, uint64_t seed, uint64_t step_offset, const double *d_T,
+                         int64_t steps_per_T, int64_t trace_every, double *d_E);
+int bip_energy_device(isb_ens *e, double *d_E);
+int bip_field_device(isb_ens *e, int layer, double *d_out, int64_t ld);  // layer 0: W tau + h, 1: W' sigma + b
+int philox_bip_fluct_device(isb_ctx *ctx, int rule, uint64_t seed, uint64_t step_offset, int layer,
+                            int nunits, int r0, int nr, int64_t nsteps, double *d_out);
+
+// bip_tc.cu (tcgen05 path)
+int bip_tc_model_init(isb_model *m, const double *W_host_rowmajor_vh);
+void bip_tc_model_free(isb_model *m);
+int bip_tc_ens_init(isb_ens *e);
+void bip_tc_ens_free(isb_ens *e);
+int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv,
+                      const double *d_Fh, uint64_t seed, uint64_t step_offset, const double *d_T,
+                      int64_t steps_per_T, int64_t trace_every, double *d_E);
+
+}  // namespace isb

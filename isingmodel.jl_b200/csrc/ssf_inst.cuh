@@ -1,0 +1,35 @@
+// ssf_inst.cuh — instantiates ssf_kernel for one (field type, coupling type) pair; included by
+// ssf_inst_dd.cu / ssf_inst_df.cu / ssf_inst_ff.cu so the three pairs compile in parallel.
+#pragma once
+#include "ssf_kernel.cuh"
+
+namespace isb {
+
+template <typename HT, typename JT, int NPL>
+static cudaError_t launch_one(const SsfParams &p, bool list, bool tma, int grid, int threads, size_t smem,
+                              cudaStream_t st) {
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, threads, smem, st>>>(p);
+        return cudaGetLastError();
+    };
+    if (list) return tma ? go(ssf_kernel<HT, JT, NPL, true, true>) : go(ssf_kernel<HT, JT, NPL, true, false>);
+    return tma ? go(ssf_kernel<HT, JT, NPL, false, true>) : go(ssf_kernel<HT, JT, NPL, false, false>);
+}
+
+template <typename HT, typename JT>
+static cudaError_t launch_pair(const SsfParams &p, int npl, bool list, bool tma, int grid, int threads,
+                               size_t smem, cudaStream_t st) {
+    switch (npl) {
+        case 1: return launch_one<HT, JT, 1>(p, list, tma, grid, threads, smem, st);
+        case 2: return launch_one<HT, JT, 2>(p, list, tma, grid, threads, smem, st);
+        case 4: return launch_one<HT, JT, 4>(p, list, tma, grid, threads, smem, st);
+        case 8: return launch_one<HT, JT, 8>(p, list, tma, grid, threads, smem, st);
+        case 16: return launch_one<HT, JT, 16>(p, list, tma, grid, threads, smem, st);
+        case 32: return launch_one<HT, JT, 32>(p, list, tma, grid, threads, smem, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace isb

@@ -1,0 +1,304 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(include/ising_b200.h via ctypes), against the CPU oracle on the same seeded inputs.
+
+Bar: spin trajectories, flip counts and magnetisations BIT-EXACT; energies within 1e-9 relative (the
+energy is a different summation order of the same Float64 quantities; north_star allows 1e-5)."""
+import numpy as np
+import pytest
+
+from cases import BIP_GOLDEN, SSF_GOLDEN, golden_J, golden_W, nodes_of
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+E_RTOL = 1e-9
+
+
+def _close(a, b):
+    scale = np.maximum(1.0, np.abs(b))
+    return np.all(np.abs(a - b) <= E_RTOL * scale)
+
+
+def _lib():
+    from isingmodel_jl_b200 import _lib
+    return _lib
+
+
+# ---------------------------------------------------------------- Philox
+def test_philox_raw_matches_oracle_and_kat(ctx, orc):
+    kat_ctr = np.array([[0, 0, 0, 0], [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]], dtype=np.uint32)
+    got = ctx.philox_raw(kat_ctr[1:], np.array([0xa4093822, 0x299f31d0], dtype=np.uint32))
+    assert got[0].tolist() == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    rng = np.random.default_rng(0)
+    ctrs = rng.integers(0, 2 ** 32, (257, 4), dtype=np.uint64).astype(np.uint32)
+    key = rng.integers(0, 2 ** 32, 2, dtype=np.uint64).astype(np.uint32)
+    got = ctx.philox_raw(ctrs, key)
+    want = np.array([orc.philox4x32_10(c, key) for c in ctrs])
+    assert np.array_equal(got, want)
+
+
+def test_philox_streams(ctx):
+    from oracle import oracle_np
+    L = _lib()
+    seed, off = 0x1234567890ABCDEF, 5
+    fl = ctx.philox_fluct(L.RULE_GLAUBER, seed, off, 3, 2, 64)
+    steps = np.arange(64, dtype=np.uint64) + np.uint64(off)
+    for i, r in enumerate((3, 4)):
+        w = oracle_np.philox_word(seed, 1 << 28, r, steps)
+        u = oracle_np.uniform_from_word(w)
+        assert np.allclose(fl[i], np.log(u / (1 - u)), rtol=1e-14, atol=1e-15)
+    fe = ctx.philox_fluct(L.RULE_METROPOLIS, seed, off, 0, 1, 64)
+    u = oracle_np.uniform_from_word(oracle_np.philox_word(seed, 1 << 28, 0, steps))
+    assert np.allclose(fe[0], -np.log(u), rtol=1e-14)
+    nd = ctx.philox_nodes(1000, seed, off, 64)
+    w = oracle_np.philox_word(seed, 2 << 28, 0, steps)
+    assert np.array_equal(nd, ((w.astype(np.uint64) * np.uint64(1000)) >> np.uint64(32)).astype(np.int32))
+
+
+# ---------------------------------------------------------------- golden files, R = 1 (the reference's one chain)
+@pytest.mark.parametrize("name", SSF_GOLDEN)
+def test_ssf_golden(ctx, synth, name):
+    L = _lib()
+    g = load_golden(name)
+    J = golden_J(name, g, synth)
+    m = L.Model.dense(ctx, J, g["h"], L.PREC_AUTO)
+    e = L.Ensemble(m, 1)
+    e.set_spins(g["s0"][None, :])
+    out = e.ssf_run(int(g["rule"]), int(g["nsteps"]), nodes=nodes_of(g), fluct=g["fluct"], T=g["T"],
+                    steps_per_T=int(g["steps_per_T"]), trace_every=int(g["trace_every"]))
+    assert np.array_equal(e.get_spins()[0], g["s_final"])
+    assert int(out["flips"][0]) == int(g["flips"])
+    assert np.array_equal(out["M"][:, 0], g["M"])
+    assert _close(out["E"][:, 0], g["E"])
+    assert _close(e.energy()[0], g["E"][-1])
+
+
+@pytest.mark.parametrize("name", BIP_GOLDEN)
+def test_bip_golden(ctx, synth, name):
+    L = _lib()
+    g = load_golden(name)
+    W = golden_W(name, g, synth)
+    m = L.Model.bipartite(ctx, W, g["h"], g["b"], L.PREC_F64)
+    e = L.Ensemble(m, 1)
+    e.set_spins(g["s0"][None, :])
+    e.set_hidden(g["t0"][None, :])
+    E = e.bip_run(int(g["rule"]), int(g["nsteps"]), Fv=g["Fv"], Fh=g["Fh"], T=g["T"], trace_every=1)
+    assert np.array_equal(e.get_spins()[0], g["s_final"])
+    assert np.array_equal(e.get_hidden()[0], g["t_final"])
+    assert _close(E[:, 0], g["E"])
+
+
+# ---------------------------------------------------------------- replica-batched sweeps vs the oracle
+SSF_CASES = [
+    # (N, kind, rule, order, prec, R, nsteps, per_replica)
+    (1, "sk", 1, "seq", "f64", 3, 7, True),
+    (2, "sk", 2, "list", "f64", 3, 50, True),
+    (31, "sk", 1, "seq", "f64", 5, 31 * 9 + 4, True),
+    (32, "sk", 2, "list", "f64", 33, 700, True),
+    (33, "sk", 1, "seq", "f64", 29, 33 * 7, False),
+    (100, "sk", 2, "seq", "f64", 40, 100 * 6 + 17, True),
+    (100, "sk", 0, "list", "f64", 4, 500, False),
+    (256, "lattice", 2, "seq", "auto", 64, 256 * 8, True),
+    (256, "lattice", 1, "list", "auto", 7, 3000, True),
+    (500, "sk", 1, "seq", "f64", 200, 500 * 3, True),
+    (1000, "sk", 2, "seq", "f64", 31, 1000 * 2 + 3, True),
+    (1024, "sk", 1, "seq", "f64", 300, 1024 * 3, True),
+    (1024, "lattice", 2, "seq", "auto", 300, 1024 * 4, True),
+    (1024, "sk", 1, "list", "f64", 15, 4000, True),
+    (1024, "sk", 0, "seq", "f64", 9, 2048, False),
+]
+
+
+def _ssf_inputs(synth, N, kind, rule, order, R, nsteps, per_replica, seed=1):
+    if kind == "lattice":
+        Lside = int(round(np.sqrt(N)))
+        J = synth.lattice_J(Lside)
+        h = np.zeros(N)
+    else:
+        J = synth.sk_J(N, seed + N)
+        h = synth.gaussian(seed + 1, N) * 0.2
+    S0 = synth.spins(seed + 2, R, N)
+    nodes = synth.nodes(seed + 3, N, nsteps) if order == "list" else None
+    shape = (R, nsteps) if per_replica else (nsteps,)
+    fl = synth.logistic(seed + 4, shape) if rule == 1 else (synth.exponential(seed + 4, shape) if rule == 2 else None)
+    nT = 7
+    spT = (nsteps + nT - 1) // nT
+    T = synth.geometric_schedule(2.5, 0.3, nT)
+    return J, h, S0, nodes, fl, T, spT
+
+
+@pytest.mark.parametrize("N,kind,rule,order,prec,R,nsteps,per_replica", SSF_CASES)
+def test_ssf_batched_bit_exact(ctx, orc, synth, N, kind, rule, order, prec, R, nsteps, per_replica):
+    L = _lib()
+    J, h, S0, nodes, fl, T, spT = _ssf_inputs(synth, N, kind, rule, order, R, nsteps, per_replica)
+    m = L.Model.dense(ctx, J, h, L.PREC_AUTO if prec == "auto" else L.PREC_F64)
+    e = L.Ensemble(m, R)
+    e.set_spins(S0)
+    e.set_tie_eps(1e-12)
+    tr = max(1, nsteps // 3)
+    out = e.ssf_run(rule, nsteps, nodes=nodes, start=(N // 3) if order == "seq" else 0, fluct=fl,
+                    fluct_per_replica=per_replica, T=T, steps_per_T=spT, trace_every=tr)
+    S = e.get_spins()
+    stats = e.last_stats()
+    mism = 0
+    for r in range(R):
+        f = None if fl is None else (fl[r] if per_replica else fl)
+        s, flips, E, M = orc.ssf_run(rule, J, h, S0[r], nsteps, nodes=nodes, start=(N // 3) if order == "seq" else 0,
+                                     fluct=f, T=T, steps_per_T=spT, trace_every=tr)
+        if not np.array_equal(s, S[r]):
+            mism += 1
+            continue
+        assert flips == out["flips"][r]
+        assert np.array_equal(M, out["M"][:, r])
+        assert _close(out["E"][:, r], E)
+    # Gaussian J: the incrementally maintained Float64 field differs from the oracle's fresh row sum by a few
+    # ulp, so a decision can differ only where |2h - fT| is below ~1e-13; the kernel counts those (near-tie audit).
+    assert mism == 0 or stats["near_ties"] > 0, f"{mism} replicas differ without any near tie"
+    assert mism == 0
+    assert stats["flips"] == int(out["flips"].sum())
+    assert _close(e.energy(), np.array([orc.energy(J, h, S[r]) for r in range(R)]))
+    assert np.array_equal(e.magnetization(), S.sum(1).astype(np.float64))
+
+
+def test_ssf_continuation_and_field_cache(ctx, orc, synth):
+    """Two runs back to back == one run (cached local fields stay valid); set_spins invalidates them."""
+    L = _lib()
+    N, R, n1, n2 = 200, 10, 500, 700
+    J, h, S0, _, fl, _, _ = _ssf_inputs(synth, N, "sk", 1, "seq", R, n1 + n2, True)
+    T = synth.geometric_schedule(2.0, 0.2, n1 + n2)  # one temperature per step
+    m = L.Model.dense(ctx, J, h, L.PREC_F64)
+    e = L.Ensemble(m, R)
+    e.set_spins(S0)
+    e.ssf_run(1, n1, fluct=fl[:, :n1].copy(), fluct_per_replica=True, T=T[:n1])
+    S_mid = e.get_spins()
+    e.ssf_run(1, n2, start=n1 % N, fluct=fl[:, n1:].copy(), fluct_per_replica=True, T=T[n1:])
+    S_end = e.get_spins()
+    for r in range(R):
+        s, *_ = orc.ssf_run(1, J, h, S0[r], n1, fluct=fl[r, :n1], T=T)
+        assert np.array_equal(s, S_mid[r])
+        s, *_ = orc.ssf_run(1, J, h, S0[r], n1 + n2, fluct=fl[r], T=T)
+        assert np.array_equal(s, S_end[r])
+    e.set_spins(S0)  # must drop the cached fields
+    e.ssf_run(1, 300, fluct=fl[:, :300].copy(), fluct_per_replica=True, T=T[:300])
+    S = e.get_spins()
+    for r in range(R):
+        s, *_ = orc.ssf_run(1, J, h, S0[r], 300, fluct=fl[r, :300], T=T)
+        assert np.array_equal(s, S[r])
+
+
+def test_ssf_philox_mode_reproduces_with_dumped_fluctuations(ctx, orc, synth):
+    """ISB_FLUCT_PHILOX: the trajectories equal the oracle's when it is fed the fluctuations the library
+    dumps for the same (seed, offset) — the 'shared uniforms' parity of north_star."""
+    L = _lib()
+    N, R, nsteps, seed, off = 1024, 40, 3 * 1024, 99, 1000
+    J = synth.sk_J(N, 2)
+    h = np.zeros(N)
+    S0 = synth.spins(3, R, N)
+    T = np.array([1.5, 1.0, 0.5])
+    for rule in (L.RULE_GLAUBER, L.RULE_METROPOLIS):
+        m = L.Model.dense(ctx, J, h, L.PREC_F64)
+        e = L.Ensemble(m, R)
+        e.set_spins(S0)
+        e.ssf_run(rule, nsteps, seed=seed, step_offset=off, T=T, steps_per_T=N)
+        S = e.get_spins()
+        fl = ctx.philox_fluct(rule, seed, off, 0, R, nsteps)
+        for r in range(R):
+            s, *_ = orc.ssf_run(rule, J, h, S0[r], nsteps, fluct=fl[r], T=T, steps_per_T=N)
+            assert np.array_equal(s, S[r])
+        # random site order drawn by the library
+        e.set_spins(S0)
+        e.ssf_run(rule, 2000, order=L.ORDER_RANDOM, seed=seed, step_offset=off, T=T, steps_per_T=N)
+        nodes = ctx.philox_nodes(N, seed, off, 2000)
+        S = e.get_spins()
+        for r in range(0, R, 7):
+            s, *_ = orc.ssf_run(rule, J, h, S0[r], 2000, nodes=nodes, fluct=fl[r, :2000], T=T, steps_per_T=N)
+            assert np.array_equal(s, S[r])
+
+
+def test_local_field_bit_exact(ctx, orc, synth):
+    L = _lib()
+    N, R = 300, 6
+    J, h = synth.sk_J(N, 8), synth.gaussian(9, N)
+    S = synth.spins(10, R, N)
+    e = L.Ensemble(L.Model.dense(ctx, J, h, L.PREC_F64), R)
+    e.set_spins(S)
+    F = e.local_field()
+    for r in range(R):
+        assert np.array_equal(F[r], orc.local_field(J, h, S[r]))  # same sequential Float64 row sums
+
+
+# ---------------------------------------------------------------- bipartite, replica-batched
+BIP_CASES = [(2, 3, 0, 5, 6, True), (17, 9, 1, 11, 5, True), (130, 70, 0, 37, 4, False), (784, 512, 0, 19, 3, True),
+             (784, 512, 1, 9, 3, True), (257, 1030, 0, 8, 2, True)]
+
+
+@pytest.mark.parametrize("nv,nh,rule,R,nsteps,per_replica", BIP_CASES)
+def test_bip_batched_bit_exact(ctx, orc, synth, nv, nh, rule, R, nsteps, per_replica):
+    L = _lib()
+    W, h, b = synth.bipartite_W(nv, nh, 21, 0.3)
+    S0, T0 = synth.spins(22, R, nv), synth.spins(23, R, nh)
+    gen = synth.logistic if rule == 0 else synth.exponential
+    shp = (R, nsteps) if per_replica else (nsteps,)
+    Fv, Fh = gen(24, shp + (nv,), 1), gen(24, shp + (nh,), 2)
+    T = synth.geometric_schedule(2.0, 0.2, nsteps)
+    e = L.Ensemble(L.Model.bipartite(ctx, W, h, b, L.PREC_F64), R)
+    e.set_spins(S0)
+    e.set_hidden(T0)
+    E = e.bip_run(rule, nsteps, Fv=Fv, Fh=Fh, fluct_per_replica=per_replica, T=T, trace_every=1)
+    S, Tm = e.get_spins(), e.get_hidden()
+    for r in range(R):
+        s, t, Eo = orc.bip_run(rule, W, h, b, S0[r], T0[r], nsteps, Fv[r] if per_replica else Fv,
+                               Fh[r] if per_replica else Fh, T, want_E=True)
+        assert np.array_equal(s, S[r]) and np.array_equal(t, Tm[r])
+        assert _close(E[:, r], Eo)
+    A, F = e.local_aux_bias(), e.local_field()
+    for r in range(min(R, 3)):
+        assert np.array_equal(A[r], orc.bip_aux_bias(W, b, S[r]))
+        assert np.array_equal(F[r], orc.bip_local_field(W, h, Tm[r]))
+
+
+def test_bip_philox_mode(ctx, orc, synth):
+    L = _lib()
+    nv, nh, R, nsteps, seed, off = 96, 40, 6, 5, 7, 3
+    W, h, b = synth.bipartite_W(nv, nh, 31, 0.3)
+    S0, T0 = synth.spins(32, R, nv), synth.spins(33, R, nh)
+    T = np.full(nsteps, 0.8)
+    for rule in (0, 1):
+        e = L.Ensemble(L.Model.bipartite(ctx, W, h, b, L.PREC_F64), R)
+        e.set_spins(S0)
+        e.set_hidden(T0)
+        e.bip_run(rule, nsteps, seed=seed, step_offset=off, T=T)
+        Fv = ctx.philox_bip_fluct(rule, seed, off, 0, nv, 0, R, nsteps)
+        Fh = ctx.philox_bip_fluct(rule, seed, off, 1, nh, 0, R, nsteps)
+        S, Tm = e.get_spins(), e.get_hidden()
+        for r in range(R):
+            s, t, _ = orc.bip_run(rule, W, h, b, S0[r], T0[r], nsteps, Fv[r], Fh[r], T)
+            assert np.array_equal(s, S[r]) and np.array_equal(t, Tm[r])
+
+
+# ---------------------------------------------------------------- errors cross the ABI as codes
+def test_error_codes(ctx, synth):
+    L = _lib()
+    with pytest.raises(L.IsbError) as ei:
+        L.Model.dense(ctx, np.array([[0.0, np.nan], [np.nan, 0.0]]), np.zeros(2))
+    assert ei.value.code == L.ERR_NONFINITE
+    m = L.Model.dense(ctx, synth.sk_J(8, 1), np.zeros(8))
+    assert m.warn == 0
+    e = L.Ensemble(m, 2)
+    with pytest.raises(L.IsbError) as ei:
+        e.set_spins(np.zeros((2, 8), dtype=np.int8))
+    assert ei.value.code == L.ERR_ARG
+    with pytest.raises(L.IsbError) as ei:
+        e.ssf_run(1, 10, nodes=np.full(10, 8), fluct=np.zeros(10), T=np.ones(10))
+    assert ei.value.code == L.ERR_ARG
+    with pytest.raises(L.IsbError) as ei:
+        e.ssf_run(1, 10, fluct=np.zeros(10), T=np.ones(3))
+    assert ei.value.code == L.ERR_SIZE
+    with pytest.raises(L.IsbError) as ei:
+        e.bip_run(0, 1, T=np.ones(1))
+    assert ei.value.code == L.ERR_STATE
+    A = np.array([[1.0, 2.0, 3.0], [0.0, 5.0, 6.0], [0.0, 0.0, 9.0]])
+    m2 = L.Model.dense(ctx, A, np.zeros(3))
+    assert m2.warn == 3  # symmetrised from the upper triangle + diagonal dropped (SpinSystems.jl:31-38)
+    e2 = L.Ensemble(m2, 1)
+    e2.set_spins(np.array([[1, 1, 1]], dtype=np.int8))
+    assert np.array_equal(e2.local_field()[0], [5.0, 8.0, 9.0])

@@ -1,0 +1,78 @@
+"""The reference's own test file (test/runtests.jl:1-32) re-expressed against the Python mirror of its API,
+running on the GPU through the C ABI."""
+import copy
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def runAnnealer(pkg, updatingAlgorithm):
+    # test/runtests.jl:6-17
+    rng = np.random.default_rng(128)
+    sampler = pkg.SamplingHelper.makeSampler_(updatingAlgorithm, 5, annealingSchedule=lambda n: 10.0 ** (-n), rng=rng)
+    result = None
+    count = 0
+    for result in sampler:
+        count += 1
+    assert count == 6  # n + 1 items (SamplingHelper.jl:44,48)
+    pkg.SamplingHelper.update_(updatingAlgorithm)
+    return result.spinSystem.spinConfiguration.tolist()
+
+
+def test_single_spin_flip(pkg, ctx):
+    import scipy.sparse as sp
+    SS, SSF = pkg.SpinSystems, pkg.SingleSpinFlip
+    ss = SS.SpinSystem([-1, +1], sp.csc_matrix(np.array([[0, 1], [1, 0]])), [0, 0])
+    assert SS.calcEnergy(ss) == 1.0
+    assert runAnnealer(pkg, SSF.AsynchronousHopfieldNetwork(copy.deepcopy(ss))) in ([1, 1], [-1, -1])
+    assert runAnnealer(pkg, SSF.GlauberDynamics(copy.deepcopy(ss), 10.0)) in ([1, 1], [-1, -1])
+    assert runAnnealer(pkg, SSF.MetropolisMethod(copy.deepcopy(ss), 10.0)) in ([1, 1], [-1, -1])
+
+
+def test_on_bipartite_graph(pkg, ctx):
+    import scipy.sparse as sp
+    OBG = pkg.OnBipartiteGraph
+    ss = OBG.SpinSystemOnBipartiteGraph([-1, +1], [-1, +1, -1], sp.csc_matrix(np.ones((2, 3))), [0, 0], [0, 0, 0])
+    assert OBG.calcEnergy(ss) == 0.0
+    assert runAnnealer(pkg, OBG.StochasticCellularAutomata(copy.deepcopy(ss), 10.0)) in ([1, 1], [-1, -1])
+    assert runAnnealer(pkg, OBG.MomentumAnnealing(copy.deepcopy(ss), 10.0)) in ([1, 1], [-1, -1])
+
+
+def test_three_argument_update_matches_oracle(pkg, ctx, orc, synth):
+    """update!(ua, node, fluct) one call at a time (the parity boundary)."""
+    N = 9
+    J = synth.lattice_J(3, -1.0)  # demo.jl 3x3 antiferromagnet
+    s0 = synth.spins(3, 1, N)[0]
+    for cls, rule in ((pkg.SingleSpinFlip.GlauberDynamics, 1), (pkg.SingleSpinFlip.MetropolisMethod, 2)):
+        ua = cls(pkg.SpinSystems.SpinSystem(s0.copy(), J, np.zeros(N)), 1.3)
+        nodes = synth.nodes(5, N, 40)
+        fl = synth.logistic(6, 40) if rule == 1 else synth.exponential(6, 40)
+        s = s0.copy()
+        for k in range(40):
+            pkg.SingleSpinFlip.update_(ua, int(nodes[k]), float(fl[k]))
+            s, *_ = orc.ssf_run(rule, J, np.zeros(N), s, 1, nodes=nodes[k:k + 1], fluct=fl[k:k + 1], T=np.array([1.3]))
+            assert np.array_equal(ua.spinSystem.spinConfiguration, s)
+        assert abs(pkg.SpinSystems.calcEnergy(ua) - orc.energy(J, np.zeros(N), s)) < 1e-12
+        assert pkg.SpinSystems.calcLocalMagneticField(ua, 4) == orc.local_field(J, np.zeros(N), s)[4]
+
+
+def test_multispinflip_embedding(pkg, ctx, orc, synth):
+    """MultiSpinFlip SCA == bipartite SCA on W = (J + qI)/2 (demo.jl:82-90)."""
+    N = 48
+    J, h = synth.sk_J(N, 4), synth.gaussian(5, N) * 0.1
+    s0 = synth.spins(6, 1, N)[0]
+    ua = pkg.MultiSpinFlip.StochasticCellularAutomata(pkg.SpinSystems.SpinSystem(s0, J, h), 0.7)
+    q = ua.pinningParameter
+    assert abs(q - 0.5 * np.linalg.eigvalsh(J)[-1]) < 1e-12
+    Fv, Fh = synth.logistic(7, (6, N), 1), synth.logistic(7, (6, N), 2)
+    s, t = s0.copy(), s0.copy()
+    W = 0.5 * (J + q * np.eye(N))
+    for k in range(6):
+        pkg.MultiSpinFlip.update_(ua, Fv[k], Fh[k])
+        s, t, _ = orc.bip_run(0, W, 0.5 * h, 0.5 * h, s, t, 1, Fv[k:k + 1], Fh[k:k + 1], np.array([0.7]))
+        assert np.array_equal(ua.spinSystem.spinConfiguration, s)
+    Hb = pkg.SpinSystems.calcEnergy(ua.bipartite)
+    sig, tau = ua.bipartite.spinSystem.spinConfiguration, ua.bipartite.spinSystem.hiddenLayer
+    assert abs(Hb - orc.bip_energy(W, 0.5 * h, 0.5 * h, sig, tau)) < 1e-9
