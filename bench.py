@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — spin-updates/s of the IsingModel.jl spin-update hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload at every N (weak scaling, replicas sharded, no data-path collective — SURVEY §8e): BASELINE.json
+configs[1] = "SK dense Gaussian J, N=1024, 4096 replicas, Glauber sweeps with annealing schedule" per GPU.
+One *step* = one full annealing run of --sweeps sequential sweeps (geometric schedule T 2.0 -> 0.05, one
+temperature per sweep) of all 4096 replicas from the same random initial spins = 4096*1024*sweeps updates.
+
+  value     : device-timed (CUDA events on the launching stream, per step, max over ranks), inputs resident in
+              HBM, noise drawn by the in-kernel Philox RNG.
+  e2e       : the same run through the public host API (isingmodel.jl_b200: SpinSystem / GlauberDynamics /
+              SamplingHelper.run_), timed on the host with pinned buffers: H2D of the initial spins and the
+              schedule, the sweeps, D2H of the final spins, energies and flip counts.
+  roofline  : the sweep kernel against the measured HBM bandwidth, algorithmic bytes = (accepted flips) x N x 8 B
+              (incremental-field formulation: a J row is consumed per accepted flip), per-chain
+              accounting.  J rows are staged once per CTA in shared memory and shared by its chains, so the
+              algorithmic rate can exceed what HBM alone could deliver; `traffic` is the DRAM traffic ncu saw.
+  cpu_baseline / --impl reference : the CPU oracle (C restatement of the reference's algorithm: a full
+              Float64 row dot per update; Julia is not installed here), on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_SITES, REPLICAS = 1024, 4096
+T0, TF = 2.0, 0.05
+SEED_J, SEED_S = 2, 3
+METRIC, UNIT = "spin-updates/sec", "updates/s"
+
+
+def workload(sweeps):
+    from isingmodel_jl_b200 import synth
+    J = synth.sk_J(N_SITES, SEED_J)
+    h = np.zeros(N_SITES)
+    T = synth.geometric_schedule(T0, TF, sweeps)
+    return J, h, T
+
+
+def config(args, extra=None):
+    c = {"workload": "C2: Sherrington-Kirkpatrick dense Gaussian J, N=1024, 4096 replicas/GPU, Glauber "
+                     f"sequential sweeps, geometric annealing T {T0}->{TF} over {args.sweeps} sweeps",
+         "n_sites": N_SITES, "replicas_per_gpu": REPLICAS, "sweeps_per_step": args.sweeps,
+         "updates_per_step_per_gpu": N_SITES * REPLICAS * args.sweeps, "sharding": "replicas (no collective)",
+         "l2": "flushed between timed steps (256 MiB write); J (8 MiB) is L2/smem-resident by design"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.t_lo = self.t_hi = None
+
+    def mark(self, lo=None, hi=None):
+        """Bounds (time.time()) of the timed region: only samples taken inside it are reported."""
+        if lo is not None:
+            self.t_lo = lo
+        if hi is not None:
+            self.t_hi = hi
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        inside = [r for t, r in self.rows if (self.t_lo is None or t >= self.t_lo) and (self.t_hi is None or t <= self.t_hi + 0.05)]
+        scope = "timed region"
+        if len(inside) < 3:  # a very short timed region: fall back to every sample under load (warm-up included)
+            inside, scope = [r for _, r in self.rows], "warm-up + timed region"
+        for r in inside:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "scope": scope}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_rate(sweeps_total, seconds_target, threads=None):
+    """Times the CPU oracle (one chain per thread, full Float64 row dot per update) on a bounded sample of
+    the same workload; returns (updates/s, description, threads)."""
+    import oracle
+    from isingmodel_jl_b200 import synth
+    threads = threads or oracle.num_threads()
+    J, h, T = workload(sweeps_total)
+    R = threads
+    S0 = synth.spins(SEED_S, R, N_SITES)
+
+    def run(nsw):
+        nsteps = nsw * N_SITES
+        fl = synth.logistic(5, (R, nsteps))
+        t0 = time.perf_counter()
+        oracle.ssf_run_batch(oracle.GLAUBER, J, h, S0, nsteps, fluct=fl, fluct_per_replica=True, T=T[:nsw],
+                             steps_per_T=N_SITES, nthreads=threads)
+        return time.perf_counter() - t0, nsteps * R
+
+    dt, n = run(2)  # calibration (also warms the caches)
+    nsw = int(max(2, min(sweeps_total, round(2 * seconds_target / max(dt, 1e-6)))))
+    reps = int(max(1, round(seconds_target / max(dt * nsw / 2, 1e-6))))
+    dt, n = 0.0, 0
+    for _ in range(reps):
+        d, m = run(nsw)
+        dt, n = dt + d, n + m
+    return n / dt, (f"{R} chains (one per thread) x first {nsw} sweeps of the C2 schedule x {reps} repeats "
+                    f"({n} updates, {dt:.1f} s wall)"), threads
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    rates = []
+    desc, threads = "", 1
+    for i in range(args.warmup + args.steps):
+        rate, desc, threads = cpu_oracle_rate(args.sweeps, args.ref_seconds)
+        if i >= args.warmup:
+            rates.append(rate)
+    v = float(np.mean(rates))
+    upd = N_SITES * REPLICAS * args.sweeps
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * upd / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config(args, {"note": "CPU restatement of the reference algorithm (Julia unavailable); "
+                                            "ms_per_step extrapolated from the bounded sample"}),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sweeps", type=int, default=1000, help="annealing sweeps per step (SURVEY §8d C2: 1000)")
+    ap.add_argument("--ref-seconds", type=float, default=8.0, help="CPU seconds per reference-arm step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU seconds of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prec", default="f64", choices=["f64", "f32"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import isingmodel_jl_b200 as pkg
+    from isingmodel_jl_b200 import _lib, synth, sharding, SpinSystems, SingleSpinFlip, SamplingHelper
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = _lib.context(local)
+    ctx.set_stream(stream.cuda_stream)
+
+    sweeps = args.sweeps
+    nsteps = sweeps * N_SITES
+    J, h, T = workload(sweeps)
+    prec = _lib.PREC_F64 if args.prec == "f64" else _lib.PREC_F32
+    bJ = 8 if args.prec == "f64" else 4
+    # this rank's replicas: global replica ids [rank*R, (rank+1)*R) -> distinct initial spins and noise streams
+    S0 = synth.spins(SEED_S + 1000 * rank, REPLICAS, N_SITES)
+    pin = torch.empty((REPLICAS, N_SITES), dtype=torch.int8).pin_memory()
+    S0p = pin.numpy()
+    S0p[:] = S0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    # ---- public-API objects (also used for the device-resident arm: same ensemble)
+    ss = SpinSystems.SpinSystem(S0p, J, h, device=local, prec=prec)
+    ua = SingleSpinFlip.GlauberDynamics(ss, T0)
+    ens = ss._ensemble()
+
+    def device_step(k):
+        ens.set_spins(S0p)                      # untimed reset to the initial configuration
+        flush.zero_()                           # L2 flush
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ens.ssf_run(_lib.RULE_GLAUBER, nsteps, order=_lib.ORDER_SEQUENTIAL, seed=12345 + rank, step_offset=k * nsteps,
+                    T=T, steps_per_T=N_SITES)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        st = ens.last_stats()
+        return e0.elapsed_time(e1), st
+
+    def e2e_step(k):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ss.spinConfiguration = S0p              # H2D (pinned)
+        out = SamplingHelper.run_(ua, nsteps, order="sequential", seed=12345 + rank, step_offset=k * nsteps,
+                                  temperatures=T, steps_per_T=N_SITES)
+        st = ens.last_stats()
+        S = ss.spinConfiguration                # D2H
+        E = SpinSystems.calcEnergy(ua)          # D2H
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        h2d = S0p.nbytes + st["h2d_bytes"]
+        d2h = S.nbytes + E.nbytes + st["d2h_bytes"]
+        return dt, h2d, d2h, float(E.mean()), int(out["flips"].sum())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for k in range(args.warmup):
+        device_step(k)
+    barrier()
+    sampler.mark(lo=time.time())
+    ms, kms, flips, launches = [], [], [], 0
+    for k in range(args.steps):
+        m, st = device_step(args.warmup + k)
+        ms.append(m)
+        kms.append(st["kernel_ms"])
+        flips.append(st["flips"])
+        launches += st["launches"]
+    barrier()
+    sampler.mark(hi=time.time())
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = sharding.max_over_ranks(sum(ms) / 1e3)
+
+    for k in range(min(args.warmup, 1)):
+        e2e_step(k)
+    barrier()
+    e2e_t, h2d, d2h, Emean, fl2 = 0.0, 0, 0, 0.0, 0
+    for k in range(args.steps):
+        dt, h2d, d2h, Emean, fl2 = e2e_step(args.warmup + k)
+        e2e_t += dt
+    barrier()
+    t_e2e = sharding.max_over_ranks(e2e_t)
+
+    upd_step = N_SITES * REPLICAS * sweeps
+    total_updates = upd_step * args.steps * world
+    value = total_updates / t_dev
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+        kern_s = float(np.mean(kms)) / 1e3
+        alg_bytes = float(np.mean(flips)) * N_SITES * bJ
+        achieved = alg_bytes / kern_s / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("ssf_kernel_dram_bytes_per_launch")
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        smem_peak = 128.0 * 148 * sm_mhz * 1e6 / 1e9  # GB/s: 128 B/clk/SM
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.prec, "data": "synthetic",
+            "config": config(args),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "isb::ssf_kernel",
+                         "kernel_ms": 1e3 * kern_s,
+                         "accounting": f"accepted flips ({np.mean(flips):.4g}/launch) x N x {bJ} B per launch, per chain",
+                         "accept_rate": float(np.mean(flips)) / upd_step,
+                         "attempts_accounting_GBps": upd_step * N_SITES * bJ / kern_s / 1e9,
+                         "smem_GBps": achieved, "smem_peak_GBps": smem_peak, "smem_frac": achieved / smem_peak},
+            "e2e": {"value": total_updates / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "mean_final_energy": Emean},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, desc, cores = cpu_oracle_rate(sweeps, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -54,19 +54,27 @@ def _schedule(ua, maxMCSteps, annealingSchedule):
 
 
 def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offset=0, order="random",
-         trace_every=0, per_replica_noise=True):
+         trace_every=0, per_replica_noise=True, temperatures=None, steps_per_T=1, start=0):
     """The whole ``makeSampler!`` loop in one library call.  Returns a dict of traces.
 
     rng given  -> site list and fluctuations are drawn on the host in the reference's order
                   (SamplingHelper.jl:39-40 / :121-122) and shipped to the GPU;
     rng None   -> drawn on the GPU by the counter RNG (Philox4x32-10, ``seed``/``step_offset``).
-    order      -> "random" (the reference's uniformly random site per step) or "sequential" (sweeps).
+    order      -> "random" (the reference's uniformly random site per step) or "sequential" (sweeps,
+                  first site ``start``).
+    temperatures / steps_per_T -> the schedule already evaluated on the host: entry k // steps_per_T is the
+                  temperature of step k (0-based); replaces ``annealingSchedule`` (e.g. one entry per sweep).
     """
     if maxMCSteps < 0:
         warnings.warn(f"{maxMCSteps} is negative.")  # SamplingHelper.jl:29-31
         maxMCSteps = 0
-    T = _schedule(ua, maxMCSteps, annealingSchedule)
-    Tsteps = None if T is None else T[1:] if maxMCSteps > 0 else T[:1]
+    if temperatures is not None and hasattr(ua, "temperature"):
+        Tsteps = np.ascontiguousarray(temperatures, dtype=np.float64)
+        T = Tsteps[[0, min(len(Tsteps) - 1, max(0, maxMCSteps - 1) // steps_per_T)]]
+    else:
+        T = _schedule(ua, maxMCSteps, annealingSchedule)
+        Tsteps = None if T is None else T[1:] if maxMCSteps > 0 else T[:1]
+        steps_per_T = 1
     if isinstance(ua, SingleSpinUpdatingAlgorithm):
         ss = ua.spinSystem
         ens = ss._ensemble()
@@ -80,8 +88,9 @@ def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offse
                 per_rep = per_replica_noise and R > 1
                 fluct = ua.distribution.rand(rng, (R, maxMCSteps) if per_rep else maxMCSteps)
         o = _lib.ORDER_SEQUENTIAL if order == "sequential" else (_lib.ORDER_LIST if nodes is not None else _lib.ORDER_RANDOM)
-        out = ens.ssf_run(ua._rule, maxMCSteps, order=o, nodes=nodes, fluct=fluct, fluct_per_replica=per_rep,
-                          seed=seed, step_offset=step_offset, T=Tsteps, trace_every=trace_every)
+        out = ens.ssf_run(ua._rule, maxMCSteps, order=o, nodes=nodes, start=start, fluct=fluct,
+                          fluct_per_replica=per_rep, seed=seed, step_offset=step_offset, T=Tsteps,
+                          steps_per_T=steps_per_T, trace_every=trace_every)
         ss._dev_newer = True
         if T is not None and maxMCSteps > 0:
             ua.temperature = float(T[-1])
@@ -95,7 +104,7 @@ def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offse
         Fv = b.distribution.rand(rng, (maxMCSteps, ens.nv))
         Fh = b.distribution.rand(rng, (maxMCSteps, ens.nh))
     E = ens.bip_run(b._rule, maxMCSteps, Fv=Fv, Fh=Fh, seed=seed, step_offset=step_offset, T=Tsteps,
-                    trace_every=trace_every)
+                    steps_per_T=steps_per_T, trace_every=trace_every)
     ss._dev_newer = True
     if maxMCSteps > 0:
         b.temperature = float(T[-1])

@@ -123,8 +123,10 @@ int isb_create(int device, isb_ctx **out) {
     return ISB_OK;
 }
 
-void isb_destroy(isb_ctx *ctx) {
-    if (!ctx) return;
+// Handles are reference counted so that destruction order does not matter to the caller (a garbage
+// collector may release a model before the ensembles that use it).
+static void ctx_release(isb_ctx *ctx) {
+    if (!ctx || ctx->refs.fetch_sub(1) != 1) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &b : ctx->scratch)
@@ -134,6 +136,8 @@ void isb_destroy(isb_ctx *ctx) {
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
+
+void isb_destroy(isb_ctx *ctx) { ctx_release(ctx); }
 
 const char *isb_last_error(const isb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
@@ -187,15 +191,14 @@ int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const doub
             }
     for (int j = 0; j < n; ++j) {
         for (int i = 0; i <= j; ++i) {
-            const double up = J[i + (int64_t)j * ld];                     // upper triangle element (i <= j)
-            const double lo = sym ? up : J[i + (int64_t)j * ld];          // Symmetric(J, :U)
+            const double up = J[i + (int64_t)j * ld];  // upper-triangle element; the lower one mirrors it: Symmetric(J, :U)
             if (!std::isfinite(up)) return fail(ctx, ISB_ERR_NONFINITE, "isb_model_dense: J[%d,%d] is not finite", i, j);
             if (i == j) {
                 if (up != 0.0) diag = true;
                 continue;
             }
             Jn[(size_t)i * npad + j] = up;
-            Jn[(size_t)j * npad + i] = lo;
+            Jn[(size_t)j * npad + i] = up;
         }
     }
     if (warn) *warn = (sym ? 0 : 1) | (diag ? 2 : 0);
@@ -208,6 +211,7 @@ int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const doub
 
     isb_model *m = new isb_model();
     m->ctx = ctx;
+    ctx->refs.fetch_add(1);
     m->kind = ISB_KIND_DENSE;
     m->prec = prec == ISB_PREC_AUTO ? ISB_PREC_F64 : prec;
     m->n = n;
@@ -286,6 +290,7 @@ int isb_model_bipartite(isb_ctx *ctx, int nv, int nh, const double *W, int64_t l
     }
     isb_model *m = new isb_model();
     m->ctx = ctx;
+    ctx->refs.fetch_add(1);
     m->kind = ISB_KIND_BIPARTITE;
     m->prec = prec;
     m->nv = nv;
@@ -317,8 +322,8 @@ int isb_model_bipartite(isb_ctx *ctx, int nv, int nh, const double *W, int64_t l
     return ISB_OK;
 }
 
-void isb_model_destroy(isb_model *m) {
-    if (!m) return;
+static void model_release(isb_model *m) {
+    if (!m || m->refs.fetch_sub(1) != 1) return;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     if (m->tc) isb::bip_tc_model_free(m);
@@ -329,8 +334,12 @@ void isb_model_destroy(isb_model *m) {
     cudaFree(m->Wt64);
     cudaFree(m->hb64);
     cudaFree(m->bb64);
+    isb_ctx *ctx = m->ctx;
     delete m;
+    ctx_release(ctx);
 }
+
+void isb_model_destroy(isb_model *m) { model_release(m); }
 
 int isb_model_num_visible(const isb_model *m) { return !m ? 0 : (m->kind == ISB_KIND_DENSE ? m->n : m->nv); }
 int isb_model_num_hidden(const isb_model *m) { return !m ? 0 : (m->kind == ISB_KIND_DENSE ? 0 : m->nh); }
@@ -345,6 +354,7 @@ int isb_ens_create(isb_model *m, int R, isb_ens **out) {
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     isb_ens *e = new isb_ens();
     e->model = m;
+    m->refs.fetch_add(1);
     e->R = R;
     int rc = ISB_OK;
     do {
@@ -390,7 +400,9 @@ void isb_ens_destroy(isb_ens *e) {
     cudaFree(e->fields);
     cudaFree(e->d_flips);
     cudaFree(e->d_counters);
+    isb_model *m = e->model;
     delete e;
+    model_release(m);
 }
 
 int isb_ens_replicas(const isb_ens *e) { return e ? e->R : 0; }

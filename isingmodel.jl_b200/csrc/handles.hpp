@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 
 #include "../../include/ising_b200.h"
@@ -13,6 +14,7 @@ struct isb_devbuf {
 };
 
 struct isb_ctx {
+    std::atomic<int> refs{1};    // the creator + every live model: destroyed when the last one lets go
     int device = 0;
     int num_sms = 148;
     size_t smem_optin = 0;
@@ -26,6 +28,7 @@ struct isb_ctx {
 enum { ISB_KIND_DENSE = 0, ISB_KIND_BIPARTITE = 1 };
 
 struct isb_model {
+    std::atomic<int> refs{1};    // the creator + every live ensemble
     isb_ctx *ctx = nullptr;
     int kind = ISB_KIND_DENSE;
     int prec = ISB_PREC_F64;
