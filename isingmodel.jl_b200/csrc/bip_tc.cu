@@ -1,12 +1,524 @@
-// bip_tc.cu — placeholder until the tcgen05 path lands (next commit).
+// bip_tc.cu — K3/K4: block-Gibbs half-steps as tcgen05 GEMMs with the sampling rule fused into the epilogue.
+//
+// Replaces, for R chains at once (ISB_PREC_BF16X3 / ISB_PREC_BF16X1 bipartite models),
+//   hidden  <- sgn+(2 (W' sigma + b) - Fh T [.* hidden])     src/OnBipartiteGraph.jl:35-38 (SCA), :58-61 (MA)
+//   visible <- sgn+(2 (W tau + h)   - Fv T [.* visible])     src/OnBipartiteGraph.jl:39-42 (SCA), :62-65 (MA)
+//   with W' sigma + b = calcLocalAuxiliaryBias, W tau + h = calcLocalMagneticField (src/SpinSystems.jl:147-157).
+//
+// One half-step is D[replica, unit] = S_in[replica, :] . Wop[unit, :] (a dense contraction over the input layer):
+//   A operand  = the spin matrix S_in [R][K] in bf16 (+-1 is exact), K-major, 128 replicas per tile (UMMA M = 128)
+//   B operand  = the couplings Wop [units][K] in bf16, K-major, BN <= 256 units per tile (UMMA N = BN);
+//                W is stored as P bf16 terms W = W1 + W2 + W3 (P = 3: 24 mantissa bits, fp32-exact split;
+//                P = 1: W rounded to bf16, exact when W is bf16-representable, e.g. small integers);
+//   D          = fp32 accumulators in TMEM (2 stages x 256 columns), all P terms accumulate into the same D.
+// Warp-specialised persistent kernel, one CTA per SM:
+//   warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage smem ring, mbarrier complete_tx)
+//   warp 1 = MMA issuer (one elected thread: tcgen05.mma.cta_group::1.kind::f16, tcgen05.commit frees the slot)
+//   warp 2 = TMEM allocator
+//   warps 4-11 = epilogue: tcgen05.ld the accumulators, draw the noise (Philox4x32-10, same words as the
+//                Float64 path), apply the rule, write the new layer as bf16 (next GEMM's operand) and as
+//                int8 (the ensemble's canonical spins), overlapping the next tile's MMAs.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <vector>
+
+#include "common.cuh"
 #include "handles.hpp"
+
 namespace isb {
-int bip_tc_model_init(isb_model *m, const double *) { return fail(m->ctx, ISB_ERR_UNSUPPORTED, "tensor-core path not built"); }
-void bip_tc_model_free(isb_model *) {}
-int bip_tc_ens_init(isb_ens *e) { return fail(e->model->ctx, ISB_ERR_UNSUPPORTED, "tensor-core path not built"); }
-void bip_tc_ens_free(isb_ens *) {}
-int bip_run_tc_device(isb_ens *e, int, int64_t, int, const double *, const double *, uint64_t, uint64_t, const double *,
-                      int64_t, int64_t, double *) {
-    return fail(e->model->ctx, ISB_ERR_UNSUPPORTED, "tensor-core path not built");
+
+constexpr int TC_BM = 128;      // replicas per tile (UMMA M)
+constexpr int TC_BK = 64;       // K elements per stage (128 bytes of bf16 = one swizzle span)
+constexpr int TC_BN_MAX = 256;  // units per tile (UMMA N), runtime BN <= 256, multiple of 16
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KiB
+constexpr int TC_B_BYTES = TC_BN_MAX * TC_BK * 2;      // 32 KiB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 32 * (4 + TC_EPI_WARPS);
+constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+struct TcModel {
+    int P = 1;
+    int ldkv = 0, ldkh = 0;            // K pitch (elements) of the two operand orientations
+    __nv_bfloat16 *Wt[3] = {};         // hidden update operand: [nh][ldkv]  (K = visible units)
+    __nv_bfloat16 *Wn[3] = {};         // visible update operand: [nv][ldkh] (K = hidden units)
+    CUtensorMap mapWt[3], mapWn[3];
+    int bn_h = 0, bn_v = 0;            // tile widths for the hidden / visible update
+};
+struct TcEns {
+    __nv_bfloat16 *Sv = nullptr, *Sh = nullptr;  // [R][ldkv], [R][ldkh]
+    CUtensorMap mapSv, mapSh;
+};
+
+struct TcParams {
+    int R, nout, kin, bn, n_tiles, m_tiles, num_kb, P;
+    int rule, fluct_mode;
+    __nv_bfloat16 *out_bf;   // [R][ldo]
+    int64_t ldo;
+    int8_t *out_i8;          // [R][ldi] canonical spins of the updated layer (also the MA "own previous value")
+    int64_t ldi;
+    const double *bias;      // [nout]
+    const double *F;         // external fluctuations (f64) or NULL
+    int64_t nsteps, k;
+    const double *Tsched;
+    int64_t steps_per_T;
+    uint64_t seed, step_abs;
+    uint32_t domain;
+};
+
+// ------------------------------------------------------------------ PTX wrappers (tcgen05 / TMA)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
 }
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, 128B-swizzled operand tile (rows x 64 bf16): SBO = 1024 B (8 rows), LBO = 1 (unused), version 1.
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem_tile) {
+    const uint32_t lo = ((smem_u32(smem_tile) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = bn
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <bool EXTF>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
+              const __grid_constant__ CUtensorMap mapB1, const __grid_constant__ CUtensorMap mapB2, const TcParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
+    uint64_t *full_bar = bars;                     // [TC_STAGES]
+    uint64_t *empty_bar = bars + TC_STAGES;        // [TC_STAGES]
+    uint64_t *tfull_bar = bars + 2 * TC_STAGES;    // [2]
+    uint64_t *tempty_bar = bars + 2 * TC_STAGES + 2;  // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int iters_per_tile = p.num_kb * p.P;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], TC_EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (lane == 0) {
+            const CUtensorMap *mapsB[3] = {&mapB0, &mapB1, &mapB2};
+            const uint32_t tx = (uint32_t)(TC_A_BYTES + p.bn * TC_BK * 2);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    for (int t = 0; t < p.P; ++t, ++it) {
+                        const int s = it % TC_STAGES;
+                        mbar_wait(&empty_bar[s], ((it / TC_STAGES) & 1) ^ 1);
+                        unsigned char *sa = smem + (size_t)s * TC_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[s], tx);
+                        tma_load_2d(sa, &mapA, kb * TC_BK, m_blk * TC_BM, &full_bar[s]);
+                        tma_load_2d(sa + TC_A_BYTES, mapsB[t], kb * TC_BK, n_blk * p.bn, &full_bar[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(p.bn);
+            uint32_t it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+                const int a = tl & 1;
+                mbar_wait(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN_MAX);
+                for (int i = 0; i < iters_per_tile; ++i, ++it) {
+                    const int s = it % TC_STAGES;
+                    mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
+                    tc_fence_after();
+                    const unsigned char *sa = smem + (size_t)s * TC_STAGE_BYTES;
+                    const uint64_t adesc = umma_desc_sw128(sa);
+                    const uint64_t bdesc = umma_desc_sw128(sa + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)  // advance 16 bf16 = 32 B = 2 descriptor units along K
+                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);  // slot free when these MMAs have read it
+                }
+                umma_commit(&tfull_bar[a]);      // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================ epilogue (sampling rule)
+        const int ew = warp - 4;
+        const int quad = warp & 3;          // TMEM lane quadrant this warp may read: lanes 32*(warpid % 4) ..
+        const int half = ew >> 2;           // two warps share a quadrant and interleave the 16-column chunks
+        const double Td = p.Tsched[p.k / p.steps_per_T];
+        const float Tf = (float)Td;
+        const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2: 2x - T ln(.) >= 0  <=>  x >= cS lg2(.)
+        const int nchunks = p.bn >> 4;
+        uint32_t tl = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+            const int a = tl & 1;
+            mbar_wait(&tfull_bar[a], (tl >> 1) & 1);
+            tc_fence_after();
+            const int r = m_blk * TC_BM + quad * 32 + lane;
+            const bool row_ok = r < p.R;
+            for (int c = half; c < nchunks; c += 2) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TC_BN_MAX + c * 16), v);
+                const int u0 = n_blk * p.bn + c * 16;
+                if (!row_ok || u0 >= p.nout) continue;
+                int8_t *oi = p.out_i8 + (int64_t)r * p.ldi + u0;
+                __nv_bfloat16 *ob = p.out_bf + (int64_t)r * p.ldo + u0;
+                const bool full = u0 + 16 <= p.nout;
+                int4 oldv = make_int4(0, 0, 0, 0);
+                if (p.rule == ISB_BIP_MA) {
+                    if (full) {
+                        oldv = *reinterpret_cast<const int4 *>(oi);
+                    } else {
+                        int8_t tmp[16];
+                        for (int j = 0; j < 16; ++j) tmp[j] = (u0 + j < p.nout) ? oi[j] : (int8_t)1;
+                        oldv = *reinterpret_cast<const int4 *>(tmp);
+                    }
+                }
+                const int8_t *olds = reinterpret_cast<const int8_t *>(&oldv);
+                uint32_t upmask = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    Philox4 blk{0, 0, 0, 0};
+                    if (!EXTF) blk = philox_unit_block(p.seed, p.domain, (uint32_t)r, p.step_abs, (uint32_t)((u0 >> 2) + q));
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = q * 4 + e;
+                        const int u = u0 + j;
+                        const float acc = __uint_as_float(v[j]);
+                        bool up;
+                        if (EXTF) {
+                            double x = 0.0;
+                            if (u < p.nout) {
+                                const double f = p.fluct_mode == ISB_FLUCT_SHARED
+                                                     ? p.F[p.k * p.nout + u]
+                                                     : p.F[((int64_t)r * p.nsteps + p.k) * p.nout + u];
+                                double ft = __dmul_rn(f, Td);
+                                if (p.rule == ISB_BIP_MA) ft = __dmul_rn(ft, (double)olds[j]);
+                                x = __dsub_rn(__dmul_rn(2.0, __dadd_rn((double)acc, p.bias[u])), ft);
+                            }
+                            up = !(x < 0.0);
+                        } else {
+                            const uint32_t w = philox_pick(blk, (uint32_t)e);
+                            const float b = u < p.nout ? (float)p.bias[u] : 0.f;
+                            const float lu = __log2f(fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f));
+                            float x;
+                            if (p.rule == ISB_BIP_SCA) {
+                                const float l1 = __log2f(fmaf((float)(~w), 2.3283064365386963e-10f, 1.1641532182693481e-10f));
+                                x = (acc + b) - cS * (lu - l1);         // 2(a+b) - T ln(u/(1-u)) >= 0
+                            } else {
+                                x = (acc + b) + cS * lu * (float)olds[j];  // 2(a+b) - (-ln u) T s_old >= 0
+                            }
+                            up = !(x < 0.f);
+                        }
+                        upmask |= (up ? 1u : 0u) << j;
+                    }
+                }
+                // pack: bf16 +-1 = 0x3F80 / 0xBF80, int8 +-1 = 0x01 / 0xFF
+                uint32_t wb[8], wi[4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t lo = (upmask >> (2 * j)) & 1u, hi = (upmask >> (2 * j + 1)) & 1u;
+                    wb[j] = (lo ? 0x3F80u : 0xBF80u) | ((hi ? 0x3F80u : 0xBF80u) << 16);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t x = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) x |= (((upmask >> (4 * j + e)) & 1u) ? 0x01u : 0xFFu) << (8 * e);
+                    wi[j] = x;
+                }
+                if (full) {
+                    *reinterpret_cast<uint4 *>(ob) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+                    *reinterpret_cast<uint4 *>(ob + 8) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
+                    *reinterpret_cast<uint4 *>(oi) = make_uint4(wi[0], wi[1], wi[2], wi[3]);
+                } else {
+                    for (int j = 0; j < 16 && u0 + j < p.nout; ++j) {
+                        const bool up = (upmask >> j) & 1u;
+                        ob[j] = __ushort_as_bfloat16(up ? (unsigned short)0x3F80 : (unsigned short)0xBF80);
+                        oi[j] = up ? (int8_t)1 : (int8_t)-1;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[a]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// int8 +-1 -> bf16 +-1 operand matrix (pad columns zero)
+__global__ void spins_to_bf16_kernel(const int8_t *s, int64_t lds, __nv_bfloat16 *o, int64_t ldo, int n, int R) {
+    const int64_t total = (int64_t)R * ldo;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / ldo;
+        const int u = (int)(idx % ldo);
+        unsigned short v = 0;
+        if (u < n) v = s[r * lds + u] > 0 ? 0x3F80 : 0xBF80;
+        o[idx] = __ushort_as_bfloat16(v);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D bf16 matrix [rows][ld] (cols valid), box = {64 cols, box_rows}, 128B swizzle, OOB -> 0
+static int make_map(isb_ctx *ctx, CUtensorMap *map, const void *base, int rows, int cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(ctx, ISB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, ISB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %d x %d, ld %lld", (int)r, rows, cols, (long long)ld);
+    return ISB_OK;
+}
+
+static unsigned short bf16_rne(double x, double *back) {
+    float f = (float)x;
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+    const unsigned short h = (unsigned short)(r >> 16);
+    uint32_t ub = (uint32_t)h << 16;
+    float fb;
+    memcpy(&fb, &ub, 4);
+    *back = (double)fb;
+    return h;
+}
+
+static int pick_bn(int nout) {
+    const int nt = (nout + TC_BN_MAX - 1) / TC_BN_MAX;
+    int bn = ((nout + nt - 1) / nt + 15) / 16 * 16;
+    return bn < 16 ? 16 : bn;
+}
+
+int bip_tc_model_init(isb_model *m, const double *W /*[nv][nh] row-major*/) {
+    isb_ctx *ctx = m->ctx;
+    TcModel *t = new TcModel();
+    m->tc = t;
+    t->P = m->prec == ISB_PREC_BF16X3 ? 3 : 1;
+    const int nv = m->nv, nh = m->nh;
+    t->ldkv = (nv + 15) / 16 * 16;
+    t->ldkh = (nh + 15) / 16 * 16;
+    t->bn_h = pick_bn(nh);
+    t->bn_v = pick_bn(nv);
+    std::vector<unsigned short> wt((size_t)nh * t->ldkv), wn((size_t)nv * t->ldkh);
+    std::vector<double> res((size_t)nv * nh);
+    for (size_t i = 0; i < res.size(); ++i) res[i] = W[i];
+    for (int term = 0; term < t->P; ++term) {
+        std::fill(wt.begin(), wt.end(), 0);
+        std::fill(wn.begin(), wn.end(), 0);
+        for (int i = 0; i < nv; ++i)
+            for (int j = 0; j < nh; ++j) {
+                double back;
+                const unsigned short hbits = bf16_rne(res[(size_t)i * nh + j], &back);
+                res[(size_t)i * nh + j] -= back;
+                wt[(size_t)j * t->ldkv + i] = hbits;
+                wn[(size_t)i * t->ldkh + j] = hbits;
+            }
+        ISB_CUDA(ctx, cudaMalloc(&t->Wt[term], wt.size() * 2));
+        ISB_CUDA(ctx, cudaMalloc(&t->Wn[term], wn.size() * 2));
+        ISB_CUDA(ctx, cudaMemcpy(t->Wt[term], wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+        ISB_CUDA(ctx, cudaMemcpy(t->Wn[term], wn.data(), wn.size() * 2, cudaMemcpyHostToDevice));
+        int rc = make_map(ctx, &t->mapWt[term], t->Wt[term], nh, nv, t->ldkv, t->bn_h);
+        if (rc) return rc;
+        rc = make_map(ctx, &t->mapWn[term], t->Wn[term], nv, nh, t->ldkh, t->bn_v);
+        if (rc) return rc;
+    }
+    for (int term = t->P; term < 3; ++term) {
+        t->mapWt[term] = t->mapWt[0];
+        t->mapWn[term] = t->mapWn[0];
+    }
+    return ISB_OK;
+}
+
+void bip_tc_model_free(isb_model *m) {
+    TcModel *t = (TcModel *)m->tc;
+    if (!t) return;
+    for (int i = 0; i < 3; ++i) {
+        cudaFree(t->Wt[i]);
+        cudaFree(t->Wn[i]);
+    }
+    delete t;
+    m->tc = nullptr;
+}
+
+int bip_tc_ens_init(isb_ens *e) {
+    isb_model *m = e->model;
+    isb_ctx *ctx = m->ctx;
+    TcModel *t = (TcModel *)m->tc;
+    TcEns *s = new TcEns();
+    e->tc = s;
+    ISB_CUDA(ctx, cudaMalloc(&s->Sv, (size_t)e->R * t->ldkv * 2));
+    ISB_CUDA(ctx, cudaMalloc(&s->Sh, (size_t)e->R * t->ldkh * 2));
+    int rc = make_map(ctx, &s->mapSv, s->Sv, e->R, m->nv, t->ldkv, TC_BM);
+    if (rc) return rc;
+    return make_map(ctx, &s->mapSh, s->Sh, e->R, m->nh, t->ldkh, TC_BM);
+}
+
+void bip_tc_ens_free(isb_ens *e) {
+    TcEns *s = (TcEns *)e->tc;
+    if (!s) return;
+    cudaFree(s->Sv);
+    cudaFree(s->Sh);
+    delete s;
+    e->tc = nullptr;
+}
+
+static int launch_half(isb_ens *e, int layer, int rule, int fluct_mode, const double *d_F, int64_t nsteps, int64_t k,
+                       const double *d_T, int64_t steps_per_T, uint64_t seed, uint64_t step_abs) {
+    isb_model *m = e->model;
+    isb_ctx *ctx = m->ctx;
+    TcModel *t = (TcModel *)m->tc;
+    TcEns *s = (TcEns *)e->tc;
+    TcParams p{};
+    p.R = e->R;
+    p.P = t->P;
+    p.rule = rule;
+    p.fluct_mode = fluct_mode;
+    p.F = d_F;
+    p.nsteps = nsteps;
+    p.k = k;
+    p.Tsched = d_T;
+    p.steps_per_T = steps_per_T;
+    p.seed = seed;
+    p.step_abs = step_abs;
+    const CUtensorMap *mapA, *mapB;
+    if (layer == 1) {  // hidden from visible
+        p.nout = m->nh; p.kin = m->nv; p.bn = t->bn_h;
+        p.out_bf = s->Sh; p.ldo = t->ldkh; p.out_i8 = e->hidden; p.ldi = e->ldh; p.bias = m->bb64;
+        p.domain = DOM_BIP_HIDDEN;
+        mapA = &s->mapSv; mapB = t->mapWt;
+    } else {           // visible from hidden
+        p.nout = m->nv; p.kin = m->nh; p.bn = t->bn_v;
+        p.out_bf = s->Sv; p.ldo = t->ldkv; p.out_i8 = e->spins; p.ldi = e->lds; p.bias = m->hb64;
+        p.domain = DOM_BIP_VISIBLE;
+        mapA = &s->mapSh; mapB = t->mapWn;
+    }
+    p.n_tiles = (p.nout + p.bn - 1) / p.bn;
+    p.m_tiles = (p.R + TC_BM - 1) / TC_BM;
+    p.num_kb = (p.kin + TC_BK - 1) / TC_BK;
+    const int grid = std::min(p.n_tiles * p.m_tiles, ctx->num_sms);
+    if (fluct_mode == ISB_FLUCT_PHILOX) {
+        ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        bip_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(*mapA, mapB[0], mapB[1], mapB[2], p);
+    } else {
+        ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        bip_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(*mapA, mapB[0], mapB[1], mapB[2], p);
+    }
+    ISB_CUDA(ctx, cudaGetLastError());
+    e->last_launches += 1;
+    return ISB_OK;
+}
+
+int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv, const double *d_Fh,
+                      uint64_t seed, uint64_t step_offset, const double *d_T, int64_t steps_per_T, int64_t trace_every,
+                      double *d_E) {
+    isb_model *m = e->model;
+    isb_ctx *ctx = m->ctx;
+    TcModel *t = (TcModel *)m->tc;
+    TcEns *s = (TcEns *)e->tc;
+    // the canonical int8 visible layer is the input of the first half-step; the hidden bf16 matrix is
+    // produced by it (MomentumAnnealing reads the hidden layer's previous value from the int8 array)
+    spins_to_bf16_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(e->spins, e->lds, s->Sv, t->ldkv, m->nv, e->R);
+    ISB_CUDA(ctx, cudaGetLastError());
+    e->last_launches += 1;
+    int64_t ntr = 0;
+    for (int64_t k = 0; k < nsteps; ++k) {
+        int rc = launch_half(e, 1, rule, fluct_mode, d_Fh, nsteps, k, d_T, steps_per_T, seed, step_offset + (uint64_t)k);
+        if (rc) return rc;
+        rc = launch_half(e, 0, rule, fluct_mode, d_Fv, nsteps, k, d_T, steps_per_T, seed, step_offset + (uint64_t)k);
+        if (rc) return rc;
+        if (d_E && trace_every > 0 && (k + 1) % trace_every == 0) {
+            rc = bip_energy_device(e, d_E + ntr * e->R);
+            if (rc) return rc;
+            e->last_launches += 1;
+            ++ntr;
+        }
+    }
+    return ISB_OK;
+}
+
 }  // namespace isb

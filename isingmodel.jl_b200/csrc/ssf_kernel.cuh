@@ -136,9 +136,9 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
             if (lane == 0) {
                 const int64_t nq = (p.nsteps + G - 1) / G;
                 int site = p.start;
+                int slot = 0;
+                uint32_t ph = 0;  // slot = q % NG, ph = (q / NG) & 1, kept incrementally (no 64-bit divisions)
                 for (int64_t q = 0; q < nq; ++q) {
-                    const int slot = (int)(q % NG);
-                    const uint32_t ph = (uint32_t)((q / NG) & 1);
                     mbar_wait(&empty_bar[slot], ph ^ 1u);
                     const int64_t left = p.nsteps - q * G;
                     const int rows = left < G ? (int)left : G;
@@ -154,10 +154,20 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                         bulk_g2s(ring + ((size_t)slot * G + g) * NPAD, Jg + (int64_t)i * p.ldj, ROWB,
                                  &full_bar[slot]);
                     }
+                    if (++slot == NG) {
+                        slot = 0;
+                        ph ^= 1u;
+                    }
                 }
-                // no bulk copy may still be in flight when the CTA retires
-                for (int64_t q = nq > NG ? nq - NG : 0; q < nq; ++q)
-                    mbar_wait(&full_bar[q % NG], (uint32_t)((q / NG) & 1));
+                // no bulk copy may still be in flight when the CTA retires: wait for the last min(nq, NG) groups
+                const int last = (int)(nq < NG ? nq : NG);
+                for (int b = 0; b < last; ++b) {
+                    if (--slot < 0) {
+                        slot = NG - 1;
+                        ph ^= 1u;
+                    }
+                    mbar_wait(&full_bar[slot], ph);
+                }
             }
         }
         return;
@@ -181,7 +191,9 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
     const int rule = p.rule;
     const bool audit = p.tie_eps > 0.0;
     unsigned long long nflips = 0, nties = 0;
-    int64_t qcur = -1;  // ring group currently held
+    int64_t qcur = -1;  // ring group currently held; cslot = qcur % NG, cph = (qcur / NG) & 1 (incremental)
+    int cslot = -1;
+    uint32_t cph = 0;
 
     // make group q the held one: release the previous groups in order, wait for each new one
     auto advance_to = [&](int64_t q) {
@@ -189,17 +201,22 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
             while (qcur < q) {
                 if (qcur >= 0) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[qcur % NG]);
+                    if (lane == 0) mbar_arrive(&empty_bar[cslot]);
                 }
                 ++qcur;
-                mbar_wait(&full_bar[qcur % NG], (uint32_t)((qcur / NG) & 1));
+                if (++cslot == NG) {
+                    cslot = 0;
+                    cph ^= 1u;
+                }
+                mbar_wait(&full_bar[cslot], cph);
             }
         }
     };
-    // row of J for step t (visiting `site`): ring slot when streamed by TMA, global memory otherwise
+    // row of J for step t (visiting `site`; its group must be the held one): ring slot when streamed by TMA,
+    // global memory otherwise
     auto row_ptr = [&](int64_t t, int site) -> const JT * {
         if constexpr (TMA) {
-            return ring + ((size_t)((t / G) % NG) * G + (size_t)(t % G)) * NPAD;
+            return ring + ((size_t)cslot * G + (size_t)((int)t & (G - 1))) * NPAD;
         } else {
             return Jg + (int64_t)site * p.ldj;
         }

@@ -302,3 +302,117 @@ def test_error_codes(ctx, synth):
     e2 = L.Ensemble(m2, 1)
     e2.set_spins(np.array([[1, 1, 1]], dtype=np.int8))
     assert np.array_equal(e2.local_field()[0], [5.0, 8.0, 9.0])
+
+
+# ---------------------------------------------------------------- tcgen05 path (bf16 split couplings, fp32 TMEM accumulation)
+def _tc_step_check(L, ctx, orc, W, h, b, S0, T0, rule, prec, Fv, Fh, T, tol):
+    """One block-Gibbs step from the same state on the tensor-core path and on the oracle.  The accumulators
+    are fp32 (not the oracle's Float64), so a decision may differ only where the oracle's decision quantity
+    |2(W's + b) - F T| is below `tol` (near tie); with exactly representable W (tol = 0) it must be bit-exact."""
+    R, nv = S0.shape
+    nh = T0.shape[1]
+    e = L.Ensemble(L.Model.bipartite(ctx, W, h, b, prec), R)
+    e.set_spins(S0)
+    e.set_hidden(T0)
+    e.bip_run(rule, 1, Fv=Fv, Fh=Fh, fluct_per_replica=True, T=np.array([T]))
+    S, Tm = e.get_spins(), e.get_hidden()
+    bad = 0
+    for r in range(R):
+        aux = orc.bip_aux_bias(W, b, S0[r])
+        ft = Fh[r, 0] * T * (T0[r] if rule == 1 else 1.0)
+        xh = 2.0 * aux - ft
+        t_or = np.where(xh < 0, -1, 1).astype(np.int8)
+        dh = Tm[r] != t_or
+        assert np.all(np.abs(xh[dh]) <= tol), (r, np.abs(xh[dh]).max())
+        bad += int(dh.sum())
+        # visible layer from the hidden layer the GPU actually produced
+        fld = orc.bip_local_field(W, h, Tm[r])
+        ftv = Fv[r, 0] * T * (S0[r] if rule == 1 else 1.0)
+        xv = 2.0 * fld - ftv
+        s_or = np.where(xv < 0, -1, 1).astype(np.int8)
+        dv = S[r] != s_or
+        assert np.all(np.abs(xv[dv]) <= tol), (r, np.abs(xv[dv]).max())
+        bad += int(dv.sum())
+    return bad, e
+
+
+TC_CASES = [(64, 48, 0, 130, "x1int"), (784, 512, 0, 300, "x3"), (784, 512, 1, 200, "x3"), (200, 1000, 0, 257, "x3"),
+            (96, 40, 1, 64, "x1int"), (1024, 1024, 0, 128, "x3")]
+
+
+@pytest.mark.parametrize("nv,nh,rule,R,kind", TC_CASES)
+def test_bip_tc_single_step(ctx, orc, synth, nv, nh, rule, R, kind):
+    L = _lib()
+    if kind == "x1int":  # small-integer couplings: exact in bf16, every partial sum exact in fp32
+        W = np.round(synth.gaussian(71, nv * nh).reshape(nv, nh) * 2.0)
+        h, b = np.round(synth.gaussian(72, nv)), np.round(synth.gaussian(73, nh))
+        prec, tol = L.PREC_BF16X1, 0.0
+    else:
+        W, h, b = synth.bipartite_W(nv, nh, 74, 0.1)
+        prec, tol = L.PREC_BF16X3, 2e-4
+    S0, T0 = synth.spins(75, R, nv), synth.spins(76, R, nh)
+    gen = synth.logistic if rule == 0 else synth.exponential
+    Fv, Fh = gen(77, (R, 1, nv), 1), gen(77, (R, 1, nh), 2)
+    bad, e = _tc_step_check(L, ctx, orc, W, h, b, S0, T0, rule, prec, Fv, Fh, 0.9, tol)
+    assert bad <= max(2, int(1e-4 * R * (nv + nh)))
+    if kind == "x1int":
+        assert bad == 0
+    # the canonical int8 state is what energy / field kernels see
+    Eg = e.energy()
+    S, Tm = e.get_spins(), e.get_hidden()
+    Eo = np.array([orc.bip_energy(W, h, b, S[r], Tm[r]) for r in range(min(R, 8))])
+    assert _close(Eg[:len(Eo)], Eo)
+
+
+def test_bip_tc_exact_trajectory_integer_W(ctx, orc, synth):
+    """Integer couplings: the tensor-core path is bit-exact, so whole trajectories match the oracle."""
+    L = _lib()
+    nv, nh, R, nsteps = 160, 96, 140, 6
+    W = np.round(synth.gaussian(81, nv * nh).reshape(nv, nh) * 1.5)
+    h, b = np.round(synth.gaussian(82, nv)), np.round(synth.gaussian(83, nh))
+    S0, T0 = synth.spins(84, R, nv), synth.spins(85, R, nh)
+    T = synth.geometric_schedule(3.0, 0.5, nsteps)
+    for rule in (0, 1):
+        gen = synth.logistic if rule == 0 else synth.exponential
+        Fv, Fh = gen(86, (R, nsteps, nv), 1), gen(86, (R, nsteps, nh), 2)
+        e = L.Ensemble(L.Model.bipartite(ctx, W, h, b, L.PREC_BF16X1), R)
+        e.set_spins(S0)
+        e.set_hidden(T0)
+        E = e.bip_run(rule, nsteps, Fv=Fv, Fh=Fh, fluct_per_replica=True, T=T, trace_every=2)
+        S, Tm = e.get_spins(), e.get_hidden()
+        for r in range(R):
+            s, t, Eo = orc.bip_run(rule, W, h, b, S0[r], T0[r], nsteps, Fv[r], Fh[r], T, want_E=True)
+            assert np.array_equal(s, S[r]) and np.array_equal(t, Tm[r])
+            assert _close(E[:, r], Eo[1::2])
+
+
+def test_bip_tc_philox_matches_f64_path(ctx, synth):
+    """ISB_FLUCT_PHILOX draws the same Philox words on both paths; the tensor-core path turns them into
+    decisions in fp32.  With integer couplings and T = 0 the noise drops out and both paths must agree
+    exactly; at T > 0 they may differ only on rare near ties, so the energy distributions must agree."""
+    L = _lib()
+    nv, nh, R = 192, 128, 512
+    W = np.round(synth.gaussian(91, nv * nh).reshape(nv, nh) * 1.5)
+    h, b = np.round(synth.gaussian(92, nv)), np.round(synth.gaussian(93, nh))
+    S0, T0 = synth.spins(94, R, nv), synth.spins(95, R, nh)
+    out = {}
+    for prec in (L.PREC_F64, L.PREC_BF16X1):
+        e = L.Ensemble(L.Model.bipartite(ctx, W, h, b, prec), R)
+        e.set_spins(S0)
+        e.set_hidden(T0)
+        e.bip_run(0, 3, seed=5, T=np.zeros(3))
+        out[prec] = (e.get_spins(), e.get_hidden())
+    assert np.array_equal(out[L.PREC_F64][0], out[L.PREC_BF16X1][0])
+    assert np.array_equal(out[L.PREC_F64][1], out[L.PREC_BF16X1][1])
+    W, h, b = synth.bipartite_W(nv, nh, 96, 0.1)
+    En = {}
+    for prec in (L.PREC_F64, L.PREC_BF16X3):
+        e = L.Ensemble(L.Model.bipartite(ctx, W, h, b, prec), R)
+        e.set_spins(S0)
+        e.set_hidden(T0)
+        e.bip_run(0, 30, seed=6, T=np.full(30, 1.0))
+        En[prec] = e.energy()
+    a, c = En[L.PREC_F64], En[L.PREC_BF16X3]
+    # same noise words -> almost every chain follows the identical trajectory
+    assert np.mean(np.abs(a - c) < 1e-9 * np.maximum(1, np.abs(a))) > 0.9
+    assert abs(a.mean() - c.mean()) < 4 * a.std() / np.sqrt(R)
