@@ -170,6 +170,189 @@ def reference_arm(args):
     return 0
 
 
+
+# ---------------------------------------------------------------------------------------------- SCA workloads
+def sca_workload(which):
+    """(W, h_visible, b_hidden, R, T schedule factory, description) of BASELINE.json configs[2] / configs[3]."""
+    from isingmodel_jl_b200 import synth
+    if which == "c4":
+        W, h, b = synth.bipartite_W(784, 512, 4, 0.1)
+        return W, h, b, 16384, (lambda n: np.ones(n)), "C4: bipartite 784x512 block Gibbs (SCA), 16384 chains/GPU, T=1"
+    N = 4096
+    J = synth.sk_J(N, 3)
+    # pinning parameter q = eigmax(J)/2 (demo.jl:82); W = (J + qI)/2, biases h/2 (h = 0 here)
+    q = 0.5 * float(np.linalg.eigvalsh(J)[-1])
+    W = 0.5 * (J + q * np.eye(N))
+    z = np.zeros(N)
+    return W, z, z, 8192, (lambda n: np.linspace(1.0, 0.05, n)), \
+        f"C3: dense Gaussian J N=4096 MultiSpinFlip SCA (bipartite embedding W=(J+qI)/2, q={q:.4f}), 8192 replicas/GPU, linear annealing T 1->0.05"
+
+
+def sca_cpu_rate(W, h, b, T, seconds_target):
+    import oracle
+    from isingmodel_jl_b200 import synth
+    threads = oracle.num_threads()
+    nv, nh = W.shape
+    S0, T0 = synth.spins(7, threads, nv), synth.spins(8, threads, nh)
+
+    def run(n):
+        Fv, Fh = synth.logistic(9, (n, nv), 1), synth.logistic(9, (n, nh), 2)
+        t0 = time.perf_counter()
+        oracle.bip_run_batch(oracle.SCA, W, h, b, S0, T0, n, Fv, Fh, T[:n] if len(T) >= n else np.resize(T, n), nthreads=threads)
+        return time.perf_counter() - t0, n * (nv + nh) * threads
+
+    dt, cnt = run(1)
+    n = int(max(1, min(200, round(seconds_target / max(dt, 1e-6)))))
+    dt, cnt = run(n)
+    return cnt / dt, f"{threads} chains (one per thread) x {n} SCA steps ({cnt} updates, {dt:.1f} s wall)", threads
+
+
+def sca_main(args):
+    which = args.workload
+    prec_name = args.prec or "bf16x3"
+    nst = args.sca_steps or (20 if which == "c3" else 200)
+    W, h, b, R, sched, desc = sca_workload(which)
+    nv, nh = W.shape
+    T = sched(nst)
+    upd_step = (nv + nh) * R * nst
+    cfg = {"workload": desc + f", {nst} SCA steps per bench step", "nv": nv, "nh": nh, "chains_per_gpu": R,
+           "sca_steps_per_step": nst, "updates_per_step_per_gpu": upd_step, "coupling_storage": prec_name,
+           "sharding": "replicas (no collective)",
+           "l2": "flushed between timed steps (256 MiB write); spin matrices exceed nothing by design: W is L2-resident"}
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        rates = []
+        for i in range(args.warmup + args.steps):
+            v, sd, cores = sca_cpu_rate(W, h, b, T, args.ref_seconds)
+            if i >= args.warmup:
+                rates.append(v)
+        v = float(np.mean(rates))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * upd_step / v,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sd},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from isingmodel_jl_b200 import _lib, synth, sharding, SpinSystems, OnBipartiteGraph, SamplingHelper
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = _lib.context(local)
+    ctx.set_stream(stream.cuda_stream)
+    prec = {"bf16x3": _lib.PREC_BF16X3, "bf16x1": _lib.PREC_BF16X1, "f64": _lib.PREC_F64}[prec_name]
+    P = {"bf16x3": 3, "bf16x1": 1, "f64": 1}[prec_name]
+    pv = torch.empty((R, nv), dtype=torch.int8).pin_memory().numpy()
+    ph = torch.empty((R, nh), dtype=torch.int8).pin_memory().numpy()
+    pv[:] = synth.spins(11 + 1000 * rank, R, nv)
+    ph[:] = synth.spins(12 + 1000 * rank, R, nh)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ss = SpinSystems.SpinSystemOnBipartiteGraph(pv, ph, W, h, b, device=local, prec=prec)
+    ua = OnBipartiteGraph.StochasticCellularAutomata(ss, float(T[0]))
+    ens = ss._ensemble()
+
+    def device_step(k):
+        ens.set_spins(pv)
+        ens.set_hidden(ph)
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ens.bip_run(_lib.BIP_SCA, nst, seed=777 + rank, step_offset=k * nst, T=T)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), ens.last_stats()
+
+    def e2e_step(k):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ss.spinConfiguration = pv
+        ss.hiddenLayer = ph
+        SamplingHelper.run_(ua, nst, seed=777 + rank, step_offset=k * nst, temperatures=T)
+        st = ens.last_stats()
+        S, Tm = ss.spinConfiguration, ss.hiddenLayer
+        E = SpinSystems.calcEnergy(ua)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return dt, pv.nbytes + ph.nbytes + st["h2d_bytes"], S.nbytes + Tm.nbytes + E.nbytes + st["d2h_bytes"], float(E.mean())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for k in range(args.warmup):
+        device_step(k)
+    barrier()
+    sampler.mark(lo=time.time())
+    ms, kms, launches = [], [], 0
+    for k in range(args.steps):
+        m, st = device_step(args.warmup + k)
+        ms.append(m)
+        kms.append(st["kernel_ms"])
+        launches += st["launches"]
+    barrier()
+    sampler.mark(hi=time.time())
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = sharding.max_over_ranks(sum(ms) / 1e3)
+    for k in range(min(args.warmup, 1)):
+        e2e_step(k)
+    barrier()
+    e2e_t = 0.0
+    for k in range(args.steps):
+        dt, h2d, d2h, Emean = e2e_step(args.warmup + k)
+        e2e_t += dt
+    barrier()
+    t_e2e = sharding.max_over_ranks(e2e_t)
+    total = upd_step * args.steps * world
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, src = float(json.load(open(peaks_path))["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
+        else:
+            peak, src = 1400.0, "B200_PROFILING.md fallback ~1.4 PFLOP/s sustained (of fallback)"
+        n_half = 2 * nst
+        kern_s = float(np.mean(kms)) / 1e3 / n_half          # average half-step (one GEMM + sample launch)
+        alg = 2.0 * nv * nh * R                               # algorithmic flops per half-step launch
+        ach = alg / kern_s / 1e12
+        line = {"metric": METRIC, "value": total / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec_name != "f64" else "f64",
+                "data": "synthetic", "config": cfg,
+                "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                             "traffic": None, "peak_source": src, "kernel": "isb::bip_tc_kernel",
+                             "kernel_ms": 1e3 * kern_s, "split_passes": P, "executed_TFLOPs": ach * P,
+                             "executed_frac": ach * P / peak,
+                             "accounting": "2 x N_out x N_in x R flop per half-step launch (one bf16 pass); executed = passes x algorithmic"},
+                "e2e": {"value": total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "mean_final_energy": Emean},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            v, sd, cores = sca_cpu_rate(W, h, b, T, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sd}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -181,8 +364,15 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=8.0, help="CPU seconds per reference-arm step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU seconds of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--prec", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--prec", default=None, help="c2: f64 | f32; c3/c4: bf16x3 | bf16x1 | f64")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2 (default, the headline): SK N=1024 single-spin Glauber annealing; c3: dense N=4096 "
+                         "MultiSpinFlip SCA, 8192 replicas; c4: bipartite 784x512 block Gibbs, 16384 chains")
+    ap.add_argument("--sca-steps", type=int, default=None, help="SCA steps per bench step (c3: 20, c4: 200)")
     args = ap.parse_args()
+    if args.workload != "c2":
+        return sca_main(args)
+    args.prec = args.prec or "f64"
     if args.impl == "reference":
         return reference_arm(args)
 

@@ -162,11 +162,15 @@ int64_t orc_ssf_run_batch(int rule, int n, const double *J, int64_t ld, const do
 /* src/SpinSystems.jl:147-150 — W*tau + h (row sums over ascending hidden index). */
 void orc_bip_local_field(int nv, int nh, const double *W, int64_t ld, const double *h,
                          const int8_t *tau, double *out) {
-    for (int i = 0; i < nv; ++i) {
-        double acc = 0.0;
-        for (int j = 0; j < nh; ++j) acc += JAT(W, ld, i, j) * (double)tau[j];
-        out[i] = acc + h[i];
+    /* Column sweep (the loop nest of a column-major gemv, as Julia's W * tau runs it): every out[i] still
+     * receives its terms in ascending j, so the result is bit-identical to the row-by-row sum. */
+    for (int i = 0; i < nv; ++i) out[i] = 0.0;
+    for (int j = 0; j < nh; ++j) {
+        const double t = (double)tau[j];
+        const double *col = W + (int64_t)j * ld;
+        for (int i = 0; i < nv; ++i) out[i] += col[i] * t;
     }
+    for (int i = 0; i < nv; ++i) out[i] = out[i] + h[i];
 }
 
 /* src/SpinSystems.jl:154-157 — W'*sigma + b (column sums over ascending visible index). */
