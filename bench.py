@@ -353,6 +353,109 @@ def sca_main(args):
     return 0
 
 
+
+# ---------------------------------------------------------------------------------------------- C5: row-sharded SCA
+def c5_main(args):
+    """BASELINE config 5: dense J with N = 8192 x GPUs (65536 on 8), rows of W = (J + qI)/2 sharded across the GPUs,
+    R replicas, SCA annealing, one all-gather of the freshly sampled spin blocks per half-step (NCCL over NVLink)."""
+    import torch
+    import torch.distributed as dist
+    from isingmodel_jl_b200 import _lib, synth, sharding, rowshard
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "config 5 (N=65536: J is 32 GiB in Float64) is GPU-only; see --workload c3 for the CPU arm of the same algorithm"}))
+        return 0
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    prec_name = args.prec or "bf16x3"
+    prec = {"bf16x3": _lib.PREC_BF16X3, "bf16x1": _lib.PREC_BF16X1}[prec_name]
+    P = 3 if prec_name == "bf16x3" else 1
+    nb, R = args.c5_n_per_gpu, args.c5_replicas
+    n = nb * world
+    nst = args.sca_steps or 10
+    sca = rowshard.RowShardedSCA(n, R, seed=5, q=1.0, prec=prec, device=local)
+    S0 = synth.spins(21, R, n)   # the same initial configuration on every rank
+    T = np.linspace(1.0, 0.05, nst)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(k):
+        sca.set_spins(S0)
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sca.run(nst, T, seed=31, step_offset=k * nst)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    sampler.mark(lo=time.time())
+    l0 = sca.launches
+    ms = [step(args.warmup + k) for k in range(args.steps)]
+    launches = sca.launches - l0
+    barrier()
+    sampler.mark(hi=time.time())
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = sharding.max_over_ranks(sum(ms) / 1e3)
+    # e2e: host spins in (pinned) -> run -> host spins out
+    pin = torch.empty((R, n), dtype=torch.int8).pin_memory().numpy()
+    pin[:] = S0
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        sca.set_spins(pin)
+        sca.run(nst, T, seed=31, step_offset=(args.warmup + k) * nst)
+        out = sca.get_spins()
+    torch.cuda.synchronize()
+    t_e2e = sharding.max_over_ranks(time.perf_counter() - t0)
+    upd_step = 2 * n * R * nst
+    if rank == 0:
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = float(json.load(open(pk))["bf16_tflops_sustained"]) if os.path.exists(pk) else 1400.0
+        half_s = t_dev / args.steps / (2 * nst)
+        flops = 2.0 * nb * n * R            # per GPU per half-step (one bf16 pass)
+        gather = (world - 1) * R * nb * 2   # bytes received per GPU per half-step
+        t_mma, t_link = flops * P / (peak * 1e12), gather / 770e9
+        ach = flops / half_s / 1e12
+        print(json.dumps({
+            "metric": METRIC, "value": upd_step * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"C5: dense SK J N={n} row-sharded over {world} GPU(s) ({nb} rows each), {R} replicas, "
+                                   f"SCA annealing T 1->0.05, {nst} steps per bench step, all-gather of spins per half-step",
+                       "n": n, "rows_per_gpu": nb, "replicas": R, "coupling_storage": prec_name,
+                       "collective": "ncclAllGather via torch.distributed" if world > 1 else "none (1 GPU)",
+                       "l2": "flushed between timed steps; W block (>= 1 GiB) exceeds L2"},
+            "roofline": {"bound": "tensor" if t_mma >= t_link else "nvlink", "achieved": ach, "peak": peak,
+                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "kernel": "isb::bip_tc_kernel",
+                         "kernel_ms": 1e3 * half_s, "split_passes": P, "executed_frac": ach * P / peak,
+                         "fused_target_ms": 1e3 * max(t_mma, t_link), "frac_of_fused_target": max(t_mma, t_link) / half_s,
+                         "all_gather_bytes_per_half_step": gather},
+            "e2e": {"value": upd_step * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(pin.nbytes),
+                    "d2h_bytes_per_step": int(out.nbytes)},
+            "gpu_launches": int(launches), "clocks": clocks}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -365,11 +468,15 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU seconds of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prec", default=None, help="c2: f64 | f32; c3/c4: bf16x3 | bf16x1 | f64")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+    ap.add_argument("--c5-n-per-gpu", type=int, default=8192, help="c5: rows of J per GPU (N = this x GPUs; 8 GPUs -> 65536)")
+    ap.add_argument("--c5-replicas", type=int, default=1024)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 (default, the headline): SK N=1024 single-spin Glauber annealing; c3: dense N=4096 "
                          "MultiSpinFlip SCA, 8192 replicas; c4: bipartite 784x512 block Gibbs, 16384 chains")
     ap.add_argument("--sca-steps", type=int, default=None, help="SCA steps per bench step (c3: 20, c4: 200)")
     args = ap.parse_args()
+    if args.workload == "c5":
+        return c5_main(args)
     if args.workload != "c2":
         return sca_main(args)
     args.prec = args.prec or "f64"

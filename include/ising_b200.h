@@ -169,6 +169,36 @@ int isb_bip_run(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const doub
 int isb_philox_bip_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64_t step_offset,
                          int layer, int nunits, int r0, int nr, int64_t nsteps, double *out);
 
+
+/* ------------------------------------------------------------------ row-sharded synchronous SCA (one process per GPU) */
+/*
+ * The large dense-J case (BASELINE config 5): the MultiSpinFlip SCA of an N-spin model, i.e. the bipartite SCA
+ * (src/OnBipartiteGraph.jl:30-43) on the embedding W = (J + qI)/2, h/2, h/2, sigma = tau = s (demo.jl:82-90),
+ * with W too large for one GPU.  Rank `block` of `n_blocks` owns the output units
+ * [block*nb, (block+1)*nb), nb = n / n_blocks, of BOTH half-steps (W is symmetric) and holds only W[block rows, :].
+ * The spin matrices live in CALLER-OWNED device buffers (the host layer allocates them with its tensor library
+ * and all-gathers them over NCCL / NVLink between half-steps):
+ *   full layer  : bf16 [n_blocks][R][nb]   (block-major, +1/-1)        — the K operand of a half-step
+ *   own block   : bf16 [R][nb] and int8 [R][nb]                        — what this rank samples
+ * Noise is the library's Philox stream indexed by GLOBAL (replica, step, unit), so the trajectory does not
+ * depend on the number of blocks.
+ */
+/* W rows given by the caller: Wrows is [nb][n] row-major (rows block*nb .. of the symmetric W). */
+int isb_shard_model_rows(isb_ctx *ctx, int n, int n_blocks, int block, const double *Wrows, const double *h_blk,
+                         const double *b_blk, int prec, isb_model **out);
+/* Synthetic SK instance generated on the device, never materialised in full: J_ij = J_ji ~ N(0, 1/n) from the
+ * counter RNG (seed), W = (J + qI)/2, zero fields. */
+int isb_shard_model_sk(isb_ctx *ctx, int n, int n_blocks, int block, uint64_t seed, double q, int prec,
+                       isb_model **out);
+/* Rows row0 .. row0+nrows of that synthetic J (out is [nrows][n] row-major), for parity tests. */
+int isb_sk_rows(isb_ctx *ctx, int n, uint64_t seed, int row0, int nrows, double *out);
+int isb_model_shard_block(const isb_model *m); /* nb, 0 for other models */
+/* One half-step of this rank's block (layer 1: hidden from the full visible layer, 0: visible from the full
+ * hidden layer): own <- sgn+(2 (W[block,:] . in + bias) - F T [.* own]) for all R replicas.  All pointers are
+ * DEVICE pointers on the context's device; the kernel is enqueued on the context's stream (isb_set_stream). */
+int isb_shard_halfstep_dev(isb_model *m, int R, int layer, int rule, const void *in_full_bf16,
+                           void *out_block_bf16, int8_t *own_block_i8, uint64_t seed, uint64_t step_abs, double T);
+
 /* ------------------------------------------------------------------ instrumentation */
 /* Device time (ms, CUDA events on the ensemble's stream) of the kernels of the last *_run call,
  * number of kernel launches it made, and bytes copied host->device / device->host by it. */

@@ -79,6 +79,11 @@ SIGNATURES = {
     "isb_philox_raw": (_i, [_vp, _vp, _vp, _i, _vp]),
     "isb_bip_run": (_i, [_vp, _i, _i64, _i, _vp, _vp, _u64, _u64, _vp, _i64, _i64, _i64, _vp]),
     "isb_philox_bip_fluct": (_i, [_vp, _i, _i, _u64, _u64, _i, _i, _i, _i, _i64, _vp]),
+    "isb_shard_model_rows": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
+    "isb_shard_model_sk": (_i, [_vp, _i, _i, _i, _u64, _d, _i, C.POINTER(_vp)]),
+    "isb_sk_rows": (_i, [_vp, _i, _u64, _i, _i, _vp]),
+    "isb_model_shard_block": (_i, [_vp]),
+    "isb_shard_halfstep_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _u64, _u64, _d]),
     "isb_ens_last_stats": (_i, [_vp, C.POINTER(_d), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "isb_ens_last_flips": (_i64, [_vp]),
     "isb_ens_last_near_ties": (_i64, [_vp]),
@@ -163,6 +168,12 @@ class Context:
         check(load().isb_philox_nodes(self.handle, n, seed, step_offset, nsteps, ptr(out)), self.handle)
         return out
 
+    def sk_rows(self, n, seed, row0, nrows):
+        """Rows of the device-generated synthetic SK matrix J (isb_sk_rows)."""
+        out = np.zeros((nrows, n), dtype=np.float64)
+        check(load().isb_sk_rows(self.handle, int(n), int(seed), int(row0), int(nrows), ptr(out)), self.handle)
+        return out
+
     def philox_bip_fluct(self, rule, seed, step_offset, layer, nunits, r0, nr, nsteps):
         out = np.zeros((nr, nsteps, nunits), dtype=np.float64)
         check(load().isb_philox_bip_fluct(self.handle, rule, PREC_F64, seed, step_offset, layer, nunits, r0, nr,
@@ -212,6 +223,31 @@ class Model:
         check(load().isb_model_bipartite(ctx.handle, A.shape[0], A.shape[1], ptr(A), max(1, A.shape[0]), ptr(h),
                                          ptr(b), prec, C.byref(m)), ctx.handle)
         return cls(ctx, m, "bipartite")
+
+    @classmethod
+    def shard_rows(cls, ctx: Context, n, n_blocks, block, Wrows, h_blk=None, b_blk=None, prec=PREC_BF16X3):
+        """Row block `block` of a symmetric W (Wrows: [n // n_blocks][n]) — isb_shard_model_rows."""
+        A = np.ascontiguousarray(Wrows, dtype=np.float64)
+        h_blk = None if h_blk is None else np.ascontiguousarray(h_blk, dtype=np.float64)
+        b_blk = None if b_blk is None else np.ascontiguousarray(b_blk, dtype=np.float64)
+        m = _vp()
+        check(load().isb_shard_model_rows(ctx.handle, int(n), int(n_blocks), int(block), ptr(A), ptr(h_blk),
+                                          ptr(b_blk), prec, C.byref(m)), ctx.handle)
+        return cls(ctx, m, "shard")
+
+    @classmethod
+    def shard_sk(cls, ctx: Context, n, n_blocks, block, seed, q, prec=PREC_BF16X3):
+        """Row block of the synthetic SK embedding W = (J + qI)/2 generated on the device — isb_shard_model_sk."""
+        m = _vp()
+        check(load().isb_shard_model_sk(ctx.handle, int(n), int(n_blocks), int(block), int(seed), float(q), prec,
+                                        C.byref(m)), ctx.handle)
+        return cls(ctx, m, "shard")
+
+    def shard_halfstep(self, R, layer, rule, in_full_ptr, out_block_ptr, own_i8_ptr, seed, step_abs, T):
+        """isb_shard_halfstep_dev with raw device pointers (ints)."""
+        check(load().isb_shard_halfstep_dev(self.handle, int(R), int(layer), int(rule), _vp(in_full_ptr),
+                                            _vp(out_block_ptr), _vp(own_i8_ptr), int(seed), int(step_abs), float(T)),
+              self.ctx.handle)
 
     @property
     def num_visible(self):

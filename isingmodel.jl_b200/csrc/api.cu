@@ -343,6 +343,7 @@ void isb_model_destroy(isb_model *m) { model_release(m); }
 
 int isb_model_num_visible(const isb_model *m) { return !m ? 0 : (m->kind == ISB_KIND_DENSE ? m->n : m->nv); }
 int isb_model_num_hidden(const isb_model *m) { return !m ? 0 : (m->kind == ISB_KIND_DENSE ? 0 : m->nh); }
+int isb_model_shard_block(const isb_model *m) { return !m ? 0 : m->shard_nb; }
 
 // ------------------------------------------------------------------ ensembles
 int isb_ens_create(isb_model *m, int R, isb_ens **out) {
@@ -351,6 +352,8 @@ int isb_ens_create(isb_model *m, int R, isb_ens **out) {
     if (!out) return fail(ctx, ISB_ERR_ARG, "isb_ens_create: out is NULL");
     *out = nullptr;
     if (R <= 0) return fail(ctx, ISB_ERR_SIZE, "isb_ens_create: R = %d must be positive", R);
+    if (m->kind == ISB_KIND_SHARD)
+        return fail(ctx, ISB_ERR_STATE, "isb_ens_create: row-sharded models keep their spin matrices in caller-owned device buffers (isb_shard_halfstep_dev)");
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     isb_ens *e = new isb_ens();
     e->model = m;
@@ -728,6 +731,85 @@ int isb_philox_bip_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64
     ISB_TRY(d2h(ctx, out, d, bytes, nullptr));
     ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ISB_OK;
+}
+
+
+// ------------------------------------------------------------------ row-sharded symmetric SCA (config 5)
+static int shard_model_common(isb_ctx *ctx, int n, int n_blocks, int block, const double *Wrows, const double *h_blk,
+                              const double *b_blk, uint64_t seed, double q, int prec, isb_model **out, const char *who) {
+    if (!ctx) return ISB_ERR_ARG;
+    if (!out) return fail(ctx, ISB_ERR_ARG, "%s: out is NULL", who);
+    *out = nullptr;
+    if (n <= 0 || n_blocks <= 0 || block < 0 || block >= n_blocks || n % n_blocks != 0)
+        return fail(ctx, ISB_ERR_SIZE, "%s: n = %d must split evenly into %d blocks (block %d)", who, n, n_blocks, block);
+    const int nb = n / n_blocks;
+    if (nb % 64 != 0) return fail(ctx, ISB_ERR_UNSUPPORTED, "%s: block size %d must be a multiple of 64", who, nb);
+    if (prec != ISB_PREC_BF16X3 && prec != ISB_PREC_BF16X1)
+        return fail(ctx, ISB_ERR_ARG, "%s: prec must be ISB_PREC_BF16X3 or ISB_PREC_BF16X1", who);
+    if (!std::isfinite(q)) return fail(ctx, ISB_ERR_NONFINITE, "%s: q is not finite", who);
+    if (Wrows && !all_finite(Wrows, (size_t)nb * n)) return fail(ctx, ISB_ERR_NONFINITE, "%s: W is not finite", who);
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    isb_model *m = new isb_model();
+    m->ctx = ctx;
+    ctx->refs.fetch_add(1);
+    m->kind = ISB_KIND_SHARD;
+    m->prec = prec;
+    m->nv = m->nh = n;
+    m->shard_nb = nb;
+    m->shard_G = n_blocks;
+    m->shard_g = block;
+    std::vector<double> hn((size_t)nb, 0.0), bn((size_t)nb, 0.0);
+    if (h_blk) std::copy(h_blk, h_blk + nb, hn.begin());
+    if (b_blk) std::copy(b_blk, b_blk + nb, bn.begin());
+    int rc = ISB_OK;
+    if (cudaMalloc(&m->hb64, nb * sizeof(double)) != cudaSuccess || cudaMalloc(&m->bb64, nb * sizeof(double)) != cudaSuccess)
+        rc = fail(ctx, ISB_ERR_CUDA, "%s: cudaMalloc failed", who);
+    if (!rc) {
+        cudaMemcpy(m->hb64, hn.data(), nb * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(m->bb64, bn.data(), nb * sizeof(double), cudaMemcpyHostToDevice);
+        rc = isb::shard_model_init(m, Wrows, seed, q);
+    }
+    if (rc) {
+        isb_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return ISB_OK;
+}
+
+int isb_shard_model_rows(isb_ctx *ctx, int n, int n_blocks, int block, const double *Wrows, const double *h_blk,
+                         const double *b_blk, int prec, isb_model **out) {
+    if (ctx && !Wrows) return fail(ctx, ISB_ERR_ARG, "isb_shard_model_rows: W rows are NULL");
+    return shard_model_common(ctx, n, n_blocks, block, Wrows, h_blk, b_blk, 0, 0.0, prec, out, "isb_shard_model_rows");
+}
+
+int isb_shard_model_sk(isb_ctx *ctx, int n, int n_blocks, int block, uint64_t seed, double q, int prec, isb_model **out) {
+    return shard_model_common(ctx, n, n_blocks, block, nullptr, nullptr, nullptr, seed, q, prec, out, "isb_shard_model_sk");
+}
+
+int isb_sk_rows(isb_ctx *ctx, int n, uint64_t seed, int row0, int nrows, double *out) {
+    if (!ctx) return ISB_ERR_ARG;
+    if (!out || n <= 0 || row0 < 0 || nrows < 0 || row0 + nrows > n) return fail(ctx, ISB_ERR_ARG, "isb_sk_rows: bad argument");
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *d;
+    const size_t bytes = (size_t)nrows * n * sizeof(double);
+    ISB_TRY(isb::dev_reserve(ctx, isb::SCR_OUT, bytes, (void **)&d));
+    ISB_TRY(isb::sk_rows_device(ctx, n, seed, row0, nrows, d));
+    ISB_TRY(d2h(ctx, out, d, bytes, nullptr));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+
+int isb_shard_halfstep_dev(isb_model *m, int R, int layer, int rule, const void *in_full_bf16, void *out_block_bf16,
+                           int8_t *own_block_i8, uint64_t seed, uint64_t step_abs, double T) {
+    if (!m) return ISB_ERR_ARG;
+    isb_ctx *ctx = m->ctx;
+    if (m->kind != ISB_KIND_SHARD) return fail(ctx, ISB_ERR_STATE, "isb_shard_halfstep_dev: not a row-sharded model");
+    if (!in_full_bf16 || !out_block_bf16 || !own_block_i8 || R <= 0 || (layer != 0 && layer != 1) ||
+        (rule != ISB_BIP_SCA && rule != ISB_BIP_MA) || !std::isfinite(T))
+        return fail(ctx, ISB_ERR_ARG, "isb_shard_halfstep_dev: bad argument");
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return isb::shard_halfstep_device(m, R, layer, rule, in_full_bf16, out_block_bf16, own_block_i8, seed, step_abs, T);
 }
 
 // ------------------------------------------------------------------ instrumentation

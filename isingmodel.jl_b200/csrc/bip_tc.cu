@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -54,6 +55,9 @@ struct TcEns {
 
 struct TcParams {
     int R, nout, kin, bn, n_tiles, m_tiles, num_kb, P;
+    int u_off;        // global index of output unit 0 (row-sharded models: this rank's block offset), else 0
+    int kb_per_blk;   // K blocks per slab of the A operand (block-major [G][R][nb] spin matrices), else num_kb
+    double T_direct;  // temperature when Tsched is NULL
     int rule, fluct_mode;
     __nv_bfloat16 *out_bf;   // [R][ldo]
     int64_t ldo;
@@ -74,6 +78,13 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(smem_dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols) {
@@ -167,7 +178,7 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         mbar_wait(&empty_bar[s], ((it / TC_STAGES) & 1) ^ 1);
                         unsigned char *sa = smem + (size_t)s * TC_STAGE_BYTES;
                         mbar_arrive_expect_tx(&full_bar[s], tx);
-                        tma_load_2d(sa, &mapA, kb * TC_BK, m_blk * TC_BM, &full_bar[s]);
+                        tma_load_3d(sa, &mapA, (kb % p.kb_per_blk) * TC_BK, m_blk * TC_BM, kb / p.kb_per_blk, &full_bar[s]);
                         tma_load_2d(sa + TC_A_BYTES, mapsB[t], kb * TC_BK, n_blk * p.bn, &full_bar[s]);
                     }
                 }
@@ -203,7 +214,7 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may read: lanes 32*(warpid % 4) ..
         const int half = ew >> 2;           // two warps share a quadrant and interleave the 16-column chunks
-        const double Td = p.Tsched[p.k / p.steps_per_T];
+        const double Td = p.Tsched ? p.Tsched[p.k / p.steps_per_T] : p.T_direct;
         const float Tf = (float)Td;
         const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2: 2x - T ln(.) >= 0  <=>  x >= cS lg2(.)
         const int nchunks = p.bn >> 4;
@@ -238,7 +249,7 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     Philox4 blk{0, 0, 0, 0};
-                    if (!EXTF) blk = philox_unit_block(p.seed, p.domain, (uint32_t)r, p.step_abs, (uint32_t)((u0 >> 2) + q));
+                    if (!EXTF) blk = philox_unit_block(p.seed, p.domain, (uint32_t)r, p.step_abs, (uint32_t)(((p.u_off + u0) >> 2) + q));
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int j = q * 4 + e;
@@ -340,6 +351,23 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+// 3-D bf16 operand [slabs][rows][ld] (cols valid per slab), box = {64 cols, 128 rows, 1 slab}: the A operand.
+// An ordinary [R][K] spin matrix is the 1-slab case; row-sharded models keep the spins block-major [G][R][nb].
+static int make_map_a(isb_ctx *ctx, CUtensorMap *map, const void *base, int slabs, int rows, int cols, int64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(ctx, ISB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slabs};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(ctx, ISB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %d x %d x %d, ld %lld", (int)r, slabs, rows, cols, (long long)ld);
+    return ISB_OK;
+}
+
 // 2-D bf16 matrix [rows][ld] (cols valid), box = {64 cols, box_rows}, 128B swizzle, OOB -> 0
 static int make_map(isb_ctx *ctx, CUtensorMap *map, const void *base, int rows, int cols, int64_t ld, int box_rows) {
     EncodeTiledFn fn = encode_fn();
@@ -433,9 +461,9 @@ int bip_tc_ens_init(isb_ens *e) {
     e->tc = s;
     ISB_CUDA(ctx, cudaMalloc(&s->Sv, (size_t)e->R * t->ldkv * 2));
     ISB_CUDA(ctx, cudaMalloc(&s->Sh, (size_t)e->R * t->ldkh * 2));
-    int rc = make_map(ctx, &s->mapSv, s->Sv, e->R, m->nv, t->ldkv, TC_BM);
+    int rc = make_map_a(ctx, &s->mapSv, s->Sv, 1, e->R, m->nv, t->ldkv);
     if (rc) return rc;
-    return make_map(ctx, &s->mapSh, s->Sh, e->R, m->nh, t->ldkh, TC_BM);
+    return make_map_a(ctx, &s->mapSh, s->Sh, 1, e->R, m->nh, t->ldkh);
 }
 
 void bip_tc_ens_free(isb_ens *e) {
@@ -480,6 +508,8 @@ static int launch_half(isb_ens *e, int layer, int rule, int fluct_mode, const do
     p.n_tiles = (p.nout + p.bn - 1) / p.bn;
     p.m_tiles = (p.R + TC_BM - 1) / TC_BM;
     p.num_kb = (p.kin + TC_BK - 1) / TC_BK;
+    p.kb_per_blk = p.num_kb;
+    p.u_off = 0;
     const int grid = std::min(p.n_tiles * p.m_tiles, ctx->num_sms);
     if (fluct_mode == ISB_FLUCT_PHILOX) {
         ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
@@ -490,6 +520,125 @@ static int launch_half(isb_ens *e, int layer, int rule, int fluct_mode, const do
     }
     ISB_CUDA(ctx, cudaGetLastError());
     e->last_launches += 1;
+    return ISB_OK;
+}
+
+
+// ------------------------------------------------------------------ row-sharded symmetric SCA (BASELINE config 5)
+// Global problem: N spins, W = (J + qI)/2 symmetric (the MultiSpinFlip embedding, demo.jl:82-90), R replicas.
+// Rank g of G owns the output units [g*nb, (g+1)*nb) of BOTH half-steps (W' = W), keeps W[block, :] as bf16
+// split terms, and needs the full previous layer as the K operand: the spin matrices are kept block-major
+// [G][R][nb] so that every rank's freshly sampled [R][nb] block is one contiguous all-gather contribution.
+
+// Synthetic SK coupling J_ij = J_ji = g(min, max) / sqrt(N), g ~ N(0,1) by Box-Muller on two Philox words.
+__device__ __forceinline__ double sk_coupling(uint64_t seed, int n, int i, int j) {
+    if (i == j) return 0.0;
+    const uint32_t a = (uint32_t)min(i, j), b = (uint32_t)max(i, j);
+    const Philox4 w = philox4x32_10(a, b, 0u, 5u << 28, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u1 = ((double)w.x + 0.5) * 2.3283064365386962890625e-10;
+    const double u2 = ((double)w.y + 0.5) * 2.3283064365386962890625e-10;
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2) * rsqrt((double)n);
+}
+__device__ __forceinline__ unsigned short bf16_rne_dev(double x, double *back) {
+    const float f = (float)x;
+    const uint32_t u = __float_as_uint(f);
+    const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+    const unsigned short h = (unsigned short)(r >> 16);
+    *back = (double)__uint_as_float((uint32_t)h << 16);
+    return h;
+}
+// Fills the P bf16 split terms of W[row0 + r][c] = (J + qI)/2 (generated, or taken from Wrows when given).
+__global__ void shard_fill_kernel(int n, int row0, int nrows, uint64_t seed, double q, const double *Wrows, int P,
+                                  __nv_bfloat16 *t0, __nv_bfloat16 *t1, __nv_bfloat16 *t2) {
+    const int64_t total = (int64_t)nrows * n;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / n), c = (int)(idx % n);
+        double w = Wrows ? Wrows[idx] : 0.5 * (sk_coupling(seed, n, row0 + r, c) + (row0 + r == c ? q : 0.0));
+        double back;
+        t0[idx] = __ushort_as_bfloat16(bf16_rne_dev(w, &back));
+        if (P > 1) {
+            w -= back;
+            t1[idx] = __ushort_as_bfloat16(bf16_rne_dev(w, &back));
+            w -= back;
+            t2[idx] = __ushort_as_bfloat16(bf16_rne_dev(w, &back));
+        }
+    }
+}
+__global__ void sk_rows_kernel(int n, uint64_t seed, int row0, int nrows, double *out) {
+    const int64_t total = (int64_t)nrows * n;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x)
+        out[idx] = sk_coupling(seed, n, row0 + (int)(idx / n), (int)(idx % n));
+}
+
+int sk_rows_device(isb_ctx *ctx, int n, uint64_t seed, int row0, int nrows, double *d_out) {
+    sk_rows_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, seed, row0, nrows, d_out);
+    ISB_CUDA(ctx, cudaGetLastError());
+    return ISB_OK;
+}
+
+int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q) {
+    isb_ctx *ctx = m->ctx;
+    TcModel *t = new TcModel();
+    m->tc = t;
+    t->P = m->prec == ISB_PREC_BF16X3 ? 3 : 1;
+    const int n = m->nv, nb = m->shard_nb;
+    t->ldkv = t->ldkh = n;
+    t->bn_h = t->bn_v = pick_bn(nb);
+    const size_t elems = (size_t)nb * n;
+    double *dW = nullptr;
+    if (Wrows) {
+        ISB_CUDA(ctx, cudaMalloc(&dW, elems * sizeof(double)));
+        ISB_CUDA(ctx, cudaMemcpyAsync(dW, Wrows, elems * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for (int term = 0; term < t->P; ++term) ISB_CUDA(ctx, cudaMalloc(&t->Wt[term], elems * 2));
+    shard_fill_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, m->shard_g * nb, nb, seed, q, dW, t->P, t->Wt[0],
+                                                                 t->Wt[1], t->Wt[2]);
+    ISB_CUDA(ctx, cudaGetLastError());
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (dW) cudaFree(dW);
+    for (int term = 0; term < 3; ++term) {
+        const int src = term < t->P ? term : 0;
+        int rc = make_map(ctx, &t->mapWt[term], t->Wt[src], nb, n, n, t->bn_h);
+        if (rc) return rc;
+    }
+    return ISB_OK;
+}
+
+int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *in_full, void *out_block, int8_t *own_i8,
+                          uint64_t seed, uint64_t step_abs, double T) {
+    isb_ctx *ctx = m->ctx;
+    TcModel *t = (TcModel *)m->tc;
+    CUtensorMap mapA;
+    int rc = make_map_a(ctx, &mapA, in_full, m->shard_G, R, m->shard_nb, m->shard_nb);
+    if (rc) return rc;
+    TcParams p{};
+    p.R = R;
+    p.P = t->P;
+    p.rule = rule;
+    p.fluct_mode = ISB_FLUCT_PHILOX;
+    p.Tsched = nullptr;
+    p.T_direct = T;
+    p.steps_per_T = 1;
+    p.seed = seed;
+    p.step_abs = step_abs;
+    p.nout = m->shard_nb;
+    p.kin = m->nv;
+    p.bn = t->bn_h;
+    p.out_bf = (__nv_bfloat16 *)out_block;
+    p.ldo = m->shard_nb;
+    p.out_i8 = own_i8;
+    p.ldi = m->shard_nb;
+    p.bias = layer == 1 ? m->bb64 : m->hb64;
+    p.domain = layer == 1 ? DOM_BIP_HIDDEN : DOM_BIP_VISIBLE;
+    p.u_off = m->shard_g * m->shard_nb;
+    p.n_tiles = (p.nout + p.bn - 1) / p.bn;
+    p.m_tiles = (R + TC_BM - 1) / TC_BM;
+    p.num_kb = p.kin / TC_BK;
+    p.kb_per_blk = m->shard_nb / TC_BK;
+    const int grid = std::min(p.n_tiles * p.m_tiles, ctx->num_sms);
+    ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    bip_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(mapA, t->mapWt[0], t->mapWt[1], t->mapWt[2], p);
+    ISB_CUDA(ctx, cudaGetLastError());
     return ISB_OK;
 }
 

@@ -1,0 +1,41 @@
+"""torchrun worker (2 ranks, NCCL): the all-gather variant of the row-sharded SCA equals the emulation."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import isingmodel_jl_b200 as pkg  # noqa: E402,F401
+from isingmodel_jl_b200 import rowshard, synth  # noqa: E402
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, R, seed, nsteps = 1024, 200, 17, 4
+    S0 = synth.spins(3, R, n)
+    T = np.array([1.0, 0.8, 0.6, 0.4])
+    sca = rowshard.RowShardedSCA(n, R, seed=seed, q=1.0, device=local)
+    assert sca.distributed and sca.G == dist.get_world_size()
+    sca.set_spins(S0)
+    sca.run(nsteps, T, seed=7)
+    got = sca.get_spins()
+    emu = rowshard.RowShardedSCA(n, R, seed=seed, q=1.0, emulate_blocks=dist.get_world_size(), device=local)
+    emu.set_spins(S0)
+    emu.run(nsteps, T, seed=7)
+    ok = np.array_equal(got, emu.get_spins()) and np.array_equal(sca.get_hidden(), emu.get_hidden())
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if dist.get_rank() == 0:
+        print("ROWSHARD-OK" if int(flag.item()) == 1 else "ROWSHARD-MISMATCH", sca.gather_bytes, flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
