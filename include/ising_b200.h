@@ -93,6 +93,12 @@ int isb_synchronize(isb_ctx *ctx);
  * diagonal is zeroed (:35-38); *warn (may be NULL) receives bit 0 / bit 1 when that happened. */
 int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const double *h, int prec,
                     int *warn, isb_model **out);
+/* SpinSystem(s, J::SparseMatrixCSC, h) — the reference's tests and demo pass sparse couplings
+ * (test/runtests.jl:20, demo.jl:60-62).  J in 0-based CSC (Julia's colptr .- 1, rowval .- 1, nzval); same
+ * symmetrise-by-upper-triangle / zero-diagonal handling and `warn` bits as isb_model_dense.  Couplings and
+ * fields are Float64; a flip touches only the stored neighbours. */
+int isb_model_sparse(isb_ctx *ctx, int n, const int64_t *colptr, const int32_t *rowval, const double *nzval,
+                     const double *h, int *warn, isb_model **out);
 /* SpinSystemOnBipartiteGraph(sigma, tau, W, h, b): src/SpinSystems.jl:97-118. W is nv x nh. */
 int isb_model_bipartite(isb_ctx *ctx, int nv, int nh, const double *W, int64_t ld,
                         const double *h, const double *b, int prec, isb_model **out);
@@ -179,7 +185,8 @@ int isb_philox_bip_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64
  * The spin matrices live in CALLER-OWNED device buffers (the host layer allocates them with its tensor library
  * and all-gathers them over NCCL / NVLink between half-steps):
  *   full layer  : bf16 [n_blocks][R][nb]   (block-major, +1/-1)        — the K operand of a half-step
- *   own block   : bf16 [R][nb] and int8 [R][nb]                        — what this rank samples
+ *   own block   : bf16 [R][nb], one buffer per layer                    — what this rank samples (on entry it
+ *                 holds the block's previous values, which MomentumAnnealing multiplies into the noise)
  * Noise is the library's Philox stream indexed by GLOBAL (replica, step, unit), so the trajectory does not
  * depend on the number of blocks.
  */
@@ -197,7 +204,7 @@ int isb_model_shard_block(const isb_model *m); /* nb, 0 for other models */
  * hidden layer): own <- sgn+(2 (W[block,:] . in + bias) - F T [.* own]) for all R replicas.  All pointers are
  * DEVICE pointers on the context's device; the kernel is enqueued on the context's stream (isb_set_stream). */
 int isb_shard_halfstep_dev(isb_model *m, int R, int layer, int rule, const void *in_full_bf16,
-                           void *out_block_bf16, int8_t *own_block_i8, uint64_t seed, uint64_t step_abs, double T);
+                           void *out_block_bf16, uint64_t seed, uint64_t step_abs, double T);
 
 /* ------------------------------------------------------------------ instrumentation */
 /* Device time (ms, CUDA events on the ensemble's stream) of the kernels of the last *_run call,

@@ -26,6 +26,7 @@ class StochasticCellularAutomata(MultiSpinUpdatingAlgorithm):
     def __init__(self, spinSystem: SpinSystem, temperature: float, pinningParameter: float | None = None, *,
                  prec=_lib.PREC_F64):
         J = spinSystem.couplingCoefficients
+        J = J.toarray() if hasattr(J, "toarray") else J
         n = J.shape[0]
         if pinningParameter is None:
             pinningParameter = 0.5 * float(np.linalg.eigvalsh(J)[-1])  # demo.jl:82

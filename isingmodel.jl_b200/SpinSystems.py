@@ -43,13 +43,12 @@ class SpinSystem:
         s = _as_spins(spinConfiguration, "spinConfiguration")
         self._single = s.ndim == 1
         s = np.atleast_2d(s)
-        J = np.asarray(couplingCoefficients)
-        if hasattr(couplingCoefficients, "toarray"):  # scipy.sparse, as the reference tests pass `sparse(...)`
-            J = couplingCoefficients.toarray()
+        sparse = hasattr(couplingCoefficients, "tocsc")  # scipy.sparse, as the reference tests pass `sparse(...)`
+        J = couplingCoefficients.tocsc().astype(np.float64) if sparse else np.asarray(couplingCoefficients)
         h = np.asarray(externalMagneticField)
         numNodes = s.shape[1]
         if J.ndim != 2 or J.shape[0] != J.shape[1]:
-            r, c = (J.shape + (0, 0))[:2]
+            r, c = (tuple(J.shape) + (0, 0))[:2]
             raise ValueError(f"The coupling-coefficient matrix is not a square matrix: {r}rows ≠ {c}columns.")
         row = J.shape[0]
         if numNodes < row:      # :25-27
@@ -62,14 +61,24 @@ class SpinSystem:
                           "coupling-coefficient matrix.  The incorresponding components of the "
                           "spin-configuration vector are ignored.")
             s = s[:, :row]
-        elif not np.array_equal(J, J.T):  # :31-33
+        elif (sparse and (J != J.T).nnz != 0) or (not sparse and not np.array_equal(J, J.T)):  # :31-33
             warnings.warn("The coupling-coefficient matrix should be symmetric.  It is symmetrized by its "
                           "upper-triangular components automatically.")
-            J = np.triu(J) + np.triu(J, 1).T
-        if np.any(np.diag(J) != 0):  # :35-38
+            if sparse:
+                import scipy.sparse as sp
+                J = (sp.triu(J) + sp.triu(J, 1).T).tocsc()
+            else:
+                J = np.triu(J) + np.triu(J, 1).T
+        if np.any(J.diagonal() != 0):  # :35-38
             warnings.warn("The diagonal components of the coupling-coefficient matrix should be zero.  Their "
                           "non-zero components are ignored.")
-            J = J - np.diag(np.diag(J))
+            if sparse:
+                J = J.tolil()
+                J.setdiag(0)
+                J = J.tocsc()
+                J.eliminate_zeros()
+            else:
+                J = J - np.diag(np.diag(J))
         numBias = h.shape[0]
         if row != numBias:      # :40-42
             raise ValueError("The size of the coupling-coefficient matrix does not match the size of the "
@@ -79,7 +88,8 @@ class SpinSystem:
                           "external-magnetic-field vector.  The incorresponding components of the "
                           "external-magnetic-field vector are ignored.")
             h = h[:numNodes]
-        self._J = np.asarray(J, dtype=np.float64)       # float.(...) :50
+        self._sparse = sparse
+        self._J = J if sparse else np.asarray(J, dtype=np.float64)       # float.(...) :50
         self._h = np.asarray(h, dtype=np.float64)
         self._host_spins = np.ascontiguousarray(s, dtype=np.int8)
         if not np.all(np.abs(np.asarray(s, dtype=np.float64)) == 1.0):
@@ -96,7 +106,9 @@ class SpinSystem:
     def _ensemble(self):
         if self._ens is None:
             ctx = _lib.context(self._device)
-            with warnings.catch_warnings():
+            if self._sparse:  # sparse couplings stay sparse on the device (csc -> isb_model_sparse)
+                self._model = _lib.Model.sparse(ctx, self._J, self._h)
+            else:
                 self._model = _lib.Model.dense(ctx, self._J, self._h, self._prec)
             self._ens = _lib.Ensemble(self._model, self.replicas)
             self._ens.set_spins(self._host_spins)
@@ -135,11 +147,12 @@ class SpinSystem:
 
     @couplingCoefficients.setter
     def couplingCoefficients(self, J):
-        J = np.asarray(J, dtype=np.float64)
+        sparse = hasattr(J, "tocsc")
+        J = J.tocsc().astype(np.float64) if sparse else np.asarray(J, dtype=np.float64)
         if J.shape != self._J.shape:
             raise ValueError("coupling-coefficient matrix has the wrong shape")
         self._invalidate_model()
-        self._J = J
+        self._J, self._sparse = J, sparse
 
     @property
     def externalMagneticField(self):

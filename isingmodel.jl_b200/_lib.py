@@ -58,6 +58,7 @@ SIGNATURES = {
     "isb_set_stream": (_i, [_vp, _vp]),
     "isb_synchronize": (_i, [_vp]),
     "isb_model_dense": (_i, [_vp, _i, _vp, _i64, _vp, _i, C.POINTER(_i), C.POINTER(_vp)]),
+    "isb_model_sparse": (_i, [_vp, _i, _vp, _vp, _vp, _vp, C.POINTER(_i), C.POINTER(_vp)]),
     "isb_model_bipartite": (_i, [_vp, _i, _i, _vp, _i64, _vp, _vp, _i, C.POINTER(_vp)]),
     "isb_model_destroy": (None, [_vp]),
     "isb_model_num_visible": (_i, [_vp]),
@@ -83,7 +84,7 @@ SIGNATURES = {
     "isb_shard_model_sk": (_i, [_vp, _i, _i, _i, _u64, _d, _i, C.POINTER(_vp)]),
     "isb_sk_rows": (_i, [_vp, _i, _u64, _i, _i, _vp]),
     "isb_model_shard_block": (_i, [_vp]),
-    "isb_shard_halfstep_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _u64, _u64, _d]),
+    "isb_shard_halfstep_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _u64, _u64, _d]),
     "isb_ens_last_stats": (_i, [_vp, C.POINTER(_d), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "isb_ens_last_flips": (_i64, [_vp]),
     "isb_ens_last_near_ties": (_i64, [_vp]),
@@ -213,6 +214,23 @@ class Model:
         return cls(ctx, m, "dense", w.value)
 
     @classmethod
+    def sparse(cls, ctx: Context, J, h):
+        """J: a scipy.sparse matrix (any format) -> 0-based CSC across the ABI (isb_model_sparse)."""
+        import scipy.sparse as sp
+        A = sp.csc_matrix(J, dtype=np.float64)
+        A.sort_indices()
+        if A.shape[0] != A.shape[1]:
+            raise IsbError(ERR_SIZE, "J must be square")
+        colptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+        rowval = np.ascontiguousarray(A.indices, dtype=np.int32)
+        nzval = np.ascontiguousarray(A.data, dtype=np.float64)
+        h = None if h is None else np.ascontiguousarray(h, dtype=np.float64)
+        m, w = _vp(), C.c_int(0)
+        check(load().isb_model_sparse(ctx.handle, A.shape[0], ptr(colptr), ptr(rowval), ptr(nzval), ptr(h), C.byref(w),
+                                      C.byref(m)), ctx.handle)
+        return cls(ctx, m, "sparse", w.value)
+
+    @classmethod
     def bipartite(cls, ctx: Context, W, h, b, prec=PREC_F64):
         A = np.asfortranarray(np.asarray(W, dtype=np.float64))
         if A.ndim != 2:
@@ -243,11 +261,10 @@ class Model:
                                         C.byref(m)), ctx.handle)
         return cls(ctx, m, "shard")
 
-    def shard_halfstep(self, R, layer, rule, in_full_ptr, out_block_ptr, own_i8_ptr, seed, step_abs, T):
+    def shard_halfstep(self, R, layer, rule, in_full_ptr, out_block_ptr, seed, step_abs, T):
         """isb_shard_halfstep_dev with raw device pointers (ints)."""
         check(load().isb_shard_halfstep_dev(self.handle, int(R), int(layer), int(rule), _vp(in_full_ptr),
-                                            _vp(out_block_ptr), _vp(own_i8_ptr), int(seed), int(step_abs), float(T)),
-              self.ctx.handle)
+                                            _vp(out_block_ptr), int(seed), int(step_abs), float(T)), self.ctx.handle)
 
     @property
     def num_visible(self):

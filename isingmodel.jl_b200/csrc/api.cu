@@ -261,6 +261,44 @@ int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const doub
     return ISB_OK;
 }
 
+
+int isb_model_sparse(isb_ctx *ctx, int n, const int64_t *colptr, const int32_t *rowval, const double *nzval,
+                     const double *h, int *warn, isb_model **out) {
+    if (!ctx) return ISB_ERR_ARG;
+    if (!out || !colptr) return fail(ctx, ISB_ERR_ARG, "isb_model_sparse: NULL argument");
+    *out = nullptr;
+    if (warn) *warn = 0;
+    if (n <= 0) return fail(ctx, ISB_ERR_SIZE, "isb_model_sparse: n = %d must be positive", n);
+    if (colptr[0] != 0) return fail(ctx, ISB_ERR_ARG, "isb_model_sparse: colptr[0] must be 0 (0-based CSC)");
+    for (int j = 0; j < n; ++j)
+        if (colptr[j + 1] < colptr[j]) return fail(ctx, ISB_ERR_ARG, "isb_model_sparse: colptr is not non-decreasing");
+    if (colptr[n] > 0 && (!rowval || !nzval)) return fail(ctx, ISB_ERR_ARG, "isb_model_sparse: NULL argument");
+    if (h && !all_finite(h, (size_t)n)) return fail(ctx, ISB_ERR_NONFINITE, "isb_model_sparse: h is not finite");
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    isb_model *m = new isb_model();
+    m->ctx = ctx;
+    ctx->refs.fetch_add(1);
+    m->kind = ISB_KIND_SPARSE;
+    m->prec = ISB_PREC_F64;
+    m->n = n;
+    m->npad = (n + 31) / 32 * 32;
+    std::vector<double> hn((size_t)m->npad, 0.0);
+    if (h) std::copy(h, h + n, hn.begin());
+    int rc = ISB_OK;
+    if (cudaMalloc(&m->h64, m->npad * sizeof(double)) != cudaSuccess)
+        rc = fail(ctx, ISB_ERR_CUDA, "isb_model_sparse: cudaMalloc failed");
+    if (!rc) {
+        cudaMemcpy(m->h64, hn.data(), m->npad * sizeof(double), cudaMemcpyHostToDevice);
+        rc = isb::sparse_model_init(m, n, colptr, rowval, nzval, warn);
+    }
+    if (rc) {
+        isb_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return ISB_OK;
+}
+
 int isb_model_bipartite(isb_ctx *ctx, int nv, int nh, const double *W, int64_t ld, const double *h, const double *b,
                         int prec, isb_model **out) {
     if (!ctx) return ISB_ERR_ARG;
@@ -327,6 +365,7 @@ static void model_release(isb_model *m) {
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     if (m->tc) isb::bip_tc_model_free(m);
+    if (m->sp) isb::sparse_model_free(m);
     cudaFree(m->J64);
     cudaFree(m->Jperm);
     cudaFree(m->h64);
@@ -341,8 +380,9 @@ static void model_release(isb_model *m) {
 
 void isb_model_destroy(isb_model *m) { model_release(m); }
 
-int isb_model_num_visible(const isb_model *m) { return !m ? 0 : (m->kind == ISB_KIND_DENSE ? m->n : m->nv); }
-int isb_model_num_hidden(const isb_model *m) { return !m ? 0 : (m->kind == ISB_KIND_DENSE ? 0 : m->nh); }
+static bool general_graph(const isb_model *m) { return m->kind == ISB_KIND_DENSE || m->kind == ISB_KIND_SPARSE; }
+int isb_model_num_visible(const isb_model *m) { return !m ? 0 : (general_graph(m) ? m->n : m->nv); }
+int isb_model_num_hidden(const isb_model *m) { return !m ? 0 : (general_graph(m) ? 0 : m->nh); }
 int isb_model_shard_block(const isb_model *m) { return !m ? 0 : m->shard_nb; }
 
 // ------------------------------------------------------------------ ensembles
@@ -362,11 +402,12 @@ int isb_ens_create(isb_model *m, int R, isb_ens **out) {
     int rc = ISB_OK;
     do {
         cudaError_t ce;
-        if (m->kind == ISB_KIND_DENSE) {
+        if (general_graph(m)) {
             e->lds = m->npad;
             ce = cudaMalloc(&e->spins, (size_t)R * e->lds);
             if (ce == cudaSuccess) ce = cudaMemsetAsync(e->spins, 1, (size_t)R * e->lds, ctx->stream);
-            if (ce == cudaSuccess && m->fast_ok) ce = cudaMalloc(&e->fields, (size_t)R * m->npad * isb::ssf_field_elem_size(m));
+            if (ce == cudaSuccess && (m->fast_ok || m->kind == ISB_KIND_SPARSE))
+                ce = cudaMalloc(&e->fields, (size_t)R * m->npad * isb::ssf_field_elem_size(m));
         } else {
             e->lds = (m->nv + 15) / 16 * 16;
             e->ldh = (m->nh + 15) / 16 * 16;
@@ -441,12 +482,12 @@ static int copy_spins_out(isb_ens *e, const int8_t *src, int64_t lds, int n, int
 int isb_ens_set_spins(isb_ens *e, const int8_t *s, int64_t ld) {
     if (!e) return ISB_ERR_ARG;
     const isb_model *m = e->model;
-    return copy_spins_in(e, e->spins, e->lds, m->kind == ISB_KIND_DENSE ? m->n : m->nv, s, ld, "isb_ens_set_spins");
+    return copy_spins_in(e, e->spins, e->lds, general_graph(m) ? m->n : m->nv, s, ld, "isb_ens_set_spins");
 }
 int isb_ens_get_spins(isb_ens *e, int8_t *s, int64_t ld) {
     if (!e) return ISB_ERR_ARG;
     const isb_model *m = e->model;
-    return copy_spins_out(e, e->spins, e->lds, m->kind == ISB_KIND_DENSE ? m->n : m->nv, s, ld, "isb_ens_get_spins");
+    return copy_spins_out(e, e->spins, e->lds, general_graph(m) ? m->n : m->nv, s, ld, "isb_ens_get_spins");
 }
 int isb_ens_set_hidden(isb_ens *e, const int8_t *t, int64_t ld) {
     if (!e) return ISB_ERR_ARG;
@@ -466,7 +507,9 @@ int isb_ens_energy(isb_ens *e, double *E) {
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     double *dE;
     ISB_TRY(isb::dev_reserve(ctx, isb::SCR_OUT, (size_t)e->R * sizeof(double), (void **)&dE));
-    ISB_TRY(e->model->kind == ISB_KIND_DENSE ? isb::dense_energy_device(e, dE) : isb::bip_energy_device(e, dE));
+    ISB_TRY(e->model->kind == ISB_KIND_DENSE    ? isb::dense_energy_device(e, dE)
+            : e->model->kind == ISB_KIND_SPARSE ? isb::sparse_energy_device(e, dE)
+                                                : isb::bip_energy_device(e, dE));
     ISB_TRY(d2h(ctx, E, dE, (size_t)e->R * sizeof(double), nullptr));
     ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ISB_OK;
@@ -488,7 +531,7 @@ int isb_ens_magnetization(isb_ens *e, double *M) {
 static int field_common(isb_ens *e, int layer, double *F, int64_t ld, const char *who) {
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
-    const int nout = m->kind == ISB_KIND_DENSE ? m->n : (layer == 0 ? m->nv : m->nh);
+    const int nout = general_graph(m) ? m->n : (layer == 0 ? m->nv : m->nh);
     if (!F) return fail(ctx, ISB_ERR_ARG, "%s: output is NULL", who);
     if (ld < nout) return fail(ctx, ISB_ERR_SIZE, "%s: leading dimension %lld < %d", who, (long long)ld, nout);
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -496,6 +539,8 @@ static int field_common(isb_ens *e, int layer, double *F, int64_t ld, const char
     ISB_TRY(isb::dev_reserve(ctx, isb::SCR_OUT, (size_t)e->R * nout * sizeof(double), (void **)&dF));
     if (m->kind == ISB_KIND_DENSE)
         ISB_TRY(isb::dense_field_device(e, dF, nout));
+    else if (m->kind == ISB_KIND_SPARSE)
+        ISB_TRY(isb::sparse_field_device(e, dF, nout, nout, 1.0));
     else
         ISB_TRY(isb::bip_field_device(e, layer, dF, nout));
     ISB_CUDA(ctx, cudaMemcpy2DAsync(F, (size_t)ld * sizeof(double), dF, (size_t)nout * sizeof(double),
@@ -539,7 +584,7 @@ int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
     const char *who = "isb_ssf_run";
-    if (m->kind != ISB_KIND_DENSE) return fail(ctx, ISB_ERR_STATE, "%s: not a general-graph ensemble", who);
+    if (!general_graph(m)) return fail(ctx, ISB_ERR_STATE, "%s: not a general-graph ensemble", who);
     if (rule < ISB_RULE_HOPFIELD || rule > ISB_RULE_METROPOLIS) return fail(ctx, ISB_ERR_ARG, "%s: unknown rule %d", who, rule);
     if (nsteps < 0) return fail(ctx, ISB_ERR_ARG, "%s: nsteps = %lld is negative", who, (long long)nsteps);
     if (order < ISB_ORDER_SEQUENTIAL || order > ISB_ORDER_RANDOM) return fail(ctx, ISB_ERR_ARG, "%s: unknown order %d", who, order);
@@ -600,8 +645,12 @@ int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *
         ISB_TRY(isb::philox_nodes_device(ctx, m->n, seed, step_offset, nsteps, d_nodes));
         e->last_launches += 1;
     }
-    ISB_TRY(isb::ssf_run_device(e, rule, nsteps, order, d_nodes, start, fluct_mode, d_fluct, seed, step_offset, d_T,
-                                steps_per_T, (d_E || d_M) ? trace_every : 0, d_E, d_M));
+    if (m->kind == ISB_KIND_SPARSE)
+        ISB_TRY(isb::ssf_sparse_run_device(e, rule, nsteps, order, d_nodes, start, fluct_mode, d_fluct, seed, step_offset,
+                                           d_T, steps_per_T, (d_E || d_M) ? trace_every : 0, d_E, d_M));
+    else
+        ISB_TRY(isb::ssf_run_device(e, rule, nsteps, order, d_nodes, start, fluct_mode, d_fluct, seed, step_offset, d_T,
+                                    steps_per_T, (d_E || d_M) ? trace_every : 0, d_E, d_M));
     ISB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 
     std::vector<unsigned long long> fl((size_t)e->R);
@@ -801,15 +850,15 @@ int isb_sk_rows(isb_ctx *ctx, int n, uint64_t seed, int row0, int nrows, double 
 }
 
 int isb_shard_halfstep_dev(isb_model *m, int R, int layer, int rule, const void *in_full_bf16, void *out_block_bf16,
-                           int8_t *own_block_i8, uint64_t seed, uint64_t step_abs, double T) {
+                           uint64_t seed, uint64_t step_abs, double T) {
     if (!m) return ISB_ERR_ARG;
     isb_ctx *ctx = m->ctx;
     if (m->kind != ISB_KIND_SHARD) return fail(ctx, ISB_ERR_STATE, "isb_shard_halfstep_dev: not a row-sharded model");
-    if (!in_full_bf16 || !out_block_bf16 || !own_block_i8 || R <= 0 || (layer != 0 && layer != 1) ||
+    if (!in_full_bf16 || !out_block_bf16 || R <= 0 || (layer != 0 && layer != 1) ||
         (rule != ISB_BIP_SCA && rule != ISB_BIP_MA) || !std::isfinite(T))
         return fail(ctx, ISB_ERR_ARG, "isb_shard_halfstep_dev: bad argument");
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
-    return isb::shard_halfstep_device(m, R, layer, rule, in_full_bf16, out_block_bf16, own_block_i8, seed, step_abs, T);
+    return isb::shard_halfstep_device(m, R, layer, rule, in_full_bf16, out_block_bf16, seed, step_abs, T);
 }
 
 // ------------------------------------------------------------------ instrumentation

@@ -15,7 +15,7 @@
 //   warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage smem ring, mbarrier complete_tx)
 //   warp 1 = MMA issuer (one elected thread: tcgen05.mma.cta_group::1.kind::f16, tcgen05.commit frees the slot)
 //   warp 2 = TMEM allocator
-//   warps 4-11 = epilogue: tcgen05.ld the accumulators, draw the noise (Philox4x32-10, same words as the
+//   warps 4-19 = epilogue: tcgen05.ld the accumulators, draw the noise (Philox4x32-10, same words as the
 //                Float64 path), apply the rule, write the new layer as bf16 (next GEMM's operand) and as
 //                int8 (the ensemble's canonical spins), overlapping the next tile's MMAs.
 #include <cuda.h>
@@ -36,7 +36,7 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KiB
 constexpr int TC_B_BYTES = TC_BN_MAX * TC_BK * 2;      // 32 KiB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 16;  // 4 per TMEM lane quadrant
 constexpr int TC_THREADS = 32 * (4 + TC_EPI_WARPS);
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
@@ -47,6 +47,7 @@ struct TcModel {
     __nv_bfloat16 *Wn[3] = {};         // visible update operand: [nv][ldkh] (K = hidden units)
     CUtensorMap mapWt[3], mapWn[3];
     int bn_h = 0, bn_v = 0;            // tile widths for the hidden / visible update
+    float *bias_hf = nullptr, *bias_vf = nullptr;  // hidden / visible biases in float, zero padded to 16
 };
 struct TcEns {
     __nv_bfloat16 *Sv = nullptr, *Sh = nullptr;  // [R][ldkv], [R][ldkh]
@@ -61,9 +62,8 @@ struct TcParams {
     int rule, fluct_mode;
     __nv_bfloat16 *out_bf;   // [R][ldo]
     int64_t ldo;
-    int8_t *out_i8;          // [R][ldi] canonical spins of the updated layer (also the MA "own previous value")
-    int64_t ldi;
     const double *bias;      // [nout]
+    const float *bias_f;     // [nout rounded up to 16] the same in float (Philox mode)
     const double *F;         // external fluctuations (f64) or NULL
     int64_t nsteps, k;
     const double *Tsched;
@@ -213,10 +213,11 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         // ================================================================ epilogue (sampling rule)
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may read: lanes 32*(warpid % 4) ..
-        const int half = ew >> 2;           // two warps share a quadrant and interleave the 16-column chunks
+        const int half = ew >> 2;           // the warps of a quadrant interleave the 16-column chunks
         const double Td = p.Tsched ? p.Tsched[p.k / p.steps_per_T] : p.T_direct;
         const float Tf = (float)Td;
-        const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2: 2x - T ln(.) >= 0  <=>  x >= cS lg2(.)
+        const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2
+        const float cE = Tf > 0.f ? -2.0f * 1.4426950408889634f / Tf : 0.f;  // e^{-2x/T} = 2^{cE x}
         const int nchunks = p.bn >> 4;
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
@@ -226,87 +227,83 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             tc_fence_after();
             const int r = m_blk * TC_BM + quad * 32 + lane;
             const bool row_ok = r < p.R;
-            for (int c = half; c < nchunks; c += 2) {
+            for (int c = half; c < nchunks; c += TC_EPI_WARPS / 4) {
                 uint32_t v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TC_BN_MAX + c * 16), v);
                 const int u0 = n_blk * p.bn + c * 16;
                 if (!row_ok || u0 >= p.nout) continue;
-                int8_t *oi = p.out_i8 + (int64_t)r * p.ldi + u0;
                 __nv_bfloat16 *ob = p.out_bf + (int64_t)r * p.ldo + u0;
                 const bool full = u0 + 16 <= p.nout;
-                int4 oldv = make_int4(0, 0, 0, 0);
+                // MomentumAnnealing multiplies the noise by the unit's own previous value: it is still in the
+                // output matrix (bf16 +-1; pad columns read as 0 and are never stored)
+                uint32_t oldw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 if (p.rule == ISB_BIP_MA) {
-                    if (full) {
-                        oldv = *reinterpret_cast<const int4 *>(oi);
-                    } else {
-                        int8_t tmp[16];
-                        for (int j = 0; j < 16; ++j) tmp[j] = (u0 + j < p.nout) ? oi[j] : (int8_t)1;
-                        oldv = *reinterpret_cast<const int4 *>(tmp);
-                    }
+                    const uint4 o0 = *reinterpret_cast<const uint4 *>(ob), o1 = *reinterpret_cast<const uint4 *>(ob + 8);
+                    oldw[0] = o0.x; oldw[1] = o0.y; oldw[2] = o0.z; oldw[3] = o0.w;
+                    oldw[4] = o1.x; oldw[5] = o1.y; oldw[6] = o1.z; oldw[7] = o1.w;
                 }
-                const int8_t *olds = reinterpret_cast<const int8_t *>(&oldv);
-                uint32_t upmask = 0;
+                uint32_t sgn[16];  // bit 31 set <=> the unit goes to -1
+                if (EXTF) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    Philox4 blk{0, 0, 0, 0};
-                    if (!EXTF) blk = philox_unit_block(p.seed, p.domain, (uint32_t)r, p.step_abs, (uint32_t)(((p.u_off + u0) >> 2) + q));
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int j = q * 4 + e;
+                    for (int j = 0; j < 16; ++j) {
                         const int u = u0 + j;
-                        const float acc = __uint_as_float(v[j]);
-                        bool up;
-                        if (EXTF) {
-                            double x = 0.0;
-                            if (u < p.nout) {
-                                const double f = p.fluct_mode == ISB_FLUCT_SHARED
-                                                     ? p.F[p.k * p.nout + u]
-                                                     : p.F[((int64_t)r * p.nsteps + p.k) * p.nout + u];
-                                double ft = __dmul_rn(f, Td);
-                                if (p.rule == ISB_BIP_MA) ft = __dmul_rn(ft, (double)olds[j]);
-                                x = __dsub_rn(__dmul_rn(2.0, __dadd_rn((double)acc, p.bias[u])), ft);
-                            }
-                            up = !(x < 0.0);
-                        } else {
-                            const uint32_t w = philox_pick(blk, (uint32_t)e);
-                            const float b = u < p.nout ? (float)p.bias[u] : 0.f;
-                            const float lu = __log2f(fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f));
-                            float x;
-                            if (p.rule == ISB_BIP_SCA) {
-                                const float l1 = __log2f(fmaf((float)(~w), 2.3283064365386963e-10f, 1.1641532182693481e-10f));
-                                x = (acc + b) - cS * (lu - l1);         // 2(a+b) - T ln(u/(1-u)) >= 0
-                            } else {
-                                x = (acc + b) + cS * lu * (float)olds[j];  // 2(a+b) - (-ln u) T s_old >= 0
-                            }
-                            up = !(x < 0.f);
+                        double x = 0.0;
+                        if (u < p.nout) {
+                            const double f = p.fluct_mode == ISB_FLUCT_SHARED ? p.F[p.k * p.nout + u]
+                                                                               : p.F[((int64_t)r * p.nsteps + p.k) * p.nout + u];
+                            double ft = __dmul_rn(f, Td);
+                            if (p.rule == ISB_BIP_MA) ft = ((oldw[j >> 1] >> (16 * (j & 1) + 15)) & 1u) ? -ft : ft;
+                            x = __dsub_rn(__dmul_rn(2.0, __dadd_rn((double)__uint_as_float(v[j]), p.bias[u])), ft);
                         }
-                        upmask |= (up ? 1u : 0u) << j;
+                        sgn[j] = (x < 0.0) ? 0x80000000u : 0u;
+                    }
+                } else {
+                    float bf[16];
+                    if (full) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias_f + u0) + q);
+                            bf[4 * q] = b4.x; bf[4 * q + 1] = b4.y; bf[4 * q + 2] = b4.z; bf[4 * q + 3] = b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) bf[j] = u0 + j < p.nout ? __ldg(p.bias_f + u0 + j) : 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const Philox4 blk =
+                            philox_unit_block(p.seed, p.domain, (uint32_t)r, p.step_abs, (uint32_t)(((p.u_off + u0) >> 2) + q));
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = q * 4 + e;
+                            const uint32_t w = philox_pick(blk, (uint32_t)e);
+                            const float x = __uint_as_float(v[j]) + bf[j];
+                            const float u = fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (w+1/2) 2^-32
+                            float t;
+                            if (Tf == 0.f) {
+                                t = x;  // no noise: sgn+(x)
+                            } else if (p.rule == ISB_BIP_SCA) {
+                                // 2x - T ln(u/(1-u)) >= 0  <=>  u (1 + e^{-2x/T}) <= 1   (one MUFU.EX2)
+                                t = 1.0f - fmaf(u, exp2f(cE * x), u);
+                            } else {
+                                // 2x - (-ln u) T s_old >= 0  <=>  x + (T/2) ln(u) s_old >= 0
+                                const float l = cS * __log2f(u);
+                                t = x + (((oldw[j >> 1] >> (16 * (j & 1) + 15)) & 1u) ? -l : l);
+                            }
+                            sgn[j] = (t < 0.f) ? 0x80000000u : 0u;  // NaN (0 * inf) cannot occur: u > 0, finite x
+                        }
                     }
                 }
-                // pack: bf16 +-1 = 0x3F80 / 0xBF80, int8 +-1 = 0x01 / 0xFF
-                uint32_t wb[8], wi[4];
+                // bf16 +-1 = 0x3F80 | sign
+                uint32_t wb[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t lo = (upmask >> (2 * j)) & 1u, hi = (upmask >> (2 * j + 1)) & 1u;
-                    wb[j] = (lo ? 0x3F80u : 0xBF80u) | ((hi ? 0x3F80u : 0xBF80u) << 16);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t x = 0;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) x |= (((upmask >> (4 * j + e)) & 1u) ? 0x01u : 0xFFu) << (8 * e);
-                    wi[j] = x;
-                }
+                for (int j = 0; j < 8; ++j) wb[j] = 0x3F803F80u | (sgn[2 * j] >> 16) | sgn[2 * j + 1];
                 if (full) {
                     *reinterpret_cast<uint4 *>(ob) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
                     *reinterpret_cast<uint4 *>(ob + 8) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
-                    *reinterpret_cast<uint4 *>(oi) = make_uint4(wi[0], wi[1], wi[2], wi[3]);
                 } else {
-                    for (int j = 0; j < 16 && u0 + j < p.nout; ++j) {
-                        const bool up = (upmask >> j) & 1u;
-                        ob[j] = __ushort_as_bfloat16(up ? (unsigned short)0x3F80 : (unsigned short)0xBF80);
-                        oi[j] = up ? (int8_t)1 : (int8_t)-1;
-                    }
+                    for (int j = 0; j < 16 && u0 + j < p.nout; ++j)
+                        ob[j] = __ushort_as_bfloat16((unsigned short)((wb[j >> 1] >> (16 * (j & 1))) & 0xFFFFu));
                 }
             }
             tc_fence_before();
@@ -319,6 +316,29 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
+    }
+}
+
+__global__ void bias_to_float_kernel(const double *b, int n, int npad, float *o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npad) o[i] = i < n ? (float)b[i] : 0.f;
+}
+static int make_float_bias(isb_ctx *ctx, const double *d_b, int n, float **out) {
+    const int npad = (n + 15) / 16 * 16;
+    ISB_CUDA(ctx, cudaMalloc(out, (size_t)npad * sizeof(float)));
+    bias_to_float_kernel<<<(npad + 255) / 256, 256, 0, ctx->stream>>>(d_b, n, npad, *out);
+    ISB_CUDA(ctx, cudaGetLastError());
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+
+// bf16 +-1 operand matrix -> canonical int8 spins
+__global__ void bf16_to_spins_kernel(const __nv_bfloat16 *b, int64_t ldb, int8_t *s, int64_t lds, int n, int R) {
+    const int64_t total = (int64_t)R * n;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / n;
+        const int u = (int)(idx % n);
+        s[r * lds + u] = (__bfloat16_as_ushort(b[r * ldb + u]) & 0x8000u) ? (int8_t)-1 : (int8_t)1;
     }
 }
 
@@ -439,7 +459,9 @@ int bip_tc_model_init(isb_model *m, const double *W /*[nv][nh] row-major*/) {
         t->mapWt[term] = t->mapWt[0];
         t->mapWn[term] = t->mapWn[0];
     }
-    return ISB_OK;
+    int rc = make_float_bias(ctx, m->bb64, nh, &t->bias_hf);
+    if (rc) return rc;
+    return make_float_bias(ctx, m->hb64, nv, &t->bias_vf);
 }
 
 void bip_tc_model_free(isb_model *m) {
@@ -449,6 +471,8 @@ void bip_tc_model_free(isb_model *m) {
         cudaFree(t->Wt[i]);
         cudaFree(t->Wn[i]);
     }
+    cudaFree(t->bias_hf);
+    cudaFree(t->bias_vf);
     delete t;
     m->tc = nullptr;
 }
@@ -496,12 +520,12 @@ static int launch_half(isb_ens *e, int layer, int rule, int fluct_mode, const do
     const CUtensorMap *mapA, *mapB;
     if (layer == 1) {  // hidden from visible
         p.nout = m->nh; p.kin = m->nv; p.bn = t->bn_h;
-        p.out_bf = s->Sh; p.ldo = t->ldkh; p.out_i8 = e->hidden; p.ldi = e->ldh; p.bias = m->bb64;
+        p.out_bf = s->Sh; p.ldo = t->ldkh; p.bias = m->bb64; p.bias_f = t->bias_hf;
         p.domain = DOM_BIP_HIDDEN;
         mapA = &s->mapSv; mapB = t->mapWt;
     } else {           // visible from hidden
         p.nout = m->nv; p.kin = m->nh; p.bn = t->bn_v;
-        p.out_bf = s->Sv; p.ldo = t->ldkv; p.out_i8 = e->spins; p.ldi = e->lds; p.bias = m->hb64;
+        p.out_bf = s->Sv; p.ldo = t->ldkv; p.bias = m->hb64; p.bias_f = t->bias_vf;
         p.domain = DOM_BIP_VISIBLE;
         mapA = &s->mapSh; mapB = t->mapWn;
     }
@@ -601,11 +625,13 @@ int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q)
         int rc = make_map(ctx, &t->mapWt[term], t->Wt[src], nb, n, n, t->bn_h);
         if (rc) return rc;
     }
-    return ISB_OK;
+    int rc = make_float_bias(ctx, m->bb64, nb, &t->bias_hf);
+    if (rc) return rc;
+    return make_float_bias(ctx, m->hb64, nb, &t->bias_vf);
 }
 
-int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *in_full, void *out_block, int8_t *own_i8,
-                          uint64_t seed, uint64_t step_abs, double T) {
+int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *in_full, void *out_block, uint64_t seed,
+                          uint64_t step_abs, double T) {
     isb_ctx *ctx = m->ctx;
     TcModel *t = (TcModel *)m->tc;
     CUtensorMap mapA;
@@ -626,9 +652,8 @@ int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *
     p.bn = t->bn_h;
     p.out_bf = (__nv_bfloat16 *)out_block;
     p.ldo = m->shard_nb;
-    p.out_i8 = own_i8;
-    p.ldi = m->shard_nb;
     p.bias = layer == 1 ? m->bb64 : m->hb64;
+    p.bias_f = layer == 1 ? t->bias_hf : t->bias_vf;
     p.domain = layer == 1 ? DOM_BIP_HIDDEN : DOM_BIP_VISIBLE;
     p.u_off = m->shard_g * m->shard_nb;
     p.n_tiles = (p.nout + p.bn - 1) / p.bn;
@@ -652,8 +677,16 @@ int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, cons
     // the canonical int8 visible layer is the input of the first half-step; the hidden bf16 matrix is
     // produced by it (MomentumAnnealing reads the hidden layer's previous value from the int8 array)
     spins_to_bf16_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(e->spins, e->lds, s->Sv, t->ldkv, m->nv, e->R);
+    spins_to_bf16_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(e->hidden, e->ldh, s->Sh, t->ldkh, m->nh, e->R);
     ISB_CUDA(ctx, cudaGetLastError());
-    e->last_launches += 1;
+    e->last_launches += 2;
+    auto sync_canonical = [&]() -> int {  // bf16 operand matrices -> the ensemble's int8 spins
+        bf16_to_spins_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(s->Sv, t->ldkv, e->spins, e->lds, m->nv, e->R);
+        bf16_to_spins_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(s->Sh, t->ldkh, e->hidden, e->ldh, m->nh, e->R);
+        ISB_CUDA(ctx, cudaGetLastError());
+        e->last_launches += 2;
+        return ISB_OK;
+    };
     int64_t ntr = 0;
     for (int64_t k = 0; k < nsteps; ++k) {
         int rc = launch_half(e, 1, rule, fluct_mode, d_Fh, nsteps, k, d_T, steps_per_T, seed, step_offset + (uint64_t)k);
@@ -661,13 +694,15 @@ int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, cons
         rc = launch_half(e, 0, rule, fluct_mode, d_Fv, nsteps, k, d_T, steps_per_T, seed, step_offset + (uint64_t)k);
         if (rc) return rc;
         if (d_E && trace_every > 0 && (k + 1) % trace_every == 0) {
+            rc = sync_canonical();
+            if (rc) return rc;
             rc = bip_energy_device(e, d_E + ntr * e->R);
             if (rc) return rc;
             e->last_launches += 1;
             ++ntr;
         }
     }
-    return ISB_OK;
+    return sync_canonical();
 }
 
 }  // namespace isb

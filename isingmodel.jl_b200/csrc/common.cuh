@@ -57,6 +57,36 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
         : "memory");
 }
 
+// Multicast variant: the bytes land at the same CTA-relative offset in every CTA of `cta_mask`, and each
+// destination CTA's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void bulk_g2s_multicast(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,
+                                                   uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+// ------------------------------------------------------------------ thread-block clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same offset in CTA `target` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t target) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(target)
+        : "memory");
+}
+
 // ------------------------------------------------------------------ warp helpers
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -114,17 +144,22 @@ __host__ __device__ __forceinline__ Philox4 philox_unit_block(uint64_t seed, uin
                          (uint32_t)(seed >> 32));
 }
 
-// u in (0,1): (w + 1/2) 2^-32 — exactly representable, never 0 or 1.
-__device__ __forceinline__ double u_from_word(uint32_t w) {
-    return __dmul_rn(__dadd_rn((double)w, 0.5), 2.3283064365386962890625e-10);
+// u in (0,1): (w + 1/2) 2^-32, never 0 or 1; 1 - u = (~w + 1/2) 2^-32 exactly.
+// The variates are evaluated in single precision with the hardware log2 (two MUFU) and returned as doubles:
+// the Float64 decision arithmetic downstream is unchanged, the fluctuation itself carries ~2^-22 relative
+// error, far below the 2^-32 granularity of u in the tails that matter.  isb_philox_*_fluct dump exactly these
+// values, so parity tests feed the oracle the same doubles.
+__device__ __forceinline__ float u_from_word_f(uint32_t w) {
+    return fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 // Logistic(0,1) by inversion: log(u / (1-u))   (GlauberDynamics / SCA: SingleSpinFlip.jl:43, OnBipartiteGraph.jl:15)
 __device__ __forceinline__ double logistic_from_word(uint32_t w) {
-    const double u = u_from_word(w);
-    return log(__ddiv_rn(u, __dsub_rn(1.0, u)));
+    return (double)(0.69314718055994531f * (__log2f(u_from_word_f(w)) - __log2f(u_from_word_f(~w))));
 }
 // Exponential(1) by inversion: -log(u)         (MetropolisMethod / MomentumAnnealing: SingleSpinFlip.jl:62, OnBipartiteGraph.jl:50)
-__device__ __forceinline__ double exponential_from_word(uint32_t w) { return -log(u_from_word(w)); }
+__device__ __forceinline__ double exponential_from_word(uint32_t w) {
+    return (double)(-0.69314718055994531f * __log2f(u_from_word_f(w)));
+}
 
 // fluctuation of a rule from a word: rule ids follow ising_b200.h (0 Hopfield, 1 Glauber, 2 Metropolis)
 __device__ __forceinline__ double ssf_fluct_from_word(int rule, uint32_t w) {

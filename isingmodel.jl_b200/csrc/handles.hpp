@@ -25,7 +25,7 @@ struct isb_ctx {
     isb_devbuf scratch[12];      // grow-only device staging buffers (see isb::dev_reserve)
 };
 
-enum { ISB_KIND_DENSE = 0, ISB_KIND_BIPARTITE = 1, ISB_KIND_SHARD = 2 };
+enum { ISB_KIND_DENSE = 0, ISB_KIND_BIPARTITE = 1, ISB_KIND_SHARD = 2, ISB_KIND_SPARSE = 3 };
 
 struct isb_model {
     std::atomic<int> refs{1};    // the creator + every live ensemble
@@ -49,6 +49,8 @@ struct isb_model {
     void *tc = nullptr;
     // ---- row-sharded symmetric SCA (kind SHARD): this rank owns units [shard_g*shard_nb, (shard_g+1)*shard_nb)
     int shard_nb = 0, shard_G = 0, shard_g = 0;
+    // ---- sparse general-graph model (kind SPARSE): CSR rows of the symmetric J, owned by sparse.cu
+    void *sp = nullptr;
 };
 
 struct isb_ens {
@@ -100,6 +102,15 @@ int dense_energy_device(isb_ens *e, double *d_E);
 int dense_field_device(isb_ens *e, double *d_F, int64_t ld);  // natural J s + h in double
 int magnetization_device(isb_ens *e, double *d_M);
 
+// sparse.cu
+int sparse_model_init(isb_model *m, int n, const int64_t *colptr, const int32_t *rowval, const double *nzval, int *warn);
+void sparse_model_free(isb_model *m);
+int sparse_field_device(isb_ens *e, double *d_out, int64_t ld, int nout, double hsign);
+int sparse_energy_device(isb_ens *e, double *d_E);
+int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *d_nodes, int start,
+                          int fluct_mode, const double *d_fluct, uint64_t seed, uint64_t step_offset, const double *d_T,
+                          int64_t steps_per_T, int64_t trace_every, double *d_E, double *d_M);
+
 // bip_exact.cu
 int bip_run_exact_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv,
                          const double *d_Fh, uint64_t seed, uint64_t step_offset, const double *d_T,
@@ -115,8 +126,8 @@ void bip_tc_model_free(isb_model *m);
 int bip_tc_ens_init(isb_ens *e);
 void bip_tc_ens_free(isb_ens *e);
 int shard_model_init(isb_model *m, const double *Wrows /*[nb][n] or NULL*/, uint64_t seed, double q);
-int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *in_full, void *out_block, int8_t *own_i8,
-                          uint64_t seed, uint64_t step_abs, double T);
+int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *in_full, void *out_block, uint64_t seed,
+                          uint64_t step_abs, double T);
 int sk_rows_device(isb_ctx *ctx, int n, uint64_t seed, int row0, int nrows, double *d_out);
 int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv,
                       const double *d_Fh, uint64_t seed, uint64_t step_offset, const double *d_T,

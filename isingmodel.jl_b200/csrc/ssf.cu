@@ -11,12 +11,12 @@
 
 namespace isb {
 
-cudaError_t launch_ssf_dd(const SsfParams &p, int npl, bool list, bool tma, int grid, int threads, size_t smem,
-                          cudaStream_t st);
-cudaError_t launch_ssf_df(const SsfParams &p, int npl, bool list, bool tma, int grid, int threads, size_t smem,
-                          cudaStream_t st);
-cudaError_t launch_ssf_ff(const SsfParams &p, int npl, bool list, bool tma, int grid, int threads, size_t smem,
-                          cudaStream_t st);
+cudaError_t launch_ssf_dd(const SsfParams &p, int npl, bool list, bool tma, int cl, int grid, int threads,
+                          size_t smem, cudaStream_t st);
+cudaError_t launch_ssf_df(const SsfParams &p, int npl, bool list, bool tma, int cl, int grid, int threads,
+                          size_t smem, cudaStream_t st);
+cudaError_t launch_ssf_ff(const SsfParams &p, int npl, bool list, bool tma, int cl, int grid, int threads,
+                          size_t smem, cudaStream_t st);
 
 size_t ssf_field_elem_size(const isb_model *m) { return m->prec == ISB_PREC_F32 ? sizeof(float) : sizeof(double); }
 
@@ -174,7 +174,7 @@ int dense_field_device(isb_ens *e, double *d_F, int64_t ld) {
 }
 int magnetization_device(isb_ens *e, double *d_M) {
     isb_model *m = e->model;
-    const int n = m->kind == ISB_KIND_DENSE ? m->n : m->nv;
+    const int n = (m->kind == ISB_KIND_DENSE || m->kind == ISB_KIND_SPARSE) ? m->n : m->nv;
     magnetization_kernel<<<(e->R + 7) / 8, 256, 0, m->ctx->stream>>>(e->spins, e->lds, n, e->R, d_M);
     ISB_CUDA(m->ctx, cudaGetLastError());
     return ISB_OK;
@@ -238,7 +238,15 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
     int NG = (int)((ctx->smem_optin - 2048) / ((size_t)SSF_G * rowb));
     NG = std::min(NG, 8);
     if (NG < 2) tma = false;
-    const size_t smem = tma ? (size_t)NG * SSF_G * rowb + (size_t)2 * NG * sizeof(uint64_t) : 0;
+    const size_t smem = tma ? (size_t)NG * SSF_G * rowb + (size_t)(3 * NG + 2) * sizeof(uint64_t) + 16 : 0;
+    // thread-block clusters: one multicast J-row stream per cluster of `cl` CTAs (L2 -> SM traffic / cl)
+    int cl = 1;  // measured on B200: the per-SM ingest of the row stream is the limit, multicast does not lift it
+    const char *env_cl = getenv("ISB_SSF_CLUSTER");
+    if (env_cl && tma) {
+        const int v = atoi(env_cl);
+        cl = (v == 2 || v == 4) ? v : 1;
+    }
+    if (cl > 1) ctas = (ctas + cl - 1) / cl * cl;  // padding CTAs own no chains but take part in the protocol
 
     SsfParams p{};
     p.J = m->Jperm;
@@ -269,19 +277,21 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
     p.tie_eps = e->tie_eps;
     p.nw = nw;
     p.NG = NG;
+    p.od_ratio = 0.8f;
+    if (const char *env_od = getenv("ISB_SSF_OD_RATIO")) p.od_ratio = (float)atof(env_od);
 
     const bool list = order != ISB_ORDER_SEQUENTIAL;
     const int threads = 32 * (nw + 1);
     cudaError_t ce;
     if (hd && !jf)
-        ce = launch_ssf_dd(p, npl, list, tma, ctas, threads, smem, ctx->stream);
+        ce = launch_ssf_dd(p, npl, list, tma, cl, ctas, threads, smem, ctx->stream);
     else if (hd && jf)
-        ce = launch_ssf_df(p, npl, list, tma, ctas, threads, smem, ctx->stream);
+        ce = launch_ssf_df(p, npl, list, tma, cl, ctas, threads, smem, ctx->stream);
     else
-        ce = launch_ssf_ff(p, npl, list, tma, ctas, threads, smem, ctx->stream);
+        ce = launch_ssf_ff(p, npl, list, tma, cl, ctas, threads, smem, ctx->stream);
     if (ce != cudaSuccess)
-        return fail(ctx, ISB_ERR_CUDA, "ssf_kernel launch failed: %s (grid %d x %d threads, %zu B smem)",
-                    cudaGetErrorString(ce), ctas, threads, smem);
+        return fail(ctx, ISB_ERR_CUDA, "ssf_kernel launch failed: %s (grid %d x %d threads, %zu B smem, cluster %d)",
+                    cudaGetErrorString(ce), ctas, threads, smem, cl);
     e->last_launches += 1;
     return ISB_OK;
 }

@@ -55,7 +55,14 @@ struct SsfParams {
     double tie_eps;
     int nw;  // consumer warps (chains) per CTA
     int NG;  // ring slots
+    // Adaptive row delivery (TMA kernels): the run is cut into epochs of SSF_EPOCH steps.  In a *streamed* epoch
+    // the producer pushes every visited row through the ring (cost: one row per step per CTA, shared by its
+    // chains); in an *on-demand* epoch each chain reads the rows of its own accepted flips straight from L2
+    // (cost: one row per flip per chain).  After each epoch the CTA compares its flip count with the step
+    // count and streams the next epoch iff flips >= od_ratio * steps (low temperatures go on-demand).
+    float od_ratio;
 };
+constexpr int SSF_EPOCH = 1024;
 
 // consumer warps (chains) per CTA for a chain that keeps `field_regs` 32-bit registers of local
 // fields per lane: 15 warps -> 128 registers/thread, 21 -> 96, 29 -> 64 (one CTA per SM, +1 producer warp)
@@ -84,22 +91,32 @@ struct alignas(sizeof(JT) * VEC) JPack {
     JT v[VEC];
 };
 
-// binary select tree: hf[k] with k known only at run time, without dynamic register indexing
-template <typename HT, int LO, int CNT>
-struct FieldSel {
-    static __device__ __forceinline__ HT get(const HT *hf, int k) {
-        if constexpr (CNT == 1) {
-            return hf[LO];
-        } else {
-            const HT a = FieldSel<HT, LO, CNT / 2>::get(hf, k);
-            const HT b = FieldSel<HT, LO + CNT / 2, CNT / 2>::get(hf, k);
-            return (k & (CNT / 2)) ? b : a;
-        }
+// hf[k] with k known only at run time and WARP-UNIFORM (k = site / 32): a jump table, not a select tree and
+// not dynamic register indexing
+template <typename HT, int NPL>
+__device__ __forceinline__ HT field_sel(const HT (&hf)[NPL], int k) {
+    HT v = hf[0];
+#define ISB_CASE(i) \
+    case i:         \
+        if constexpr (i < NPL) v = hf[i < NPL ? i : 0]; \
+        break;
+    switch (k) {
+        ISB_CASE(1) ISB_CASE(2) ISB_CASE(3) ISB_CASE(4) ISB_CASE(5) ISB_CASE(6) ISB_CASE(7) ISB_CASE(8)
+        ISB_CASE(9) ISB_CASE(10) ISB_CASE(11) ISB_CASE(12) ISB_CASE(13) ISB_CASE(14) ISB_CASE(15) ISB_CASE(16)
+        ISB_CASE(17) ISB_CASE(18) ISB_CASE(19) ISB_CASE(20) ISB_CASE(21) ISB_CASE(22) ISB_CASE(23) ISB_CASE(24)
+        ISB_CASE(25) ISB_CASE(26) ISB_CASE(27) ISB_CASE(28) ISB_CASE(29) ISB_CASE(30) ISB_CASE(31)
+        default: break;
     }
-};
+#undef ISB_CASE
+    return v;
+}
 
-template <typename HT, typename JT, int NPL, bool LIST, bool TMA>
+// CL > 1: the CTAs of a thread-block cluster (same GPC) walk the same row sequence, so the leader CTA's
+// producer issues each J row ONCE as a multicast bulk copy that lands in every CTA's ring (one L2 read for CL
+// SMs).  Followers arm their own full barriers and tell the leader (remote mbarrier arrive) when their slot is free.
+template <typename HT, typename JT, int NPL, bool LIST, bool TMA, int CL = 1>
 __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(const SsfParams p) {
+    static_assert(CL == 1 || TMA, "clusters only make sense with the TMA ring");
     constexpr int G = SSF_G;
     constexpr int NPAD = NPL * 32;
     constexpr int ROWB = NPAD * (int)sizeof(JT);
@@ -111,6 +128,12 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
     JT *ring = reinterpret_cast<JT *>(smem_raw);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)p.NG * G * ROWB);
     uint64_t *empty_bar = full_bar + p.NG;
+    uint64_t *peer_bar = empty_bar + p.NG;  // leader only: followers' "slot armed and free" arrivals
+    uint64_t *ep_bar = peer_bar + p.NG;     // consumers -> producer: "epoch finished" (count = chains of this CTA)
+    uint64_t *go_bar = ep_bar + 1;          // producer -> consumers: "mode of the next epoch decided"
+    unsigned int *ep_flips = reinterpret_cast<unsigned int *>(go_bar + 1);  // flips of the CTA in the current epoch
+    volatile int *ep_mode = reinterpret_cast<volatile int *>(ep_flips + 1); // 1 = streamed, 0 = on demand
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nw = p.nw;
@@ -123,44 +146,87 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
         if (threadIdx.x == 0) {
             for (int s = 0; s < NG; ++s) {
                 mbar_init(&full_bar[s], 1);
-                mbar_init(&empty_bar[s], (uint32_t)nactive);
+                mbar_init(&empty_bar[s], (uint32_t)(nactive > 0 ? nactive : 1));
+                if constexpr (CL > 1) mbar_init(&peer_bar[s], CL - 1);
             }
+            mbar_init(ep_bar, (uint32_t)(nactive > 0 ? nactive : 1));
+            mbar_init(go_bar, 1);
+            *ep_flips = 0u;
+            *ep_mode = 1;
             mbar_fence_init();
         }
-        __syncthreads();
+        if constexpr (CL > 1)
+            cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive / multicast
+        else
+            __syncthreads();
     }
 
     // ------------------------------------------------------------------ producer warp
     if (warp == nw) {
         if constexpr (TMA) {
             if (lane == 0) {
-                const int64_t nq = (p.nsteps + G - 1) / G;
+                // Adaptive delivery is decided per CTA; inside a cluster all CTAs must stream the same epochs, so
+                // clusters always stream.
+                const bool adaptive = CL == 1 && p.od_ratio > 0.f && nactive > 0;
                 int site = p.start;
                 int slot = 0;
-                uint32_t ph = 0;  // slot = q % NG, ph = (q / NG) & 1, kept incrementally (no 64-bit divisions)
-                for (int64_t q = 0; q < nq; ++q) {
-                    mbar_wait(&empty_bar[slot], ph ^ 1u);
-                    const int64_t left = p.nsteps - q * G;
-                    const int rows = left < G ? (int)left : G;
-                    mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(rows * ROWB));
-                    for (int g = 0; g < rows; ++g) {
-                        int i;
-                        if constexpr (LIST) {
-                            i = __ldg(&p.nodes[q * G + g]);
-                        } else {
-                            i = site;
-                            if (++site == p.n) site = 0;
-                        }
-                        bulk_g2s(ring + ((size_t)slot * G + g) * NPAD, Jg + (int64_t)i * p.ldj, ROWB,
-                                 &full_bar[slot]);
+                uint32_t ph = 0;  // (slot, ph) of the next streamed group, kept incrementally (no 64-bit divisions)
+                int64_t issued = 0;
+                uint32_t ep = 0;
+                for (int64_t t0 = 0; t0 < p.nsteps; t0 += SSF_EPOCH, ++ep) {
+                    const int64_t esteps = p.nsteps - t0 < SSF_EPOCH ? p.nsteps - t0 : SSF_EPOCH;
+                    bool stream = true;
+                    if (adaptive && ep > 0) {
+                        mbar_wait(ep_bar, (ep - 1) & 1u);  // every chain of the CTA has finished epoch ep - 1
+                        stream = (float)(*ep_flips) >= p.od_ratio * (float)SSF_EPOCH;
+                        *ep_flips = 0u;
+                        *ep_mode = stream ? 1 : 0;
+                        mbar_arrive(go_bar);
                     }
-                    if (++slot == NG) {
-                        slot = 0;
-                        ph ^= 1u;
+                    if (!stream) {
+                        if constexpr (!LIST) site = (int)(((int64_t)site + esteps) % p.n);
+                        continue;
+                    }
+                    const int64_t nq = (esteps + G - 1) / G;
+                    for (int64_t q = 0; q < nq; ++q, ++issued) {
+                        // slot free in this CTA: its chains released the group that used it NG groups ago (a CTA
+                        // without chains instead waits until that group's bytes have landed, so the barrier is
+                        // never armed twice per phase)
+                        if (nactive > 0)
+                            mbar_wait(&empty_bar[slot], ph ^ 1u);
+                        else if (issued >= NG)
+                            mbar_wait(&full_bar[slot], ph ^ 1u);
+                        const int64_t left = esteps - q * G;
+                        const int rows = left < G ? (int)left : G;
+                        mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(rows * ROWB));
+                        if (CL > 1 && crank != 0) {
+                            mbar_arrive_remote(&peer_bar[slot], 0);  // armed and free: the leader may multicast into it
+                        } else {
+                            if constexpr (CL > 1) mbar_wait(&peer_bar[slot], ph);
+                            for (int g = 0; g < rows; ++g) {
+                                int i;
+                                if constexpr (LIST) {
+                                    i = __ldg(&p.nodes[t0 + q * G + g]);
+                                } else {
+                                    i = site;
+                                    if (++site == p.n) site = 0;
+                                }
+                                if constexpr (CL > 1)
+                                    bulk_g2s_multicast(ring + ((size_t)slot * G + g) * NPAD, Jg + (int64_t)i * p.ldj,
+                                                       ROWB, &full_bar[slot], (uint16_t)((1u << CL) - 1u));
+                                else
+                                    bulk_g2s(ring + ((size_t)slot * G + g) * NPAD, Jg + (int64_t)i * p.ldj, ROWB,
+                                             &full_bar[slot]);
+                            }
+                        }
+                        if (++slot == NG) {
+                            slot = 0;
+                            ph ^= 1u;
+                        }
                     }
                 }
-                // no bulk copy may still be in flight when the CTA retires: wait for the last min(nq, NG) groups
-                const int last = (int)(nq < NG ? nq : NG);
+                // no bulk copy may still be in flight when the CTA retires: wait for the last min(issued, NG) groups
+                const int last = (int)(issued < NG ? issued : NG);
                 for (int b = 0; b < last; ++b) {
                     if (--slot < 0) {
                         slot = NG - 1;
@@ -170,9 +236,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 }
             }
         }
-        return;
-    }
-    if (warp >= nactive) return;
+    } else if (warp < nactive) {
 
     // ------------------------------------------------------------------ consumer warp = one chain
     const int r = first_chain + warp;
@@ -191,43 +255,79 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
     const int rule = p.rule;
     const bool audit = p.tie_eps > 0.0;
     unsigned long long nflips = 0, nties = 0;
-    int64_t qcur = -1;  // ring group currently held; cslot = qcur % NG, cph = (qcur / NG) & 1 (incremental)
+    // Ring position of this chain within the current (streamed) epoch: qcur = group of the epoch being read
+    // (-1: none yet), held = it has not been released; cslot / cph walk the ring across epochs (only streamed
+    // groups are ever pushed, so producer and chains stay in step).  te = steps done in the current epoch.
+    int qcur = -1;
+    bool held = false;
     int cslot = -1;
     uint32_t cph = 0;
+    bool stream = TMA;  // delivery mode of the current epoch
+    int te = 0;
+    uint32_t ep_idx = 0;
+    unsigned int ep_nflips = 0;
+    const bool adaptive = TMA && CL == 1 && p.od_ratio > 0.f;
 
-    // make group q the held one: release the previous groups in order, wait for each new one
-    auto advance_to = [&](int64_t q) {
+    auto release_held = [&]() {
+        if (held) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[cslot]);
+            held = false;
+        }
+    };
+    // make group q of this epoch the held one: release the previous groups in order, wait for each new one
+    auto advance_to = [&](int q) {
         if constexpr (TMA) {
             while (qcur < q) {
-                if (qcur >= 0) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[cslot]);
-                }
+                release_held();
                 ++qcur;
                 if (++cslot == NG) {
                     cslot = 0;
                     cph ^= 1u;
                 }
                 mbar_wait(&full_bar[cslot], cph);
+                held = true;
             }
         }
     };
-    // row of J for step t (visiting `site`; its group must be the held one): ring slot when streamed by TMA,
-    // global memory otherwise
-    auto row_ptr = [&](int64_t t, int site) -> const JT * {
+    // called when te == SSF_EPOCH (t = global step count): finish the epoch, learn the next one's delivery mode
+    auto epoch_boundary = [&](int64_t t) {
         if constexpr (TMA) {
-            return ring + ((size_t)cslot * G + (size_t)((int)t & (G - 1))) * NPAD;
-        } else {
-            return Jg + (int64_t)site * p.ldj;
+            if (stream) {
+                advance_to((SSF_EPOCH - 1) / G);  // consume (and then release) every group of the epoch
+                release_held();
+            }
+            qcur = -1;
+            nflips += ep_nflips;
+            if (adaptive && t < p.nsteps) {
+                __syncwarp();
+                if (lane == 0) {
+                    atomicAdd(ep_flips, ep_nflips);
+                    mbar_arrive(ep_bar);
+                }
+                mbar_wait(go_bar, ep_idx & 1u);
+                stream = *ep_mode != 0;
+            }
+            ep_nflips = 0;
+            ++ep_idx;
+            te = 0;
         }
     };
-    // fields += d * J[row]
+    // fields += d * J[row], in batches of at most 8 vector loads (32 registers in flight): the compiler barrier
+    // keeps it from hoisting all NCH loads above the FMAs, which would spill the register-resident fields
     auto apply_row = [&](const JT *row, HT d) {
+        constexpr int BATCH = NCH < 8 ? NCH : 8;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const JPack<JT, VEC> pk = *reinterpret_cast<const JPack<JT, VEC> *>(row + c * 32 * VEC + lane * VEC);
+        for (int c0 = 0; c0 < NCH; c0 += BATCH) {
+            JPack<JT, VEC> pk[BATCH];
 #pragma unroll
-            for (int b = 0; b < VEC; ++b) hf[c * VEC + b] += d * (HT)pk.v[b];
+            for (int c = 0; c < BATCH; ++c)
+                pk[c] = *reinterpret_cast<const JPack<JT, VEC> *>(row + (c0 + c) * 32 * VEC + lane * VEC);
+#pragma unroll
+            for (int c = 0; c < BATCH; ++c)
+#pragma unroll
+                for (int b = 0; b < VEC; ++b) hf[(c0 + c) * VEC + b] += d * (HT)pk[c].v[b];
+            asm volatile("" ::: "memory");
         }
     };
     auto write_trace = [&](int64_t idx) {
@@ -272,6 +372,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
             if (p.n - site < len) len = p.n - site;
             if (p.nsteps - t < len) len = (int)(p.nsteps - t);
             if (next_trace - t < len) len = (int)(next_trace - t);
+            if (TMA && SSF_EPOCH - te < len) len = SSF_EPOCH - te;
             const int off = lane - l_first;
             const bool mine = off >= 0 && off < len;
             // temperature of my step
@@ -305,7 +406,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
             const double ftl = __dmul_rn(f, Tl);
             bool mybit = (sw >> k) & 1u;
             // hk mirrors hf[k] (my own site's field) for this block; both receive identical updates
-            HT hk = FieldSel<HT, 0, NPL>::get(hf, k);
+            HT hk = field_sel<HT, NPL>(hf, k);
             const int kpos = (k / VEC) * (32 * VEC) + lane * VEC + (k % VEC);
             uint32_t rem = __ballot_sync(FULL, mine);
             while (true) {
@@ -322,17 +423,24 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 const int l0 = __ffs(fm) - 1;
                 const uint32_t upto = (2u << l0) - 1u;  // lanes <= l0 (l0 == 31 -> all ones)
                 const bool up = (__ballot_sync(FULL, nb) >> l0) & 1u;
-                const int64_t tt = t + (l0 - l_first);
-                advance_to(tt / G);
-                const JT *row = row_ptr(tt, k * 32 + l0);
                 const HT d = up ? (HT)2 : (HT)-2;
+                // one update path over a generic pointer (ring slot or L2): two specialised copies (LDS / LDG)
+                // made ptxas hoist 16 x LDG.128 above the FMAs and spill the register-resident fields
+                const JT *row;
+                if (TMA && stream) {
+                    const int se = te + (l0 - l_first);  // step within the epoch
+                    advance_to(se / G);
+                    row = ring + ((size_t)cslot * G + (size_t)(se & (G - 1))) * NPAD;
+                } else {
+                    row = Jg + (int64_t)(k * 32 + l0) * p.ldj;
+                }
                 hk += d * (HT)row[kpos];
                 apply_row(row, d);
                 if (lane == l0) {
                     sw ^= 1u << k;
                     mybit = !mybit;
                 }
-                ++nflips;
+                ++ep_nflips;
                 rem &= ~upto;
                 if (rem == 0) break;
             }
@@ -344,11 +452,13 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 ti += tr / spT;
                 tr %= spT;
             }
-            advance_to((t - 1) / G);
+            te += len;
+            if (TMA && stream) advance_to((te - 1) / G);
             if (t == next_trace) {
                 write_trace(trace_idx++);
                 next_trace += p.trace_every;
             }
+            if (TMA && te == SSF_EPOCH) epoch_boundary(t);
         }
     } else {
         // ---------------------------------------------------------- explicit site list, one step at a time
@@ -385,19 +495,23 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
             const int k = site >> 5, l = site & 31;
             const double ft = __dmul_rn(f, Tcur);
             const bool mybit = (sw >> k) & 1u;
-            const double h2 = 2.0 * (double)FieldSel<HT, 0, NPL>::get(hf, k);
+            const double h2 = 2.0 * (double)field_sel<HT, NPL>(hf, k);
             const double fts = metro ? (mybit ? ft : -ft) : ft;
             const double x = __dsub_rn(h2, fts);
             const bool nb = !(x < 0.0);
             uint32_t code = (nb != mybit ? 1u : 0u) | (nb ? 2u : 0u) | (fabs(x) < p.tie_eps ? 4u : 0u);
             code = __shfl_sync(FULL, code, l);
             if (audit) nties += (code >> 2) & 1u;
-            advance_to(t / G);
+            if (TMA && stream) advance_to(te / G);
             if (code & 1u) {
-                apply_row(row_ptr(t, site), (code & 2u) ? (HT)2 : (HT)-2);
+                const HT d = (code & 2u) ? (HT)2 : (HT)-2;
+                apply_row((TMA && stream) ? ring + ((size_t)cslot * G + (size_t)(te & (G - 1))) * NPAD
+                                          : Jg + (int64_t)site * p.ldj,
+                          d);
                 if (lane == l) sw ^= 1u << k;
-                ++nflips;
+                ++ep_nflips;
             }
+            ++te;
             if (++tr == spT) {
                 tr = 0;
                 ++ti;
@@ -406,6 +520,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 write_trace(trace_idx++);
                 next_trace += p.trace_every;
             }
+            if (TMA && te == SSF_EPOCH) epoch_boundary(t + 1);
         }
     }
 
@@ -419,10 +534,13 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
             if (k * 32 + lane < p.n) sr[k * 32 + lane] = ((sw >> k) & 1u) ? (int8_t)1 : (int8_t)-1;
         }
         if (lane == 0) {
-            p.flips[r] = nflips;
+            p.flips[r] = nflips + ep_nflips;
             if (nties) atomicAdd(p.near_ties, nties);
         }
     }
+    }  // consumer warp
+    // no CTA of the cluster may retire while a peer can still multicast into its ring or arrive on its barriers
+    if constexpr (CL > 1) cluster_sync_all();
 }
 
 }  // namespace isb

@@ -49,9 +49,9 @@ class RowShardedSCA:
         bf = torch.bfloat16
         self.full_v = torch.zeros((self.G, self.R, self.nb), dtype=bf, device=self.dev)
         self.full_h = torch.zeros((self.G, self.R, self.nb), dtype=bf, device=self.dev)
-        self.blk = [torch.zeros((self.R, self.nb), dtype=bf, device=self.dev) for _ in self.blocks]
-        self.own_v = [torch.ones((self.R, self.nb), dtype=torch.int8, device=self.dev) for _ in self.blocks]
-        self.own_h = [torch.ones((self.R, self.nb), dtype=torch.int8, device=self.dev) for _ in self.blocks]
+        # this rank's freshly sampled blocks, one per layer (they also hold the block's previous values)
+        self.blk_v = [torch.ones((self.R, self.nb), dtype=bf, device=self.dev) for _ in self.blocks]
+        self.blk_h = [torch.ones((self.R, self.nb), dtype=bf, device=self.dev) for _ in self.blocks]
         self.launches = 0
         self.gather_bytes = 0
 
@@ -64,8 +64,8 @@ class RowShardedSCA:
         self.full_v.copy_(full.to(torch.bfloat16))
         self.full_h.copy_(self.full_v)
         for i, g in enumerate(self.blocks):
-            self.own_v[i].copy_(full[g])
-            self.own_h[i].copy_(full[g])
+            self.blk_v[i].copy_(self.full_v[g])
+            self.blk_h[i].copy_(self.full_v[g])
 
     def get_spins(self):
         """(R, n) int8 visible layer (identical on every rank after the all-gather)."""
@@ -79,18 +79,17 @@ class RowShardedSCA:
     # ---- one half-step: every owned block samples its units, then the blocks are exchanged
     def _half(self, layer, seed, step_abs, T):
         src, dst = (self.full_v, self.full_h) if layer == 1 else (self.full_h, self.full_v)
-        own = self.own_h if layer == 1 else self.own_v
+        blk = self.blk_h if layer == 1 else self.blk_v
         for i, m in enumerate(self.models):
-            m.shard_halfstep(self.R, layer, self.rule, src.data_ptr(), self.blk[i].data_ptr(), own[i].data_ptr(), seed,
-                             step_abs, T)
+            m.shard_halfstep(self.R, layer, self.rule, src.data_ptr(), blk[i].data_ptr(), seed, step_abs, T)
             self.launches += 1
         if self.distributed:
             # the one real exchange step of this path: [R][nb] per rank -> [G][R][nb] everywhere
-            self.dist.all_gather_into_tensor(dst.view(-1), self.blk[0].view(-1), group=self.group)
-            self.gather_bytes += (self.G - 1) * self.blk[0].numel() * 2
+            self.dist.all_gather_into_tensor(dst.view(-1), blk[0].view(-1), group=self.group)
+            self.gather_bytes += (self.G - 1) * blk[0].numel() * 2
         else:
             for i, g in enumerate(self.blocks):
-                dst[g].copy_(self.blk[i])
+                dst[g].copy_(blk[i])
 
     def run(self, nsteps, T, *, seed=0, step_offset=0):
         """nsteps synchronous SCA steps; T: array of nsteps temperatures (T[k] applies to step k)."""

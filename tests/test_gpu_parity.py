@@ -45,10 +45,10 @@ def test_philox_streams(ctx):
     for i, r in enumerate((3, 4)):
         w = oracle_np.philox_word(seed, 1 << 28, r, steps)
         u = oracle_np.uniform_from_word(w)
-        assert np.allclose(fl[i], np.log(u / (1 - u)), rtol=1e-14, atol=1e-15)
+        assert np.allclose(fl[i], np.log(u / (1 - u)), rtol=4e-6, atol=4e-6)  # variates evaluated in fp32 on the device
     fe = ctx.philox_fluct(L.RULE_METROPOLIS, seed, off, 0, 1, 64)
     u = oracle_np.uniform_from_word(oracle_np.philox_word(seed, 1 << 28, 0, steps))
-    assert np.allclose(fe[0], -np.log(u), rtol=1e-14)
+    assert np.allclose(fe[0], -np.log(u), rtol=4e-6, atol=4e-6)
     nd = ctx.philox_nodes(1000, seed, off, 64)
     w = oracle_np.philox_word(seed, 2 << 28, 0, steps)
     assert np.array_equal(nd, ((w.astype(np.uint64) * np.uint64(1000)) >> np.uint64(32)).astype(np.int32))

@@ -1,0 +1,113 @@
+"""GPU parity tests of the sparse-coupling single-spin path (isb_model_sparse) against the CPU oracle (which
+takes the same J densified): bit-exact spins / flips / magnetisation, energies to 1e-9."""
+import numpy as np
+import pytest
+
+from cases import golden_J, nodes_of
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b):
+    return np.all(np.abs(a - b) <= 1e-9 * np.maximum(1.0, np.abs(b)))
+
+
+def _lib():
+    from isingmodel_jl_b200 import _lib
+    return _lib
+
+
+def _random_sparse(synth, n, deg, seed, integer):
+    """Symmetric sparse J with about `deg` neighbours per site."""
+    import scipy.sparse as sp
+    m = n * deg // 2
+    i = synth.nodes(seed, n, m)
+    j = synth.nodes(seed + 1, n, m)
+    v = synth.gaussian(seed + 2, m)
+    if integer:
+        v = np.round(v * 2.0)
+    keep = i != j
+    A = sp.coo_matrix((v[keep], (i[keep], j[keep])), shape=(n, n)).tocsr()
+    A = sp.triu(A + A.T, 1)
+    A = (A + A.T).tocsc()
+    A.eliminate_zeros()
+    return A
+
+
+@pytest.mark.parametrize("name", ["ssf_2spin_glauber", "ssf_3x3_metropolis", "ssf_c1_32x32_metropolis", "ssf_sk64_glauber",
+                                  "ssf_sk64_hopfield"])
+def test_sparse_golden(ctx, synth, name):
+    import scipy.sparse as sp
+    L = _lib()
+    g = load_golden(name)
+    J = golden_J(name, g, synth)
+    m = L.Model.sparse(ctx, sp.csc_matrix(J), g["h"])
+    e = L.Ensemble(m, 1)
+    e.set_spins(g["s0"][None, :])
+    out = e.ssf_run(int(g["rule"]), int(g["nsteps"]), nodes=nodes_of(g), fluct=g["fluct"], T=g["T"],
+                    steps_per_T=int(g["steps_per_T"]), trace_every=int(g["trace_every"]))
+    assert np.array_equal(e.get_spins()[0], g["s_final"])
+    assert int(out["flips"][0]) == int(g["flips"])
+    assert np.array_equal(out["M"][:, 0], g["M"])
+    assert _close(out["E"][:, 0], g["E"]) and _close(e.energy()[0], g["E"][-1])
+
+
+CASES = [(50, 4, 1, "seq", 7, 50 * 9 + 3, True), (300, 6, 2, "list", 33, 2500, True), (1024, 4, 2, "seq", 200, 1024 * 3, False),
+         (2000, 8, 1, "seq", 64, 2000 * 2 + 11, False), (5000, 3, 0, "seq", 9, 5000, True), (777, 10, 1, "list", 50, 3000, False)]
+
+
+@pytest.mark.parametrize("n,deg,rule,order,R,nsteps,integer", CASES)
+def test_sparse_batched_bit_exact(ctx, orc, synth, n, deg, rule, order, R, nsteps, integer):
+    L = _lib()
+    A = _random_sparse(synth, n, deg, 40 + n, integer)
+    J = A.toarray()
+    h = synth.gaussian(5, n) * 0.3
+    S0 = synth.spins(6, R, n)
+    nodes = synth.nodes(7, n, nsteps) if order == "list" else None
+    fl = synth.logistic(8, (R, nsteps)) if rule == 1 else (synth.exponential(8, (R, nsteps)) if rule == 2 else None)
+    T = synth.geometric_schedule(2.0, 0.2, 5)
+    spT = (nsteps + 4) // 5
+    e = L.Ensemble(L.Model.sparse(ctx, A, h), R)
+    e.set_spins(S0)
+    tr = max(1, nsteps // 2)
+    out = e.ssf_run(rule, nsteps, nodes=nodes, start=n // 2 if order == "seq" else 0, fluct=fl, fluct_per_replica=True,
+                    T=T, steps_per_T=spT, trace_every=tr)
+    S = e.get_spins()
+    for r in range(min(R, 12)):
+        s, flips, E, M = orc.ssf_run(rule, J, h, S0[r], nsteps, nodes=nodes, start=n // 2 if order == "seq" else 0,
+                                     fluct=None if fl is None else fl[r], T=T, steps_per_T=spT, trace_every=tr)
+        assert np.array_equal(s, S[r]) and flips == out["flips"][r]
+        assert np.array_equal(M, out["M"][:, r]) and _close(out["E"][:, r], E)
+    Eg = e.energy()
+    assert _close(Eg[:4], np.array([orc.energy(J, h, S[r]) for r in range(4)]))
+    F = e.local_field()
+    assert np.array_equal(F[0], orc.local_field(J, h, S[0]))
+
+
+def test_sparse_equals_dense_path(ctx, synth):
+    """The same lattice through the sparse and the dense kernels, Philox noise: identical trajectories."""
+    import scipy.sparse as sp
+    L = _lib()
+    J = synth.lattice_J(32)
+    S0 = synth.spins(1, 64, 1024)
+    T = np.full(8, 2.269)
+    res = []
+    for model in (L.Model.dense(ctx, J, np.zeros(1024), L.PREC_AUTO), L.Model.sparse(ctx, sp.csc_matrix(J), np.zeros(1024))):
+        e = L.Ensemble(model, 64)
+        e.set_spins(S0)
+        out = e.ssf_run(L.RULE_METROPOLIS, 8 * 1024, seed=9, T=T, steps_per_T=1024, trace_every=1024)
+        res.append((e.get_spins(), out["flips"], out["E"]))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert _close(res[0][2], res[1][2])
+
+
+def test_reference_style_sparse_system(pkg, ctx):
+    """SpinSystem built from a scipy sparse matrix (the reference's tests use sparse(...)) stays sparse on the GPU."""
+    import scipy.sparse as sp
+    ss = pkg.SpinSystems.SpinSystem([-1, +1], sp.csc_matrix(np.array([[0, 1], [1, 0]])), [0, 0])
+    assert pkg.SpinSystems.calcEnergy(ss) == 1.0
+    assert ss._model.kind == "sparse"
+    ua = pkg.SingleSpinFlip.GlauberDynamics(ss, 0.0)
+    pkg.SingleSpinFlip.update_(ua, 0, 0.0)
+    assert ss.spinConfiguration.tolist() == [1, 1] and pkg.SpinSystems.calcEnergy(ss) == -1.0

@@ -83,3 +83,17 @@ def test_replica_range(pkg):
         assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
         sizes = [hi - lo for lo, hi in parts]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_sparse_input_validation(pkg):
+    import scipy.sparse as sp
+    SS = pkg.SpinSystems
+    J = sp.csc_matrix(np.array([[0, 1, 0], [1, 0, 2.0], [0, 2.0, 0]]))
+    ss = SS.SpinSystem([1, -1, 1], J, np.zeros(3))
+    assert ss._sparse and ss.couplingCoefficients.nnz == 4
+    with pytest.warns(UserWarning, match="should be symmetric"):
+        ss = SS.SpinSystem([1, -1, 1], sp.csc_matrix(np.array([[0, 1, 2.0], [5, 0, 3], [6, 7, 0]])), np.zeros(3))
+    assert np.array_equal(ss.couplingCoefficients.toarray(), np.array([[0, 1, 2], [1, 0, 3], [2, 3, 0.0]]))
+    with pytest.warns(UserWarning, match="diagonal"):
+        ss = SS.SpinSystem([1, -1], sp.csc_matrix(np.array([[4.0, 1], [1, 9.0]])), np.zeros(2))
+    assert not ss.couplingCoefficients.diagonal().any()
