@@ -252,6 +252,24 @@ int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const doub
         }
         cudaError_t ce = cudaStreamSynchronize(ctx->stream);
         if (ce != cudaSuccess) rc = fail(ctx, ISB_ERR_CUDA, "isb_model_dense: upload failed: %s", cudaGetErrorString(ce));
+        if (!rc && !fast) {
+            // N > 1024: the register-resident sweep kernel does not apply; sweeps run through the neighbour-list
+            // kernel (sparse.cu) over the nonzero couplings, fields in shared memory
+            std::vector<int64_t> colptr((size_t)n + 1, 0);
+            std::vector<int32_t> rowval;
+            std::vector<double> nzval;
+            for (int j = 0; j < n; ++j) {
+                for (int i = 0; i < n; ++i) {
+                    const double v = Jn[(size_t)i * npad + j];
+                    if (v != 0.0) {
+                        rowval.push_back(i);
+                        nzval.push_back(v);
+                    }
+                }
+                colptr[j + 1] = (int64_t)rowval.size();
+            }
+            rc = isb::sparse_model_init(m, n, colptr.data(), rowval.data(), nzval.data(), nullptr);
+        }
     } while (0);
     if (rc) {
         isb_model_destroy(m);
@@ -406,8 +424,8 @@ int isb_ens_create(isb_model *m, int R, isb_ens **out) {
             e->lds = m->npad;
             ce = cudaMalloc(&e->spins, (size_t)R * e->lds);
             if (ce == cudaSuccess) ce = cudaMemsetAsync(e->spins, 1, (size_t)R * e->lds, ctx->stream);
-            if (ce == cudaSuccess && (m->fast_ok || m->kind == ISB_KIND_SPARSE))
-                ce = cudaMalloc(&e->fields, (size_t)R * m->npad * isb::ssf_field_elem_size(m));
+            if (ce == cudaSuccess)
+                ce = cudaMalloc(&e->fields, (size_t)R * m->npad * (m->fast_ok ? isb::ssf_field_elem_size(m) : sizeof(double)));
         } else {
             e->lds = (m->nv + 15) / 16 * 16;
             e->ldh = (m->nh + 15) / 16 * 16;
@@ -645,7 +663,7 @@ int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *
         ISB_TRY(isb::philox_nodes_device(ctx, m->n, seed, step_offset, nsteps, d_nodes));
         e->last_launches += 1;
     }
-    if (m->kind == ISB_KIND_SPARSE)
+    if (m->kind == ISB_KIND_SPARSE || !m->fast_ok)
         ISB_TRY(isb::ssf_sparse_run_device(e, rule, nsteps, order, d_nodes, start, fluct_mode, d_fluct, seed, step_offset,
                                            d_T, steps_per_T, (d_E || d_M) ? trace_every : 0, d_E, d_M));
     else

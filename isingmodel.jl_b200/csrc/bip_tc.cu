@@ -21,6 +21,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <utility>
 #include <vector>
 
@@ -54,22 +56,79 @@ struct TcEns {
     CUtensorMap mapSv, mapSh;
 };
 
-struct TcParams {
-    int R, nout, kin, bn, n_tiles, m_tiles, num_kb, P;
+// One layer update (= one GEMM shape): which units are sampled, from which input layer
+struct TcLayer {
+    int nout, kin, bn, n_tiles, num_kb;
     int u_off;        // global index of output unit 0 (row-sharded models: this rank's block offset), else 0
     int kb_per_blk;   // K blocks per slab of the A operand (block-major [G][R][nb] spin matrices), else num_kb
-    double T_direct;  // temperature when Tsched is NULL
-    int rule, fluct_mode;
-    __nv_bfloat16 *out_bf;   // [R][ldo]
+    __nv_bfloat16 *out_bf;   // [R][ldo] the sampled layer (on entry: its previous values, read by MomentumAnnealing)
     int64_t ldo;
     const double *bias;      // [nout]
     const float *bias_f;     // [nout rounded up to 16] the same in float (Philox mode)
     const double *F;         // external fluctuations (f64) or NULL
-    int64_t nsteps, k;
+    uint32_t domain;         // Philox stream of this layer
+};
+struct TcParams {
+    TcLayer L[2];     // [1] = hidden from visible, [0] = visible from hidden (persistent mode uses both)
+    int R, P, rule, fluct_mode;
+    // work decomposition.  persist == 0: one half-step (layer `layer`), tiles (m_blk, n_blk) strided over the grid.
+    // persist == 1: chain-resident: CTA c owns the replicas [c*rows_per_cta, (c+1)*rows_per_cta) and runs
+    // `nsteps_seg` full steps (hidden then visible) on them without leaving the SM — chains are independent, so
+    // no grid-wide synchronisation exists; only the CTA's own producer waits for its own epilogue.
+    int persist, layer, m_tiles, rows_per_cta, nsteps_seg;
+    int64_t nsteps, k0;      // steps of the whole run (fluctuation array pitch), first step of this launch
     const double *Tsched;
     int64_t steps_per_T;
-    uint64_t seed, step_abs;
-    uint32_t domain;
+    double T_direct;         // temperature when Tsched is NULL
+    uint64_t seed, step_abs0;  // Philox step of k0
+};
+
+// The tile jobs of a CTA, enumerated identically by the producer, the MMA issuer and the epilogue warps.
+struct TcJob {
+    int layer, m0, n_blk, hs;   // hs = half-step index within the launch (0 when !persist)
+    int64_t k;                  // step index within the run
+    bool hs_first, hs_last;
+};
+struct TcJobIter {
+    int tile, layer, n_blk, step;
+    __device__ __forceinline__ void init(const TcParams &p) {
+        tile = blockIdx.x;
+        layer = 1;
+        n_blk = 0;
+        step = 0;
+    }
+    __device__ __forceinline__ bool next(const TcParams &p, TcJob &j) {
+        if (!p.persist) {
+            const int nt = p.L[p.layer].n_tiles;
+            if (tile >= p.m_tiles * nt) return false;
+            j.layer = p.layer;
+            j.m0 = (tile / nt) * TC_BM;
+            j.n_blk = tile % nt;
+            j.hs = 0;
+            j.k = p.k0;
+            j.hs_first = j.hs_last = false;
+            tile += gridDim.x;
+            return true;
+        }
+        if (step >= p.nsteps_seg) return false;
+        j.layer = layer;
+        j.m0 = blockIdx.x * p.rows_per_cta;
+        j.n_blk = n_blk;
+        j.hs = 2 * step + (layer == 1 ? 0 : 1);
+        j.k = p.k0 + step;
+        j.hs_first = n_blk == 0;
+        j.hs_last = n_blk == p.L[layer].n_tiles - 1;
+        if (++n_blk == p.L[layer].n_tiles) {
+            n_blk = 0;
+            if (layer == 1) {
+                layer = 0;
+            } else {
+                layer = 1;
+                ++step;
+            }
+        }
+        return true;
+    }
 };
 
 // ------------------------------------------------------------------ PTX wrappers (tcgen05 / TMA)
@@ -130,10 +189,15 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int bn) {
 }
 
 // ------------------------------------------------------------------ the kernel
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+struct TcMaps {
+    CUtensorMap A[2];     // input spin matrix of layer update [1] (visible layer) and [0] (hidden layer)
+    CUtensorMap B[2][3];  // coupling terms of the two orientations
+};
+
 template <bool EXTF>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
-              const __grid_constant__ CUtensorMap mapB1, const __grid_constant__ CUtensorMap mapB2, const TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
@@ -141,11 +205,10 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     uint64_t *empty_bar = bars + TC_STAGES;        // [TC_STAGES]
     uint64_t *tfull_bar = bars + 2 * TC_STAGES;    // [2]
     uint64_t *tempty_bar = bars + 2 * TC_STAGES + 2;  // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
+    uint64_t *hs_done = bars + 2 * TC_STAGES + 4;  // persistent mode: epilogue -> producer, "half-step written"
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = p.m_tiles * p.n_tiles;
-    const int iters_per_tile = p.num_kb * p.P;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -156,6 +219,7 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], TC_EPI_WARPS);
         }
+        mbar_init(hs_done, TC_EPI_WARPS);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -163,23 +227,28 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    TcJobIter jobs;
+    jobs.init(p);
+    TcJob job;
 
     if (warp == 0) {
         // ================================================================ TMA producer
         if (lane == 0) {
-            const CUtensorMap *mapsB[3] = {&mapB0, &mapB1, &mapB2};
-            const uint32_t tx = (uint32_t)(TC_A_BYTES + p.bn * TC_BK * 2);
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+            while (jobs.next(p, job)) {
+                const TcLayer &L = p.L[job.layer];
+                // chain-resident mode: this half-step's A operand is what the CTA's own epilogue wrote during the
+                // previous half-step (generic-proxy stores, fenced to the async proxy before the arrive)
+                if (p.persist && job.hs_first && job.hs > 0) mbar_wait(hs_done, (uint32_t)(job.hs - 1) & 1u);
+                const uint32_t tx = (uint32_t)(TC_A_BYTES + L.bn * TC_BK * 2);
+                for (int kb = 0; kb < L.num_kb; ++kb) {
                     for (int t = 0; t < p.P; ++t, ++it) {
                         const int s = it % TC_STAGES;
                         mbar_wait(&empty_bar[s], ((it / TC_STAGES) & 1) ^ 1);
                         unsigned char *sa = smem + (size_t)s * TC_STAGE_BYTES;
                         mbar_arrive_expect_tx(&full_bar[s], tx);
-                        tma_load_3d(sa, &mapA, (kb % p.kb_per_blk) * TC_BK, m_blk * TC_BM, kb / p.kb_per_blk, &full_bar[s]);
-                        tma_load_2d(sa + TC_A_BYTES, mapsB[t], kb * TC_BK, n_blk * p.bn, &full_bar[s]);
+                        tma_load_3d(sa, &maps.A[job.layer], (kb % L.kb_per_blk) * TC_BK, job.m0, kb / L.kb_per_blk, &full_bar[s]);
+                        tma_load_2d(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * TC_BK, job.n_blk * L.bn, &full_bar[s]);
                     }
                 }
             }
@@ -187,14 +256,16 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     } else if (warp == 1) {
         // ================================================================ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(p.bn);
             uint32_t it = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            while (jobs.next(p, job)) {
+                const TcLayer &L = p.L[job.layer];
+                const uint32_t idesc = umma_idesc_bf16(L.bn);
+                const int iters = L.num_kb * p.P;
                 const int a = tl & 1;
                 mbar_wait(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN_MAX);
-                for (int i = 0; i < iters_per_tile; ++i, ++it) {
+                for (int i = 0; i < iters; ++i, ++it) {
                     const int s = it % TC_STAGES;
                     mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
                     tc_fence_after();
@@ -207,6 +278,7 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     umma_commit(&empty_bar[s]);  // slot free when these MMAs have read it
                 }
                 umma_commit(&tfull_bar[a]);      // accumulator complete
+                ++tl;
             }
         }
     } else if (warp >= 4) {
@@ -214,26 +286,28 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may read: lanes 32*(warpid % 4) ..
         const int half = ew >> 2;           // the warps of a quadrant interleave the 16-column chunks
-        const double Td = p.Tsched ? p.Tsched[p.k / p.steps_per_T] : p.T_direct;
-        const float Tf = (float)Td;
-        const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2
-        const float cE = Tf > 0.f ? -2.0f * 1.4426950408889634f / Tf : 0.f;  // e^{-2x/T} = 2^{cE x}
-        const int nchunks = p.bn >> 4;
         uint32_t tl = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-            const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+        while (jobs.next(p, job)) {
+            const TcLayer &L = p.L[job.layer];
+            const double Td = p.Tsched ? p.Tsched[job.k / p.steps_per_T] : p.T_direct;
+            const float Tf = (float)Td;
+            const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2
+            const float cE = Tf > 0.f ? -2.0f * 1.4426950408889634f / Tf : 0.f;  // e^{-2x/T} = 2^{cE x}
+            const uint64_t step_abs = p.step_abs0 + (uint64_t)(job.k - p.k0);
+            const int nchunks = L.bn >> 4;
             const int a = tl & 1;
             mbar_wait(&tfull_bar[a], (tl >> 1) & 1);
             tc_fence_after();
-            const int r = m_blk * TC_BM + quad * 32 + lane;
-            const bool row_ok = r < p.R;
+            const int lrow = quad * 32 + lane;
+            const int r = job.m0 + lrow;
+            const bool row_ok = r < p.R && (!p.persist || lrow < p.rows_per_cta);
             for (int c = half; c < nchunks; c += TC_EPI_WARPS / 4) {
                 uint32_t v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TC_BN_MAX + c * 16), v);
-                const int u0 = n_blk * p.bn + c * 16;
-                if (!row_ok || u0 >= p.nout) continue;
-                __nv_bfloat16 *ob = p.out_bf + (int64_t)r * p.ldo + u0;
-                const bool full = u0 + 16 <= p.nout;
+                const int u0 = job.n_blk * L.bn + c * 16;
+                if (!row_ok || u0 >= L.nout) continue;
+                __nv_bfloat16 *ob = L.out_bf + (int64_t)r * L.ldo + u0;
+                const bool full = u0 + 16 <= L.nout;
                 // MomentumAnnealing multiplies the noise by the unit's own previous value: it is still in the
                 // output matrix (bf16 +-1; pad columns read as 0 and are never stored)
                 uint32_t oldw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -248,12 +322,12 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     for (int j = 0; j < 16; ++j) {
                         const int u = u0 + j;
                         double x = 0.0;
-                        if (u < p.nout) {
-                            const double f = p.fluct_mode == ISB_FLUCT_SHARED ? p.F[p.k * p.nout + u]
-                                                                               : p.F[((int64_t)r * p.nsteps + p.k) * p.nout + u];
+                        if (u < L.nout) {
+                            const double f = p.fluct_mode == ISB_FLUCT_SHARED ? L.F[job.k * L.nout + u]
+                                                                               : L.F[((int64_t)r * p.nsteps + job.k) * L.nout + u];
                             double ft = __dmul_rn(f, Td);
                             if (p.rule == ISB_BIP_MA) ft = ((oldw[j >> 1] >> (16 * (j & 1) + 15)) & 1u) ? -ft : ft;
-                            x = __dsub_rn(__dmul_rn(2.0, __dadd_rn((double)__uint_as_float(v[j]), p.bias[u])), ft);
+                            x = __dsub_rn(__dmul_rn(2.0, __dadd_rn((double)__uint_as_float(v[j]), L.bias[u])), ft);
                         }
                         sgn[j] = (x < 0.0) ? 0x80000000u : 0u;
                     }
@@ -262,17 +336,17 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     if (full) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias_f + u0) + q);
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(L.bias_f + u0) + q);
                             bf[4 * q] = b4.x; bf[4 * q + 1] = b4.y; bf[4 * q + 2] = b4.z; bf[4 * q + 3] = b4.w;
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) bf[j] = u0 + j < p.nout ? __ldg(p.bias_f + u0 + j) : 0.f;
+                        for (int j = 0; j < 16; ++j) bf[j] = u0 + j < L.nout ? __ldg(L.bias_f + u0 + j) : 0.f;
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const Philox4 blk =
-                            philox_unit_block(p.seed, p.domain, (uint32_t)r, p.step_abs, (uint32_t)(((p.u_off + u0) >> 2) + q));
+                            philox_unit_block(p.seed, L.domain, (uint32_t)r, step_abs, (uint32_t)(((L.u_off + u0) >> 2) + q));
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int j = q * 4 + e;
@@ -302,13 +376,21 @@ bip_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     *reinterpret_cast<uint4 *>(ob) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
                     *reinterpret_cast<uint4 *>(ob + 8) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
                 } else {
-                    for (int j = 0; j < 16 && u0 + j < p.nout; ++j)
+                    for (int j = 0; j < 16 && u0 + j < L.nout; ++j)
                         ob[j] = __ushort_as_bfloat16((unsigned short)((wb[j >> 1] >> (16 * (j & 1))) & 0xFFFFu));
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[a]);
+            if (p.persist && job.hs_last) {
+                // the layer this CTA just wrote is the next half-step's TMA operand: order the generic-proxy
+                // stores before the async-proxy reads, then tell the producer
+                fence_proxy_async_global();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(hs_done);
+            }
+            ++tl;
         }
     }
     tc_fence_before();
@@ -499,54 +581,94 @@ void bip_tc_ens_free(isb_ens *e) {
     e->tc = nullptr;
 }
 
-static int launch_half(isb_ens *e, int layer, int rule, int fluct_mode, const double *d_F, int64_t nsteps, int64_t k,
-                       const double *d_T, int64_t steps_per_T, uint64_t seed, uint64_t step_abs) {
+static void fill_layer(TcLayer &L, int nout, int kin, int bn, __nv_bfloat16 *out_bf, int64_t ldo, const double *bias,
+                       const float *bias_f, const double *F, uint32_t domain) {
+    L.nout = nout;
+    L.kin = kin;
+    L.bn = bn;
+    L.n_tiles = (nout + bn - 1) / bn;
+    L.num_kb = (kin + TC_BK - 1) / TC_BK;
+    L.u_off = 0;
+    L.kb_per_blk = L.num_kb;
+    L.out_bf = out_bf;
+    L.ldo = ldo;
+    L.bias = bias;
+    L.bias_f = bias_f;
+    L.F = F;
+    L.domain = domain;
+}
+
+static int launch_tc(isb_ctx *ctx, const TcMaps &maps, const TcParams &p, int grid, bool extf) {
+    if (extf) {
+        ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        bip_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(maps, p);
+    } else {
+        ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        bip_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(maps, p);
+    }
+    ISB_CUDA(ctx, cudaGetLastError());
+    return ISB_OK;
+}
+
+// Steps [k0, k0 + nseg) of a run: one chain-resident launch when the replicas fill the SMs, else 2 * nseg
+// half-step launches.
+static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv, const double *d_Fh, int64_t nsteps,
+                        int64_t k0, int64_t nseg, const double *d_T, int64_t steps_per_T, uint64_t seed,
+                        uint64_t step_offset) {
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
     TcModel *t = (TcModel *)m->tc;
     TcEns *s = (TcEns *)e->tc;
+    TcMaps maps;
+    maps.A[1] = s->mapSv;
+    maps.A[0] = s->mapSh;
+    for (int i = 0; i < 3; ++i) {
+        maps.B[1][i] = t->mapWt[i];
+        maps.B[0][i] = t->mapWn[i];
+    }
     TcParams p{};
+    fill_layer(p.L[1], m->nh, m->nv, t->bn_h, s->Sh, t->ldkh, m->bb64, t->bias_hf, d_Fh, DOM_BIP_HIDDEN);
+    fill_layer(p.L[0], m->nv, m->nh, t->bn_v, s->Sv, t->ldkv, m->hb64, t->bias_vf, d_Fv, DOM_BIP_VISIBLE);
     p.R = e->R;
     p.P = t->P;
     p.rule = rule;
     p.fluct_mode = fluct_mode;
-    p.F = d_F;
     p.nsteps = nsteps;
-    p.k = k;
     p.Tsched = d_T;
     p.steps_per_T = steps_per_T;
     p.seed = seed;
-    p.step_abs = step_abs;
-    const CUtensorMap *mapA, *mapB;
-    if (layer == 1) {  // hidden from visible
-        p.nout = m->nh; p.kin = m->nv; p.bn = t->bn_h;
-        p.out_bf = s->Sh; p.ldo = t->ldkh; p.bias = m->bb64; p.bias_f = t->bias_hf;
-        p.domain = DOM_BIP_HIDDEN;
-        mapA = &s->mapSv; mapB = t->mapWt;
-    } else {           // visible from hidden
-        p.nout = m->nv; p.kin = m->nh; p.bn = t->bn_v;
-        p.out_bf = s->Sv; p.ldo = t->ldkv; p.bias = m->hb64; p.bias_f = t->bias_vf;
-        p.domain = DOM_BIP_VISIBLE;
-        mapA = &s->mapSh; mapB = t->mapWn;
+    p.m_tiles = (e->R + TC_BM - 1) / TC_BM;
+    const bool extf = fluct_mode != ISB_FLUCT_PHILOX;
+    // chain-resident mode pays off when every SM gets a (nearly) full 128-row block of replicas to itself
+    int rows = (e->R + ctx->num_sms - 1) / ctx->num_sms;
+    rows = std::min(rows, TC_BM);
+    bool persist = rows >= 96;
+    if (const char *env = getenv("ISB_TC_PERSIST")) persist = atoi(env) != 0 && e->R >= 1;
+    if (persist) {
+        p.persist = 1;
+        p.rows_per_cta = rows;
+        p.nsteps_seg = (int)nseg;
+        p.k0 = k0;
+        p.step_abs0 = step_offset + (uint64_t)k0;
+        const int grid = (e->R + rows - 1) / rows;
+        int rc = launch_tc(ctx, maps, p, grid, extf);
+        if (rc) return rc;
+        e->last_launches += 1;
+        return ISB_OK;
     }
-    p.n_tiles = (p.nout + p.bn - 1) / p.bn;
-    p.m_tiles = (p.R + TC_BM - 1) / TC_BM;
-    p.num_kb = (p.kin + TC_BK - 1) / TC_BK;
-    p.kb_per_blk = p.num_kb;
-    p.u_off = 0;
-    const int grid = std::min(p.n_tiles * p.m_tiles, ctx->num_sms);
-    if (fluct_mode == ISB_FLUCT_PHILOX) {
-        ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        bip_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(*mapA, mapB[0], mapB[1], mapB[2], p);
-    } else {
-        ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        bip_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(*mapA, mapB[0], mapB[1], mapB[2], p);
-    }
-    ISB_CUDA(ctx, cudaGetLastError());
-    e->last_launches += 1;
+    for (int64_t k = k0; k < k0 + nseg; ++k)
+        for (int layer = 1; layer >= 0; --layer) {
+            p.persist = 0;
+            p.layer = layer;
+            p.k0 = k;
+            p.step_abs0 = step_offset + (uint64_t)k;
+            const int grid = std::min(p.L[layer].n_tiles * p.m_tiles, ctx->num_sms);
+            int rc = launch_tc(ctx, maps, p, grid, extf);
+            if (rc) return rc;
+            e->last_launches += 1;
+        }
     return ISB_OK;
 }
-
 
 // ------------------------------------------------------------------ row-sharded symmetric SCA (BASELINE config 5)
 // Global problem: N spins, W = (J + qI)/2 symmetric (the MultiSpinFlip embedding, demo.jl:82-90), R replicas.
@@ -634,10 +756,19 @@ int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *
                           uint64_t step_abs, double T) {
     isb_ctx *ctx = m->ctx;
     TcModel *t = (TcModel *)m->tc;
-    CUtensorMap mapA;
-    int rc = make_map_a(ctx, &mapA, in_full, m->shard_G, R, m->shard_nb, m->shard_nb);
+    TcMaps maps;
+    int rc = make_map_a(ctx, &maps.A[layer], in_full, m->shard_G, R, m->shard_nb, m->shard_nb);
     if (rc) return rc;
+    maps.A[1 - layer] = maps.A[layer];
+    for (int i = 0; i < 3; ++i) maps.B[0][i] = maps.B[1][i] = t->mapWt[i];  // W is symmetric: one orientation
     TcParams p{};
+    fill_layer(p.L[layer], m->shard_nb, m->nv, t->bn_h, (__nv_bfloat16 *)out_block, m->shard_nb,
+               layer == 1 ? m->bb64 : m->hb64, layer == 1 ? t->bias_hf : t->bias_vf, nullptr,
+               layer == 1 ? DOM_BIP_HIDDEN : DOM_BIP_VISIBLE);
+    p.L[layer].u_off = m->shard_g * m->shard_nb;
+    p.L[layer].num_kb = m->nv / TC_BK;
+    p.L[layer].kb_per_blk = m->shard_nb / TC_BK;
+    p.L[1 - layer] = p.L[layer];
     p.R = R;
     p.P = t->P;
     p.rule = rule;
@@ -646,25 +777,12 @@ int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *
     p.T_direct = T;
     p.steps_per_T = 1;
     p.seed = seed;
-    p.step_abs = step_abs;
-    p.nout = m->shard_nb;
-    p.kin = m->nv;
-    p.bn = t->bn_h;
-    p.out_bf = (__nv_bfloat16 *)out_block;
-    p.ldo = m->shard_nb;
-    p.bias = layer == 1 ? m->bb64 : m->hb64;
-    p.bias_f = layer == 1 ? t->bias_hf : t->bias_vf;
-    p.domain = layer == 1 ? DOM_BIP_HIDDEN : DOM_BIP_VISIBLE;
-    p.u_off = m->shard_g * m->shard_nb;
-    p.n_tiles = (p.nout + p.bn - 1) / p.bn;
+    p.step_abs0 = step_abs;
+    p.persist = 0;
+    p.layer = layer;
     p.m_tiles = (R + TC_BM - 1) / TC_BM;
-    p.num_kb = p.kin / TC_BK;
-    p.kb_per_blk = m->shard_nb / TC_BK;
-    const int grid = std::min(p.n_tiles * p.m_tiles, ctx->num_sms);
-    ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    bip_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(mapA, t->mapWt[0], t->mapWt[1], t->mapWt[2], p);
-    ISB_CUDA(ctx, cudaGetLastError());
-    return ISB_OK;
+    const int grid = std::min(p.L[layer].n_tiles * p.m_tiles, ctx->num_sms);
+    return launch_tc(ctx, maps, p, grid, false);
 }
 
 int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv, const double *d_Fh,
@@ -688,12 +806,14 @@ int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, cons
         return ISB_OK;
     };
     int64_t ntr = 0;
-    for (int64_t k = 0; k < nsteps; ++k) {
-        int rc = launch_half(e, 1, rule, fluct_mode, d_Fh, nsteps, k, d_T, steps_per_T, seed, step_offset + (uint64_t)k);
+    const bool tracing = d_E && trace_every > 0;
+    for (int64_t k0 = 0; k0 < nsteps;) {
+        const int64_t nseg = tracing ? std::min<int64_t>(trace_every - (k0 % trace_every), nsteps - k0)
+                                     : std::min<int64_t>(nsteps - k0, 1 << 20);
+        int rc = launch_steps(e, rule, fluct_mode, d_Fv, d_Fh, nsteps, k0, nseg, d_T, steps_per_T, seed, step_offset);
         if (rc) return rc;
-        rc = launch_half(e, 0, rule, fluct_mode, d_Fv, nsteps, k, d_T, steps_per_T, seed, step_offset + (uint64_t)k);
-        if (rc) return rc;
-        if (d_E && trace_every > 0 && (k + 1) % trace_every == 0) {
+        k0 += nseg;
+        if (tracing && k0 % trace_every == 0) {
             rc = sync_canonical();
             if (rc) return rc;
             rc = bip_energy_device(e, d_E + ntr * e->R);

@@ -416,3 +416,40 @@ def test_bip_tc_philox_matches_f64_path(ctx, synth):
     # same noise words -> almost every chain follows the identical trajectory
     assert np.mean(np.abs(a - c) < 1e-9 * np.maximum(1, np.abs(a))) > 0.9
     assert abs(a.mean() - c.mean()) < 4 * a.std() / np.sqrt(R)
+
+
+@pytest.mark.parametrize("R,nv,nh", [(300, 160, 96), (19500, 96, 80), (1000, 784, 512)])
+def test_bip_tc_chain_resident_equals_per_half_step_launches(ctx, synth, monkeypatch, R, nv, nh):
+    """The chain-resident persistent kernel (one launch for all steps, each CTA keeps its replicas) must give
+    exactly what the one-launch-per-half-step path gives: same tiles, same K order, same noise words."""
+    L = _lib()
+    W, h, b = synth.bipartite_W(nv, nh, 101, 0.2)
+    S0, T0 = synth.spins(102, R, nv), synth.spins(103, R, nh)
+    nsteps = 5
+    T = synth.geometric_schedule(1.5, 0.4, nsteps)
+    for rule in (0, 1):
+        res = []
+        for persist in ("0", "1"):
+            monkeypatch.setenv("ISB_TC_PERSIST", persist)
+            e = L.Ensemble(L.Model.bipartite(ctx, W, h, b, L.PREC_BF16X3), R)
+            e.set_spins(S0)
+            e.set_hidden(T0)
+            E = e.bip_run(rule, nsteps, seed=42, step_offset=7, T=T, trace_every=2)
+            res.append((e.get_spins(), e.get_hidden(), E, e.last_stats()["launches"]))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+        assert np.array_equal(res[0][2], res[1][2])
+        assert res[1][3] < res[0][3]  # fewer launches in chain-resident mode
+    # caller-supplied fluctuations through the chain-resident kernel vs the oracle-checked exact path at T = 0
+    monkeypatch.setenv("ISB_TC_PERSIST", "1")
+    if R <= 1000:
+        Wi = np.round(W * 10.0)
+        gen = synth.logistic
+        Fv, Fh = gen(104, (3, nv), 1), gen(104, (3, nh), 2)
+        out = []
+        for prec in (L.PREC_F64, L.PREC_BF16X1):
+            e = L.Ensemble(L.Model.bipartite(ctx, Wi, np.round(h * 10), np.round(b * 10), prec), R)
+            e.set_spins(S0)
+            e.set_hidden(T0)
+            e.bip_run(0, 3, Fv=Fv, Fh=Fh, T=np.array([2.0, 1.0, 0.5]))
+            out.append((e.get_spins(), e.get_hidden()))
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])

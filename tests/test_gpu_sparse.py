@@ -111,3 +111,21 @@ def test_reference_style_sparse_system(pkg, ctx):
     ua = pkg.SingleSpinFlip.GlauberDynamics(ss, 0.0)
     pkg.SingleSpinFlip.update_(ua, 0, 0.0)
     assert ss.spinConfiguration.tolist() == [1, 1] and pkg.SpinSystems.calcEnergy(ss) == -1.0
+
+
+def test_dense_model_above_1024_sites(ctx, orc, synth):
+    """Dense J with N > 1024 runs through the neighbour-list kernel (no ISB_ERR_UNSUPPORTED)."""
+    L = _lib()
+    n, R, nsteps = 1500, 6, 1500 * 2
+    J, h = synth.sk_J(n, 3), synth.gaussian(4, n) * 0.1
+    S0 = synth.spins(5, R, n)
+    fl = synth.logistic(6, (R, nsteps))
+    T = np.array([1.5, 0.5])
+    e = L.Ensemble(L.Model.dense(ctx, J, h, L.PREC_F64), R)
+    e.set_spins(S0)
+    out = e.ssf_run(1, nsteps, fluct=fl, fluct_per_replica=True, T=T, steps_per_T=n, trace_every=n)
+    S = e.get_spins()
+    for r in range(R):
+        s, flips, E, M = orc.ssf_run(1, J, h, S0[r], nsteps, fluct=fl[r], T=T, steps_per_T=n, trace_every=n)
+        assert np.array_equal(s, S[r]) and flips == out["flips"][r] and _close(out["E"][:, r], E)
+    assert _close(e.energy(), np.array([orc.energy(J, h, S[r]) for r in range(R)]))
