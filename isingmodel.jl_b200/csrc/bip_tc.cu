@@ -189,6 +189,11 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int bn) {
 }
 
 // ------------------------------------------------------------------ the kernel
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 struct TcMaps {
@@ -286,6 +291,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may read: lanes 32*(warpid % 4) ..
         const int half = ew >> 2;           // the warps of a quadrant interleave the 16-column chunks
+        const PhiloxKeys keys = philox_keys(p.seed);
         uint32_t tl = 0;
         while (jobs.next(p, job)) {
             const TcLayer &L = p.L[job.layer];
@@ -345,8 +351,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const Philox4 blk =
-                            philox_unit_block(p.seed, L.domain, (uint32_t)r, step_abs, (uint32_t)(((L.u_off + u0) >> 2) + q));
+                        // == philox_unit_block(seed, domain, r, step, unit >> 2) with the round keys hoisted
+                        const Philox4 blk = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), (uint32_t)r,
+                                                           (L.domain << 28) | (uint32_t)(((L.u_off + u0) >> 2) + q), keys);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int j = q * 4 + e;
@@ -355,16 +362,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                             const float u = fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (w+1/2) 2^-32
                             float t;
                             if (Tf == 0.f) {
-                                t = x;  // no noise: sgn+(x)
+                                t = x + 0.0f;  // no noise: sgn+(x); the addition turns a -0 accumulator into +0 (tie -> +1)
                             } else if (p.rule == ISB_BIP_SCA) {
                                 // 2x - T ln(u/(1-u)) >= 0  <=>  u (1 + e^{-2x/T}) <= 1   (one MUFU.EX2)
-                                t = 1.0f - fmaf(u, exp2f(cE * x), u);
+                                t = 1.0f - fmaf(u, ex2_approx(cE * x), u);
                             } else {
                                 // 2x - (-ln u) T s_old >= 0  <=>  x + (T/2) ln(u) s_old >= 0
                                 const float l = cS * __log2f(u);
                                 t = x + (((oldw[j >> 1] >> (16 * (j & 1) + 15)) & 1u) ? -l : l);
                             }
-                            sgn[j] = (t < 0.f) ? 0x80000000u : 0u;  // NaN (0 * inf) cannot occur: u > 0, finite x
+                            sgn[j] = __float_as_uint(t) & 0x80000000u;  // t < 0 (t is never NaN: u > 0, x finite; -0 cannot arise)
                         }
                     }
                 }

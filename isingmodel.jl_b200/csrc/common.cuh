@@ -120,6 +120,37 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     }
     return Philox4{c0, c1, c2, c3};
 }
+// Same function with the ten round keys precomputed (they depend on the seed only): saves the 20 key-schedule
+// additions per block in kernels that draw many blocks per thread.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+__host__ __device__ __forceinline__ PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys K;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        K.k0[r] = a;
+        K.k1[r] = b;
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+    }
+    return K;
+}
+__host__ __device__ __forceinline__ Philox4 philox4x32_10k(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                           const PhiloxKeys &K) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[r];
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k1[r];
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
 __host__ __device__ __forceinline__ uint32_t philox_pick(const Philox4 &p, uint32_t w) {
     return w == 0 ? p.x : (w == 1 ? p.y : (w == 2 ? p.z : p.w));
 }
