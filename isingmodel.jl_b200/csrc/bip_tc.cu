@@ -48,7 +48,13 @@ struct TcModel {
     __nv_bfloat16 *Wt[3] = {};         // hidden update operand: [nh][ldkv]  (K = visible units)
     __nv_bfloat16 *Wn[3] = {};         // visible update operand: [nv][ldkh] (K = hidden units)
     CUtensorMap mapWt[3], mapWn[3];
-    int bn_h = 0, bn_v = 0;            // tile widths for the hidden / visible update
+    int bn_h = 0, bn_v = 0;            // default tile widths for the hidden / visible update (least padding)
+    int rows_t = 0, cols_t = 0, rows_n = 0, cols_n = 0;  // shapes of the two operand orientations
+    struct BnMaps {
+        int orient, bn;
+        CUtensorMap m[3];
+    };
+    std::vector<BnMaps> bn_cache;      // tensor maps for other tile widths (the box height is part of the map)
     float *bias_hf = nullptr, *bias_vf = nullptr;  // hidden / visible biases in float, zero padded to 16
 };
 struct TcEns {
@@ -67,6 +73,10 @@ struct TcLayer {
     const float *bias_f;     // [nout rounded up to 16] the same in float (Philox mode)
     const double *F;         // external fluctuations (f64) or NULL
     uint32_t domain;         // Philox stream of this layer
+    // fused all-gather (row-sharded SCA): the sampled block is also stored straight into every peer GPU's
+    // gathered matrix through NVLink-mapped pointers (same [R][ldo] addressing as out_bf), tile by tile
+    int npeer;
+    __nv_bfloat16 *peer[7];
 };
 struct TcParams {
     TcLayer L[2];     // [1] = hidden from visible, [0] = visible from hidden (persistent mode uses both)
@@ -382,6 +392,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 if (full) {
                     *reinterpret_cast<uint4 *>(ob) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
                     *reinterpret_cast<uint4 *>(ob + 8) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
+                    for (int q = 0; q < L.npeer; ++q) {  // peer stores over NVLink overlap the next tile's MMAs
+                        __nv_bfloat16 *pb = L.peer[q] + (int64_t)r * L.ldo + u0;
+                        *reinterpret_cast<uint4 *>(pb) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+                        *reinterpret_cast<uint4 *>(pb + 8) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
+                    }
                 } else {
                     for (int j = 0; j < 16 && u0 + j < L.nout; ++j)
                         ob[j] = __ushort_as_bfloat16((unsigned short)((wb[j >> 1] >> (16 * (j & 1))) & 0xFFFFu));
@@ -505,6 +520,22 @@ static unsigned short bf16_rne(double x, double *back) {
     return h;
 }
 
+// Tile width for a one-launch-per-half-step GEMM: the launch takes waves x bn "column units" of MMA time, so
+// minimise ceil(m_tiles * ceil(nout / bn) / SMs) * bn over the legal widths (multiples of 16 up to 256).
+static int pick_bn_waves(int nout, int m_tiles, int num_sms) {
+    int best = 0;
+    long best_cost = 0;
+    for (int bn = 256; bn >= 64; bn -= 16) {
+        const long tiles = (long)m_tiles * ((nout + bn - 1) / bn);
+        const long cost = ((tiles + num_sms - 1) / num_sms) * bn;
+        if (best == 0 || cost < best_cost) {
+            best = bn;
+            best_cost = cost;
+        }
+    }
+    return best;
+}
+
 static int pick_bn(int nout) {
     const int nt = (nout + TC_BN_MAX - 1) / TC_BN_MAX;
     int bn = ((nout + nt - 1) / nt + 15) / 16 * 16;
@@ -521,6 +552,7 @@ int bip_tc_model_init(isb_model *m, const double *W /*[nv][nh] row-major*/) {
     t->ldkh = (nh + 15) / 16 * 16;
     t->bn_h = pick_bn(nh);
     t->bn_v = pick_bn(nv);
+    t->rows_t = nh; t->cols_t = nv; t->rows_n = nv; t->cols_n = nh;
     std::vector<unsigned short> wt((size_t)nh * t->ldkv), wn((size_t)nv * t->ldkh);
     std::vector<double> res((size_t)nv * nh);
     for (size_t i = 0; i < res.size(); ++i) res[i] = W[i];
@@ -588,6 +620,33 @@ void bip_tc_ens_free(isb_ens *e) {
     e->tc = nullptr;
 }
 
+static int make_map(isb_ctx *ctx, CUtensorMap *map, const void *base, int rows, int cols, int64_t ld, int box_rows);
+// Coupling tensor maps of orientation `orient` (1: Wt, hidden update; 0: Wn, visible update) for tile width bn
+static int get_maps_b(isb_ctx *ctx, TcModel *t, int orient, int bn, CUtensorMap out[3]) {
+    const int dflt = orient == 1 ? t->bn_h : t->bn_v;
+    if (bn == dflt) {
+        for (int i = 0; i < 3; ++i) out[i] = orient == 1 ? t->mapWt[i] : t->mapWn[i];
+        return ISB_OK;
+    }
+    for (auto &c : t->bn_cache)
+        if (c.orient == orient && c.bn == bn) {
+            for (int i = 0; i < 3; ++i) out[i] = c.m[i];
+            return ISB_OK;
+        }
+    TcModel::BnMaps c;
+    c.orient = orient;
+    c.bn = bn;
+    for (int i = 0; i < 3; ++i) {
+        const int src = i < t->P ? i : 0;
+        int rc = orient == 1 ? make_map(ctx, &c.m[i], t->Wt[src], t->rows_t, t->cols_t, t->ldkv, bn)
+                             : make_map(ctx, &c.m[i], t->Wn[src], t->rows_n, t->cols_n, t->ldkh, bn);
+        if (rc) return rc;
+        out[i] = c.m[i];
+    }
+    t->bn_cache.push_back(c);
+    return ISB_OK;
+}
+
 static void fill_layer(TcLayer &L, int nout, int kin, int bn, __nv_bfloat16 *out_bf, int64_t ldo, const double *bias,
                        const float *bias_f, const double *F, uint32_t domain) {
     L.nout = nout;
@@ -603,6 +662,7 @@ static void fill_layer(TcLayer &L, int nout, int kin, int bn, __nv_bfloat16 *out
     L.bias_f = bias_f;
     L.F = F;
     L.domain = domain;
+    L.npeer = 0;
 }
 
 static int launch_tc(isb_ctx *ctx, const TcMaps &maps, const TcParams &p, int grid, bool extf) {
@@ -626,16 +686,26 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     isb_ctx *ctx = m->ctx;
     TcModel *t = (TcModel *)m->tc;
     TcEns *s = (TcEns *)e->tc;
+    const int m_tiles = (e->R + TC_BM - 1) / TC_BM;
+    const bool extf = fluct_mode != ISB_FLUCT_PHILOX;
+    // chain-resident mode pays off when every SM gets a (nearly) full 128-row block of replicas to itself
+    int rows = (e->R + ctx->num_sms - 1) / ctx->num_sms;
+    rows = std::min(rows, TC_BM);
+    bool persist = rows >= 96;
+    if (const char *env = getenv("ISB_TC_PERSIST")) persist = atoi(env) != 0 && e->R >= 1;
+    // tile widths: least padding per CTA in chain-resident mode, fewest (waves x width) otherwise
+    const int bn_h = persist ? t->bn_h : pick_bn_waves(m->nh, m_tiles, ctx->num_sms);
+    const int bn_v = persist ? t->bn_v : pick_bn_waves(m->nv, m_tiles, ctx->num_sms);
     TcMaps maps;
     maps.A[1] = s->mapSv;
     maps.A[0] = s->mapSh;
-    for (int i = 0; i < 3; ++i) {
-        maps.B[1][i] = t->mapWt[i];
-        maps.B[0][i] = t->mapWn[i];
-    }
+    int rcm = get_maps_b(ctx, t, 1, bn_h, maps.B[1]);
+    if (rcm) return rcm;
+    rcm = get_maps_b(ctx, t, 0, bn_v, maps.B[0]);
+    if (rcm) return rcm;
     TcParams p{};
-    fill_layer(p.L[1], m->nh, m->nv, t->bn_h, s->Sh, t->ldkh, m->bb64, t->bias_hf, d_Fh, DOM_BIP_HIDDEN);
-    fill_layer(p.L[0], m->nv, m->nh, t->bn_v, s->Sv, t->ldkv, m->hb64, t->bias_vf, d_Fv, DOM_BIP_VISIBLE);
+    fill_layer(p.L[1], m->nh, m->nv, bn_h, s->Sh, t->ldkh, m->bb64, t->bias_hf, d_Fh, DOM_BIP_HIDDEN);
+    fill_layer(p.L[0], m->nv, m->nh, bn_v, s->Sv, t->ldkv, m->hb64, t->bias_vf, d_Fv, DOM_BIP_VISIBLE);
     p.R = e->R;
     p.P = t->P;
     p.rule = rule;
@@ -644,13 +714,7 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     p.Tsched = d_T;
     p.steps_per_T = steps_per_T;
     p.seed = seed;
-    p.m_tiles = (e->R + TC_BM - 1) / TC_BM;
-    const bool extf = fluct_mode != ISB_FLUCT_PHILOX;
-    // chain-resident mode pays off when every SM gets a (nearly) full 128-row block of replicas to itself
-    int rows = (e->R + ctx->num_sms - 1) / ctx->num_sms;
-    rows = std::min(rows, TC_BM);
-    bool persist = rows >= 96;
-    if (const char *env = getenv("ISB_TC_PERSIST")) persist = atoi(env) != 0 && e->R >= 1;
+    p.m_tiles = m_tiles;
     if (persist) {
         p.persist = 1;
         p.rows_per_cta = rows;
@@ -737,6 +801,7 @@ int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q)
     const int n = m->nv, nb = m->shard_nb;
     t->ldkv = t->ldkh = n;
     t->bn_h = t->bn_v = pick_bn(nb);
+    t->rows_t = t->rows_n = nb; t->cols_t = t->cols_n = n;
     const size_t elems = (size_t)nb * n;
     double *dW = nullptr;
     if (Wrows) {
@@ -759,22 +824,27 @@ int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q)
     return make_float_bias(ctx, m->hb64, nb, &t->bias_vf);
 }
 
-int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *in_full, void *out_block, uint64_t seed,
-                          uint64_t step_abs, double T) {
+int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *in_full, void *out_block, int n_peers,
+                          void *const *peer_blocks, uint64_t seed, uint64_t step_abs, double T) {
     isb_ctx *ctx = m->ctx;
     TcModel *t = (TcModel *)m->tc;
     TcMaps maps;
     int rc = make_map_a(ctx, &maps.A[layer], in_full, m->shard_G, R, m->shard_nb, m->shard_nb);
     if (rc) return rc;
     maps.A[1 - layer] = maps.A[layer];
-    for (int i = 0; i < 3; ++i) maps.B[0][i] = maps.B[1][i] = t->mapWt[i];  // W is symmetric: one orientation
+    const int bn = pick_bn_waves(m->shard_nb, (R + TC_BM - 1) / TC_BM, ctx->num_sms);
+    rc = get_maps_b(ctx, t, 1, bn, maps.B[1]);  // W is symmetric: one orientation serves both half-steps
+    if (rc) return rc;
+    for (int i = 0; i < 3; ++i) maps.B[0][i] = maps.B[1][i];
     TcParams p{};
-    fill_layer(p.L[layer], m->shard_nb, m->nv, t->bn_h, (__nv_bfloat16 *)out_block, m->shard_nb,
+    fill_layer(p.L[layer], m->shard_nb, m->nv, bn, (__nv_bfloat16 *)out_block, m->shard_nb,
                layer == 1 ? m->bb64 : m->hb64, layer == 1 ? t->bias_hf : t->bias_vf, nullptr,
                layer == 1 ? DOM_BIP_HIDDEN : DOM_BIP_VISIBLE);
     p.L[layer].u_off = m->shard_g * m->shard_nb;
     p.L[layer].num_kb = m->nv / TC_BK;
     p.L[layer].kb_per_blk = m->shard_nb / TC_BK;
+    p.L[layer].npeer = n_peers;
+    for (int q = 0; q < n_peers; ++q) p.L[layer].peer[q] = (__nv_bfloat16 *)peer_blocks[q];
     p.L[1 - layer] = p.L[layer];
     p.R = R;
     p.P = t->P;

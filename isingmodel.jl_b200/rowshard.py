@@ -17,7 +17,8 @@ from . import _lib
 
 class RowShardedSCA:
     def __init__(self, n: int, R: int, *, seed: int | None = None, q: float = 1.0, W=None, h=None, rule=_lib.BIP_SCA,
-                 prec=_lib.PREC_BF16X3, emulate_blocks: int | None = None, device: int | None = None, group=None):
+                 prec=_lib.PREC_BF16X3, emulate_blocks: int | None = None, device: int | None = None, group=None,
+                 fused: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -47,8 +48,28 @@ class RowShardedSCA:
             else:
                 self.models.append(_lib.Model.shard_sk(self.ctx, self.n, self.G, g, int(seed), q, prec))
         bf = torch.bfloat16
-        self.full_v = torch.zeros((self.G, self.R, self.nb), dtype=bf, device=self.dev)
-        self.full_h = torch.zeros((self.G, self.R, self.nb), dtype=bf, device=self.dev)
+        # Fused exchange: the gathered matrices live in symmetric (peer-mapped) memory and every rank's sampling
+        # epilogue stores its block straight into all peers' copies over NVLink; a cross-GPU barrier then replaces
+        # the all-gather.  Falls back to ncclAllGather when symmetric memory is unavailable.
+        self.fused = False
+        self.full_v = self.full_h = None
+        if self.distributed and fused and 2 <= self.G <= 8:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                self.full_v = symm_mem.empty((self.G, self.R, self.nb), dtype=bf, device=self.dev)
+                self.full_h = symm_mem.empty((self.G, self.R, self.nb), dtype=bf, device=self.dev)
+                self._hv = symm_mem.rendezvous(self.full_v, grp)
+                self._hh = symm_mem.rendezvous(self.full_h, grp)
+                self.full_v.zero_()
+                self.full_h.zero_()
+                self.fused = True
+            except Exception as exc:  # pragma: no cover - depends on the driver / torch build
+                self.fused_error = repr(exc)
+                self.full_v = self.full_h = None
+        if self.full_v is None:
+            self.full_v = torch.zeros((self.G, self.R, self.nb), dtype=bf, device=self.dev)
+            self.full_h = torch.zeros((self.G, self.R, self.nb), dtype=bf, device=self.dev)
         # this rank's freshly sampled blocks, one per layer (they also hold the block's previous values)
         self.blk_v = [torch.ones((self.R, self.nb), dtype=bf, device=self.dev) for _ in self.blocks]
         self.blk_h = [torch.ones((self.R, self.nb), dtype=bf, device=self.dev) for _ in self.blocks]
@@ -66,6 +87,10 @@ class RowShardedSCA:
         for i, g in enumerate(self.blocks):
             self.blk_v[i].copy_(self.full_v[g])
             self.blk_h[i].copy_(self.full_v[g])
+        if self.fused:
+            # no peer may store into this rank's matrices before they hold the initial configuration
+            torch.cuda.synchronize(self.dev)
+            self.dist.barrier(group=self.group)
 
     def get_spins(self):
         """(R, n) int8 visible layer (identical on every rank after the all-gather)."""
@@ -79,6 +104,16 @@ class RowShardedSCA:
     # ---- one half-step: every owned block samples its units, then the blocks are exchanged
     def _half(self, layer, seed, step_abs, T):
         src, dst = (self.full_v, self.full_h) if layer == 1 else (self.full_h, self.full_v)
+        if self.fused:
+            g, hdl = self.blocks[0], (self._hh if layer == 1 else self._hv)
+            slab = g * self.R * self.nb * 2  # byte offset of this rank's block in every gathered matrix
+            peers = [int(ptr) + slab for q, ptr in enumerate(hdl.buffer_ptrs) if q != hdl.rank]
+            self.models[0].shard_halfstep_fused(self.R, layer, self.rule, src.data_ptr(), dst.data_ptr() + slab, peers, seed,
+                                                step_abs, T)
+            self.launches += 1
+            self.gather_bytes += (self.G - 1) * self.R * self.nb * 2
+            hdl.barrier(channel=0)  # all peers' stores have landed before anyone reads the layer
+            return
         blk = self.blk_h if layer == 1 else self.blk_v
         for i, m in enumerate(self.models):
             m.shard_halfstep(self.R, layer, self.rule, src.data_ptr(), blk[i].data_ptr(), seed, step_abs, T)

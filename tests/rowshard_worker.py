@@ -19,19 +19,22 @@ def main():
     n, R, seed, nsteps = 1024, 200, 17, 4
     S0 = synth.spins(3, R, n)
     T = np.array([1.0, 0.8, 0.6, 0.4])
-    sca = rowshard.RowShardedSCA(n, R, seed=seed, q=1.0, device=local)
-    assert sca.distributed and sca.G == dist.get_world_size()
-    sca.set_spins(S0)
-    sca.run(nsteps, T, seed=7)
-    got = sca.get_spins()
     emu = rowshard.RowShardedSCA(n, R, seed=seed, q=1.0, emulate_blocks=dist.get_world_size(), device=local)
     emu.set_spins(S0)
     emu.run(nsteps, T, seed=7)
-    ok = np.array_equal(got, emu.get_spins()) and np.array_equal(sca.get_hidden(), emu.get_hidden())
+    ok, modes = True, []
+    for fused in (False, True):   # ncclAllGather between half-steps / peer stores fused into the epilogue
+        sca = rowshard.RowShardedSCA(n, R, seed=seed, q=1.0, device=local, fused=fused)
+        assert sca.distributed and sca.G == dist.get_world_size()
+        for rep in range(2):      # a second run on the same object exercises the re-initialisation barrier
+            sca.set_spins(S0)
+            sca.run(nsteps, T, seed=7)
+            ok = ok and np.array_equal(sca.get_spins(), emu.get_spins()) and np.array_equal(sca.get_hidden(), emu.get_hidden())
+        modes.append("fused" if sca.fused else "nccl" + (":" + getattr(sca, "fused_error", "") if fused else ""))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if dist.get_rank() == 0:
-        print("ROWSHARD-OK" if int(flag.item()) == 1 else "ROWSHARD-MISMATCH", sca.gather_bytes, flush=True)
+        print("ROWSHARD-OK" if int(flag.item()) == 1 else "ROWSHARD-MISMATCH", modes, sca.gather_bytes, flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
