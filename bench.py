@@ -258,8 +258,8 @@ def sca_main(args):
     torch.cuda.set_stream(stream)
     ctx = _lib.context(local)
     ctx.set_stream(stream.cuda_stream)
-    prec = {"bf16x3": _lib.PREC_BF16X3, "bf16x1": _lib.PREC_BF16X1, "f64": _lib.PREC_F64}[prec_name]
-    P = {"bf16x3": 3, "bf16x1": 1, "f64": 1}[prec_name]
+    prec = {"bf16x3": _lib.PREC_BF16X3, "bf16x2": _lib.PREC_BF16X2, "bf16x1": _lib.PREC_BF16X1, "f64": _lib.PREC_F64}[prec_name]
+    P = {"bf16x3": 3, "bf16x2": 2, "bf16x1": 1, "f64": 1}[prec_name]
     pv = torch.empty((R, nv), dtype=torch.int8).pin_memory().numpy()
     ph = torch.empty((R, nh), dtype=torch.int8).pin_memory().numpy()
     pv[:] = synth.spins(11 + 1000 * rank, R, nv)
@@ -374,8 +374,8 @@ def c5_main(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     prec_name = args.prec or "bf16x3"
-    prec = {"bf16x3": _lib.PREC_BF16X3, "bf16x1": _lib.PREC_BF16X1}[prec_name]
-    P = 3 if prec_name == "bf16x3" else 1
+    prec = {"bf16x3": _lib.PREC_BF16X3, "bf16x2": _lib.PREC_BF16X2, "bf16x1": _lib.PREC_BF16X1}[prec_name]
+    P = {"bf16x3": 3, "bf16x2": 2, "bf16x1": 1}[prec_name]
     nb, R = args.c5_n_per_gpu, args.c5_replicas
     n = nb * world
     nst = args.sca_steps or 10
@@ -457,6 +457,141 @@ def c5_main(args):
     return 0
 
 
+
+# ---------------------------------------------------------------------------------------------- C1: 32x32 lattice
+def c1_main(args):
+    """BASELINE config 1: 2-D ferromagnetic 32x32 periodic lattice, Metropolis at T = 2.269, sequential sweeps, built
+    from a sparse J exactly as the reference's tests / demo build theirs (neighbour-list kernel); 4096 replicas."""
+    import scipy.sparse as sp
+    from isingmodel_jl_b200 import synth
+    N, R, T0 = 1024, 4096, 2.269
+    sweeps = args.sweeps if args.sweeps != 1000 else 10000
+    J = synth.lattice_J(32)
+    upd_step = N * R * sweeps
+    cfg = {"workload": f"C1: 32x32 periodic ferromagnet (sparse J, 4 neighbours), Metropolis at T={T0}, {sweeps} sequential "
+                       f"sweeps, {R} replicas/GPU", "n_sites": N, "replicas_per_gpu": R, "sweeps_per_step": sweeps,
+           "updates_per_step_per_gpu": upd_step, "sharding": "replicas (no collective)", "l2": "flushed between timed steps"}
+    rank = int(os.environ.get("RANK", "0"))
+
+    def cpu_rate(seconds):
+        import oracle
+        threads = oracle.num_threads()
+        S0 = synth.spins(SEED_S, threads, N)
+
+        def run(nsw):
+            fl = synth.exponential(5, (threads, nsw * N))
+            t0 = time.perf_counter()
+            oracle.ssf_run_batch(oracle.METROPOLIS, J, np.zeros(N), S0, nsw * N, fluct=fl, fluct_per_replica=True,
+                                 T=np.array([T0]), steps_per_T=nsw * N, nthreads=threads)
+            return time.perf_counter() - t0
+
+        dt = run(4)  # calibration
+        nsw = int(max(4, min(4000, round(4 * seconds / max(dt, 1e-6)))))
+        dt = run(nsw)
+        return threads * nsw * N / dt, (f"{threads} chains (one per thread) x {nsw} sweeps ({dt:.1f} s wall), dense-row dot "
+                                        "per update as the reference does"), threads
+
+    if args.impl == "reference":
+        if rank == 0:
+            v, sd, cores = cpu_rate(args.ref_seconds)
+            print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * upd_step / v,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                              "data": "synthetic", "config": cfg,
+                              "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sd},
+                              "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                              "gpu_launches": 0}))
+        return 0
+    import torch
+    import torch.distributed as dist
+    from isingmodel_jl_b200 import _lib, sharding, SpinSystems, SingleSpinFlip, SamplingHelper
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = _lib.context(local)
+    ctx.set_stream(stream.cuda_stream)
+    pin = torch.empty((R, N), dtype=torch.int8).pin_memory().numpy()
+    pin[:] = synth.spins(SEED_S + 1000 * rank, R, N)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ss = SpinSystems.SpinSystem(pin, sp.csc_matrix(J), np.zeros(N), device=local)
+    ua = SingleSpinFlip.MetropolisMethod(ss, T0)
+    ens = ss._ensemble()
+    nsteps = sweeps * N
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(k):
+        ens.set_spins(pin)
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ens.ssf_run(_lib.RULE_METROPOLIS, nsteps, seed=99 + rank, step_offset=k * nsteps, T=np.array([T0]), steps_per_T=nsteps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), ens.last_stats()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for k in range(args.warmup):
+        device_step(k)
+    barrier()
+    sampler.mark(lo=time.time())
+    ms, kms, flips, launches = [], [], [], 0
+    for k in range(args.steps):
+        m, st = device_step(args.warmup + k)
+        ms.append(m)
+        kms.append(st["kernel_ms"])
+        flips.append(st["flips"])
+        launches += st["launches"]
+    barrier()
+    sampler.mark(hi=time.time())
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = sharding.max_over_ranks(sum(ms) / 1e3)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        ss.spinConfiguration = pin
+        SamplingHelper.run_(ua, nsteps, order="sequential", seed=99 + rank, step_offset=(args.warmup + k) * nsteps,
+                            temperatures=np.array([T0]), steps_per_T=nsteps)
+        S = ss.spinConfiguration
+        E = SpinSystems.calcEnergy(ua)
+    torch.cuda.synchronize()
+    t_e2e = sharding.max_over_ranks(time.perf_counter() - t0)
+    if rank == 0:
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = float(json.load(open(pk))["hbm_gbs"]) if os.path.exists(pk) else 6650.0
+        kern_s = float(np.mean(kms)) / 1e3
+        alg = float(np.mean(flips)) * 4 * 12.0   # accepted flips x 4 neighbours x (8 B coupling + 4 B index)
+        line = {"metric": METRIC, "value": upd_step * args.steps * world / t_dev, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": cfg,
+                "roofline": {"bound": "hbm", "achieved": alg / kern_s / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / kern_s / 1e9 / peak, "traffic": None, "kernel": "isb::ssf_sparse_kernel",
+                             "kernel_ms": 1e3 * kern_s, "accept_rate": float(np.mean(flips)) / upd_step,
+                             "accounting": "accepted flips x 4 neighbours x 12 B; the neighbour-list kernel is bound by "
+                                           "per-window noise / decision arithmetic and shared-memory latency, not by bytes"},
+                "e2e": {"value": upd_step * args.steps * world / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(pin.nbytes),
+                        "d2h_bytes_per_step": int(S.nbytes + E.nbytes), "mean_final_energy": float(E.mean())},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            v, sd, cores = cpu_rate(args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sd}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -468,16 +603,18 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=8.0, help="CPU seconds per reference-arm step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU seconds of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--prec", default=None, help="c2: f64 | f32; c3/c4: bf16x3 | bf16x1 | f64")
+    ap.add_argument("--prec", default=None, help="c2: f64 | f32; c3/c4/c5: bf16x3 | bf16x2 | bf16x1 (c3/c4 also f64)")
     ap.add_argument("--c5-n-per-gpu", type=int, default=8192, help="c5: rows of J per GPU (N = this x GPUs; 8 GPUs -> 65536)")
     ap.add_argument("--c5-replicas", type=int, default=1024)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="c2 (default, the headline): SK N=1024 single-spin Glauber annealing; c3: dense N=4096 "
                          "MultiSpinFlip SCA, 8192 replicas; c4: bipartite 784x512 block Gibbs, 16384 chains")
     ap.add_argument("--sca-steps", type=int, default=None, help="SCA steps per bench step (c3: 20, c4: 200)")
     args = ap.parse_args()
     if args.workload == "c5":
         return c5_main(args)
+    if args.workload == "c1":
+        return c1_main(args)
     if args.workload != "c2":
         return sca_main(args)
     args.prec = args.prec or "f64"

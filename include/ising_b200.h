@@ -73,7 +73,9 @@ enum {
     ISB_PREC_F32 = 1, /* J and fields in float; decisions still taken in double                 */
     ISB_PREC_AUTO = 2,/* F64 fields; J stored as float iff that is lossless                      */
     ISB_PREC_BF16X3 = 3, /* bipartite tensor path: W split into 3 bf16 terms, fp32 accumulation */
-    ISB_PREC_BF16X1 = 4  /* bipartite tensor path: W rounded to one bf16 term (exact when W is)  */
+    ISB_PREC_BF16X1 = 4, /* bipartite tensor path: W rounded to one bf16 term (exact when W is)  */
+    ISB_PREC_BF16X2 = 5  /* bipartite tensor path: 2 bf16 terms (16 mantissa bits: the split error, 2^-17
+                            relative per coupling, is of the order of the fp32 accumulation error itself) */
 };
 
 /* ------------------------------------------------------------------ context */

@@ -546,7 +546,7 @@ int bip_tc_model_init(isb_model *m, const double *W /*[nv][nh] row-major*/) {
     isb_ctx *ctx = m->ctx;
     TcModel *t = new TcModel();
     m->tc = t;
-    t->P = m->prec == ISB_PREC_BF16X3 ? 3 : 1;
+    t->P = m->prec == ISB_PREC_BF16X3 ? 3 : (m->prec == ISB_PREC_BF16X2 ? 2 : 1);
     const int nv = m->nv, nh = m->nh;
     t->ldkv = (nv + 15) / 16 * 16;
     t->ldkh = (nh + 15) / 16 * 16;
@@ -776,6 +776,8 @@ __global__ void shard_fill_kernel(int n, int row0, int nrows, uint64_t seed, dou
         if (P > 1) {
             w -= back;
             t1[idx] = __ushort_as_bfloat16(bf16_rne_dev(w, &back));
+        }
+        if (P > 2) {
             w -= back;
             t2[idx] = __ushort_as_bfloat16(bf16_rne_dev(w, &back));
         }
@@ -797,7 +799,7 @@ int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q)
     isb_ctx *ctx = m->ctx;
     TcModel *t = new TcModel();
     m->tc = t;
-    t->P = m->prec == ISB_PREC_BF16X3 ? 3 : 1;
+    t->P = m->prec == ISB_PREC_BF16X3 ? 3 : (m->prec == ISB_PREC_BF16X2 ? 2 : 1);
     const int n = m->nv, nb = m->shard_nb;
     t->ldkv = t->ldkh = n;
     t->bn_h = t->bn_v = pick_bn(nb);

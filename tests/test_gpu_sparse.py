@@ -129,3 +129,25 @@ def test_dense_model_above_1024_sites(ctx, orc, synth):
         s, flips, E, M = orc.ssf_run(1, J, h, S0[r], nsteps, fluct=fl[r], T=T, steps_per_T=n, trace_every=n)
         assert np.array_equal(s, S[r]) and flips == out["flips"][r] and _close(out["E"][:, r], E)
     assert _close(e.energy(), np.array([orc.energy(J, h, S[r]) for r in range(R)]))
+
+
+@pytest.mark.parametrize("path,rule", [("dense", 2), ("dense", 1), ("sparse", 2), ("sparse", 1)])
+def test_energy_distribution_matches_exact_result(ctx, synth, path, rule):
+    """Independent RNG (in-kernel Philox): the mean energy of the 16 x 16 torus at T = 2.269 sampled by 4096
+    chains of sequential sweeps agrees with Kaufman's exact finite-size value (tolerance: 5 standard errors
+    estimated from the replica scatter + 0.1 % for the residual equilibration bias)."""
+    import scipy.sparse as sp
+    from exact_ising import mean_energy
+    L_, T, R = 16, 2.269, 4096
+    N = L_ * L_
+    L = _lib()
+    J = synth.lattice_J(L_)
+    model = L.Model.dense(ctx, J, np.zeros(N), L.PREC_AUTO) if path == "dense" else L.Model.sparse(ctx, sp.csc_matrix(J), np.zeros(N))
+    e = L.Ensemble(model, R)
+    e.set_spins(synth.spins(3, R, N))
+    e.ssf_run(rule, 600 * N, seed=11, T=np.array([T]), steps_per_T=600 * N)            # equilibrate
+    out = e.ssf_run(rule, 200 * N, seed=11, step_offset=600 * N, T=np.array([T]), steps_per_T=200 * N, trace_every=10 * N)
+    Em = out["E"].mean(0)                       # time average per replica
+    exact = mean_energy(L_, T)
+    err = Em.std() / np.sqrt(R)
+    assert abs(Em.mean() - exact) < 5 * err + 1e-3 * abs(exact), (Em.mean(), exact, err)

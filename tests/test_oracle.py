@@ -146,3 +146,29 @@ def test_philox_known_answers(orc):
         assert tuple(int(x) for x in orc.philox4x32_10(ctr, key)) == want
         got = oracle_np.philox4x32_10(*[np.uint32(c) for c in ctr], key[0], key[1])
         assert tuple(int(x) for x in got) == want
+
+
+# ---------------------------------------------------------------- the sampled distribution (RNG-independent)
+def test_kaufman_matches_enumeration():
+    from exact_ising import enumerate_mean_energy, mean_energy
+    for L in (3, 4):
+        assert abs(enumerate_mean_energy(L, 2.269) - mean_energy(L, 2.269)) < 1e-6
+
+
+@pytest.mark.parametrize("rule", [1, 2])
+def test_oracle_samples_the_boltzmann_distribution(orc, synth, rule):
+    """Glauber (heat bath) and Metropolis single-spin dynamics of the oracle reproduce the exact mean energy of
+    the 4 x 4 torus at T = 2.269 (random-site updates as the reference draws them)."""
+    from exact_ising import mean_energy
+    L, T, sweeps = 4, 2.269, 60000
+    N = L * L
+    J = synth.lattice_J(L)
+    rng = np.random.default_rng(5)
+    nsteps = sweeps * N
+    nodes = rng.integers(0, N, nsteps).astype(np.int32)
+    fl = rng.logistic(size=nsteps) if rule == 1 else rng.exponential(size=nsteps)
+    _, _, E, _ = orc.ssf_run(rule, J, np.zeros(N), synth.spins(1, 1, N)[0], nsteps, nodes=nodes, fluct=fl,
+                             T=np.array([T]), steps_per_T=nsteps, trace_every=N)
+    E = E[1000:]
+    blocks = E[: len(E) // 50 * 50].reshape(50, -1).mean(1)
+    assert abs(blocks.mean() - mean_energy(L, T)) < 5 * blocks.std() / np.sqrt(50) + 0.02
