@@ -147,6 +147,15 @@ int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *
                 const double *Tsched, int64_t nT, int64_t steps_per_T, int64_t trace_every,
                 double *out_E, double *out_M, int64_t *out_flips);
 
+/* isb_ssf_run that also records the spin configuration of every replica at each trace point
+ * (out_S: [nsteps/trace_every][R][ldS] int8, ldS >= N): the strided snapshots behind the streaming sampler —
+ * makeSampler!'s Channel yields the state after every step (src/SamplingHelper.jl:44,48), and the host layer
+ * replays it from these snapshots instead of synchronising with the device once per spin. */
+int isb_ssf_run_snap(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *nodes, int start,
+                     int fluct_mode, const double *fluct, uint64_t seed, uint64_t step_offset,
+                     const double *Tsched, int64_t nT, int64_t steps_per_T, int64_t trace_every,
+                     double *out_E, double *out_M, int64_t *out_flips, int8_t *out_S, int64_t ldS);
+
 /* Fluctuations exactly as ISB_FLUCT_PHILOX generates them inside isb_ssf_run, for parity tests:
  * out[r*nsteps + k], r in [r0, r0+nr). rule selects the transform. prec as the model's. */
 int isb_philox_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64_t step_offset,

@@ -113,12 +113,15 @@ def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offse
     return {"E": E}
 
 
-def makeSampler_(updatingAlgorithm, maxMCSteps, annealingSchedule=None, rng=None, *, stride=1):
+def makeSampler_(updatingAlgorithm, maxMCSteps, annealingSchedule=None, rng=None, *, stride=1, chunk=4096):
     """``makeSampler!(ua, n; annealingSchedule, rng)`` — src/SamplingHelper.jl:28-51, 69-91, 110-133.
 
     A generator standing in for the Julia ``Channel``: yields ``updatingAlgorithm`` (the same mutable
     object every time) once before the first step and then after every ``stride`` steps (reference:
-    stride = 1, n + 1 items).  All randomness is drawn up front in the reference's order.
+    stride = 1, n + 1 items).  All randomness is drawn up front in the reference's order.  For single-spin
+    algorithms the device runs `chunk` steps per library call and records the state after every `stride` steps
+    (isb_ssf_run_snap); the generator replays those snapshots, so `map(calcEnergy, sampler)` (demo.jl:108-115)
+    costs no device round trip per spin.
     """
     ua = updatingAlgorithm
     if maxMCSteps < 0:
@@ -143,22 +146,37 @@ def makeSampler_(updatingAlgorithm, maxMCSteps, annealingSchedule=None, rng=None
         yield ua                                                   # :44
         k = 0
         while k < maxMCSteps:
-            m = min(stride, maxMCSteps - k)
             if single:
+                # one library call per chunk; the kernel records the spins (and energies) after every `stride`
+                # steps and the Channel contract is replayed from those snapshots
                 ss = ua.spinSystem
-                ss._ensemble().ssf_run(ua._rule, m, nodes=updatedNodes[k:k + m],
-                                       fluct=None if ua._rule == _lib.RULE_HOPFIELD else fluctuations[k:k + m],
-                                       T=None if T is None else T[k + 1:k + 1 + m])
+                per_yield = max(1, stride)
+                m = min(maxMCSteps - k, max(per_yield, (chunk // per_yield) * per_yield))
+                full = (m // per_yield) * per_yield
+                if full == 0:
+                    full = m                                       # the last, shorter piece: one yield at its end
+                    per_yield = m
+                out = ss._ensemble().ssf_run(ua._rule, full, nodes=updatedNodes[k:k + full],
+                                             fluct=None if ua._rule == _lib.RULE_HOPFIELD else fluctuations[k:k + full],
+                                             T=None if T is None else T[k + 1:k + 1 + full], trace_every=per_yield,
+                                             want_M=False, want_S=True)
                 ss._dev_newer = True
-            else:
-                b = _bip(ua)
-                b.spinSystem._ensemble().bip_run(b._rule, m, Fv=Fv[k:k + m], Fh=Fh[k:k + m], T=T[k + 1:k + 1 + m])
-                b.spinSystem._dev_newer = True
-                if b is not ua:
-                    ua._sync_back()
+                for j in range(full // per_yield):
+                    ss._set_snapshot(out["S"][j], out["E"][j])
+                    if T is not None:
+                        ua.temperature = float(T[k + (j + 1) * per_yield])   # :46
+                    yield ua                                       # :48
+                ss._set_snapshot(None)
+                k += full
+                continue
+            m = min(stride, maxMCSteps - k)
+            b = _bip(ua)
+            b.spinSystem._ensemble().bip_run(b._rule, m, Fv=Fv[k:k + m], Fh=Fh[k:k + m], T=T[k + 1:k + 1 + m])
+            b.spinSystem._dev_newer = True
+            if b is not ua:
+                ua._sync_back()
             k += m
-            if T is not None:
-                ua.temperature = float(T[k])                       # :46 / :128
-            yield ua                                               # :48 / :130
+            ua.temperature = float(T[k])                           # :128
+            yield ua                                               # :130
 
     return gen()

@@ -97,11 +97,31 @@ class SpinSystem:
         self._device, self._prec = device, prec
         self._model = self._ens = None
         self._dev_newer = False
+        # streaming sampler: while a recorded trajectory is being replayed (SamplingHelper.makeSampler_), the
+        # state a consumer sees is a snapshot that lags the device; queries on it use a scratch ensemble
+        self._snap = None       # (spins2d, energies or None)
+        self._query_ens = None
+        self._query_loaded = None
 
     # ---- device plumbing
     @property
     def replicas(self):
         return self._host_spins.shape[0]
+
+    def _set_snapshot(self, spins2d, energies=None):
+        self._snap = None if spins2d is None else (spins2d, energies)
+
+    def _query_ensemble(self):
+        """The ensemble that holds the state a caller currently sees (the snapshot during a replay)."""
+        ens = self._ensemble()
+        if self._snap is None:
+            return ens
+        if self._query_ens is None:
+            self._query_ens = _lib.Ensemble(self._model, self.replicas)
+        if self._query_loaded is not self._snap[0]:
+            self._query_ens.set_spins(self._snap[0])
+            self._query_loaded = self._snap[0]
+        return self._query_ens
 
     def _ensemble(self):
         if self._ens is None:
@@ -117,10 +137,12 @@ class SpinSystem:
     def _invalidate_model(self):
         s = self._spins2d()
         self._host_spins = s
-        self._ens = self._model = None
+        self._ens = self._model = self._query_ens = self._query_loaded = None
         self._dev_newer = False
 
     def _spins2d(self):
+        if self._snap is not None:
+            return self._snap[0]
         if self._dev_newer:
             self._host_spins = self._ens.get_spins()
             self._dev_newer = False
@@ -356,14 +378,20 @@ def setAuxiliaryBias(ua, auxiliaryBias):
 def calcEnergy(x):
     """src/SpinSystems.jl:68-73 / :139-145 (on the GPU: isb_ens_energy)."""
     ss = _ss(x)
-    E = ss._ensemble().energy()
+    snap = getattr(ss, "_snap", None)
+    if snap is not None and snap[1] is not None:
+        E = snap[1]  # recorded by the kernel at this trace point
+    elif snap is not None:
+        E = ss._query_ensemble().energy()
+    else:
+        E = ss._ensemble().energy()
     return float(E[0]) if ss._single else E
 
 
 def calcLocalMagneticField(x, nodeIndex=None):
     """src/SpinSystems.jl:75-86 / :147-152 (isb_ens_local_field); ``nodeIndex`` is 0-based."""
     ss = _ss(x)
-    F = ss._ensemble().local_field()
+    F = (ss._query_ensemble() if getattr(ss, "_snap", None) is not None else ss._ensemble()).local_field()
     if nodeIndex is not None:
         if isinstance(ss, SpinSystemOnBipartiteGraph):
             raise TypeError("calcLocalMagneticField(ss, i) is defined for SpinSystem only")

@@ -75,6 +75,8 @@ SIGNATURES = {
     "isb_ens_local_field": (_i, [_vp, _vp, _i64]),
     "isb_ens_local_aux_bias": (_i, [_vp, _vp, _i64]),
     "isb_ssf_run": (_i, [_vp, _i, _i64, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "isb_ssf_run_snap": (_i, [_vp, _i, _i64, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp,
+                              _i64]),
     "isb_philox_fluct": (_i, [_vp, _i, _i, _u64, _u64, _i, _i, _i64, _vp]),
     "isb_philox_nodes": (_i, [_vp, _i, _u64, _u64, _i64, _vp]),
     "isb_philox_raw": (_i, [_vp, _vp, _vp, _i, _vp]),
@@ -360,8 +362,8 @@ class Ensemble:
 
     def ssf_run(self, rule, nsteps, *, order=ORDER_SEQUENTIAL, nodes=None, start=0, fluct=None,
                 fluct_per_replica=False, seed=0, step_offset=0, T=None, steps_per_T=1, trace_every=0,
-                want_E=True, want_M=True):
-        """isb_ssf_run. Returns dict(flips[R], E[ntr][R] | None, M[ntr][R] | None)."""
+                want_E=True, want_M=True, want_S=False):
+        """isb_ssf_run / isb_ssf_run_snap. Returns dict(flips[R], E[ntr][R] | None, M[ntr][R] | None, S[ntr][R][N] | None)."""
         nsteps = int(nsteps)
         nodes_a = None if nodes is None else np.ascontiguousarray(nodes, dtype=np.int32)
         if nodes_a is not None:
@@ -380,11 +382,13 @@ class Ensemble:
         ntr = nsteps // trace_every if trace_every > 0 else 0
         E = np.zeros((ntr, self.R)) if (ntr and want_E) else None
         M = np.zeros((ntr, self.R)) if (ntr and want_M) else None
+        S = np.zeros((ntr, self.R, self.nv), dtype=np.int8) if (ntr and want_S) else None
         flips = np.zeros(self.R, dtype=np.int64)
-        self._chk(load().isb_ssf_run(self.handle, rule, nsteps, order, ptr(nodes_a), int(start), mode, ptr(fl),
-                                     int(seed), int(step_offset), ptr(Ta), 0 if Ta is None else Ta.size,
-                                     int(steps_per_T), int(trace_every), ptr(E), ptr(M), ptr(flips)))
-        return {"flips": flips, "E": E, "M": M}
+        self._chk(load().isb_ssf_run_snap(self.handle, rule, nsteps, order, ptr(nodes_a), int(start), mode, ptr(fl),
+                                          int(seed), int(step_offset), ptr(Ta), 0 if Ta is None else Ta.size,
+                                          int(steps_per_T), int(trace_every), ptr(E), ptr(M), ptr(flips), ptr(S),
+                                          self.nv))
+        return {"flips": flips, "E": E, "M": M, "S": S}
 
     def bip_run(self, rule, nsteps, *, Fv=None, Fh=None, fluct_per_replica=False, seed=0, step_offset=0, T=None,
                 steps_per_T=1, trace_every=0):

@@ -473,12 +473,15 @@ static int copy_spins_in(isb_ens *e, int8_t *dst, int64_t ldd, int n, const int8
     isb_ctx *ctx = e->model->ctx;
     if (!s) return fail(ctx, ISB_ERR_ARG, "%s: NULL spin array", who);
     if (ld < n) return fail(ctx, ISB_ERR_SIZE, "%s: leading dimension %lld < %d units", who, (long long)ld, n);
-    for (int r = 0; r < e->R; ++r)
-        for (int i = 0; i < n; ++i) {
-            const int8_t v = s[(int64_t)r * ld + i];
-            if (v != 1 && v != -1)
-                return fail(ctx, ISB_ERR_ARG, "%s: spin [%d, replica %d] = %d is not +1 / -1", who, i, r, (int)v);
-        }
+    for (int r = 0; r < e->R; ++r) {
+        const int8_t *row = s + (int64_t)r * ld;
+        unsigned bad = 0;  // branch-free so that the host compiler vectorises the scan
+        for (int i = 0; i < n; ++i) bad |= (unsigned)((row[i] != 1) & (row[i] != -1));
+        if (bad)
+            for (int i = 0; i < n; ++i)
+                if (row[i] != 1 && row[i] != -1)
+                    return fail(ctx, ISB_ERR_ARG, "%s: spin [%d, replica %d] = %d is not +1 / -1", who, i, r, (int)row[i]);
+    }
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     ISB_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)ldd, s, (size_t)ld, (size_t)n, (size_t)e->R, cudaMemcpyHostToDevice,
                                     ctx->stream));
@@ -598,6 +601,14 @@ static void begin_stats(isb_ens *e) {
 int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *nodes, int start, int fluct_mode,
                 const double *fluct, uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT,
                 int64_t steps_per_T, int64_t trace_every, double *out_E, double *out_M, int64_t *out_flips) {
+    return isb_ssf_run_snap(e, rule, nsteps, order, nodes, start, fluct_mode, fluct, seed, step_offset, Tsched, nT,
+                            steps_per_T, trace_every, out_E, out_M, out_flips, nullptr, 0);
+}
+
+int isb_ssf_run_snap(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *nodes, int start, int fluct_mode,
+                     const double *fluct, uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT,
+                     int64_t steps_per_T, int64_t trace_every, double *out_E, double *out_M, int64_t *out_flips,
+                     int8_t *out_S, int64_t ldS) {
     if (!e) return ISB_ERR_ARG;
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
@@ -609,6 +620,7 @@ int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *
     if (fluct_mode < ISB_FLUCT_PHILOX || fluct_mode > ISB_FLUCT_PER_REPLICA)
         return fail(ctx, ISB_ERR_ARG, "%s: unknown fluct_mode %d", who, fluct_mode);
     if (trace_every < 0) return fail(ctx, ISB_ERR_ARG, "%s: trace_every is negative", who);
+    if (out_S && ldS < m->n) return fail(ctx, ISB_ERR_SIZE, "%s: snapshot pitch %lld < N = %d", who, (long long)ldS, m->n);
     const bool stochastic = rule != ISB_RULE_HOPFIELD;
     if (!stochastic) fluct_mode = ISB_FLUCT_PHILOX;  // the fluctuation is a dummy (SingleSpinFlip.jl:31)
     if (order == ISB_ORDER_LIST) {
@@ -656,6 +668,8 @@ int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *
     const int64_t ntr = trace_every > 0 ? nsteps / trace_every : 0;
     if (ntr > 0 && out_E) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_E, (size_t)ntr * e->R * sizeof(double), (void **)&d_E));
     if (ntr > 0 && out_M) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_M, (size_t)ntr * e->R * sizeof(double), (void **)&d_M));
+    int8_t *d_S = nullptr;
+    if (ntr > 0 && out_S) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_S, (size_t)ntr * e->R * m->n, (void **)&d_S));
     ISB_CUDA(ctx, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
 
     ISB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -665,10 +679,10 @@ int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *
     }
     if (m->kind == ISB_KIND_SPARSE || !m->fast_ok)
         ISB_TRY(isb::ssf_sparse_run_device(e, rule, nsteps, order, d_nodes, start, fluct_mode, d_fluct, seed, step_offset,
-                                           d_T, steps_per_T, (d_E || d_M) ? trace_every : 0, d_E, d_M));
+                                           d_T, steps_per_T, (d_E || d_M || d_S) ? trace_every : 0, d_E, d_M, d_S));
     else
         ISB_TRY(isb::ssf_run_device(e, rule, nsteps, order, d_nodes, start, fluct_mode, d_fluct, seed, step_offset, d_T,
-                                    steps_per_T, (d_E || d_M) ? trace_every : 0, d_E, d_M));
+                                    steps_per_T, (d_E || d_M || d_S) ? trace_every : 0, d_E, d_M, d_S));
     ISB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 
     std::vector<unsigned long long> fl((size_t)e->R);
@@ -677,6 +691,11 @@ int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *
     ISB_TRY(d2h(ctx, counters, e->d_counters, sizeof counters, &e->last_d2h));
     if (d_E) ISB_TRY(d2h(ctx, out_E, d_E, (size_t)ntr * e->R * sizeof(double), &e->last_d2h));
     if (d_M) ISB_TRY(d2h(ctx, out_M, d_M, (size_t)ntr * e->R * sizeof(double), &e->last_d2h));
+    if (d_S) {
+        ISB_CUDA(ctx, cudaMemcpy2DAsync(out_S, (size_t)ldS, d_S, (size_t)m->n, (size_t)m->n, (size_t)ntr * e->R,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+        e->last_d2h += (int64_t)ntr * e->R * m->n;
+    }
     cudaError_t ce = cudaStreamSynchronize(ctx->stream);
     if (ce != cudaSuccess) return fail(ctx, ISB_ERR_CUDA, "%s: kernel failed: %s", who, cudaGetErrorString(ce));
     float ms = 0.f;

@@ -76,7 +76,7 @@ int fail(isb_ctx *ctx, int code, const char *fmt, ...);
 // Grow-only device scratch buffer `slot` of the context, at least `bytes` long.
 int dev_reserve(isb_ctx *ctx, int slot, size_t bytes, void **out);
 enum { SCR_NODES = 0, SCR_FLUCT = 1, SCR_T = 2, SCR_E = 3, SCR_M = 4, SCR_FLUCT2 = 5, SCR_OUT = 6, SCR_TMP = 7,
-       SCR_TC0 = 8, SCR_TC1 = 9 };
+       SCR_TC0 = 8, SCR_TC1 = 9, SCR_S = 10, SCR_S2 = 11 };
 
 #define ISB_CUDA(ctx, call)                                                                      \
     do {                                                                                         \
@@ -89,7 +89,7 @@ enum { SCR_NODES = 0, SCR_FLUCT = 1, SCR_T = 2, SCR_E = 3, SCR_M = 4, SCR_FLUCT2
 // ssf.cu
 int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *d_nodes, int start,
                    int fluct_mode, const double *d_fluct, uint64_t seed, uint64_t step_offset,
-                   const double *d_T, int64_t steps_per_T, int64_t trace_every, double *d_E, double *d_M);
+                   const double *d_T, int64_t steps_per_T, int64_t trace_every, double *d_E, double *d_M, int8_t *d_S);
 int ssf_ensure_fields(isb_ens *e, int sign);
 size_t ssf_field_elem_size(const isb_model *m);
 int philox_fluct_device(isb_ctx *ctx, int rule, uint64_t seed, uint64_t step_offset, int r0, int nr,
@@ -109,7 +109,7 @@ int sparse_field_device(isb_ens *e, double *d_out, int64_t ld, int nout, double 
 int sparse_energy_device(isb_ens *e, double *d_E);
 int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *d_nodes, int start,
                           int fluct_mode, const double *d_fluct, uint64_t seed, uint64_t step_offset, const double *d_T,
-                          int64_t steps_per_T, int64_t trace_every, double *d_E, double *d_M);
+                          int64_t steps_per_T, int64_t trace_every, double *d_E, double *d_M, int8_t *d_S);
 
 // bip_exact.cu
 int bip_run_exact_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv,

@@ -45,6 +45,8 @@ struct SpParams {
     int64_t steps_per_T;
     int64_t trace_every;
     double *out_E, *out_M;
+    int8_t *out_S;
+    int64_t ldS;
     unsigned long long *flips, *near_ties;
     double tie_eps;
     int chains_per_cta;
@@ -100,6 +102,8 @@ __global__ void ssf_sparse_kernel(const SpParams p) {
             if (p.out_E) p.out_E[idx * p.R + r] = -0.5 * sf - p.ecoef * sh;
             if (p.out_M) p.out_M[idx * p.R + r] = (double)m;
         }
+        if (p.out_S)
+            for (int i = lane; i < p.n; i += 32) p.out_S[(idx * p.R + r) * p.ldS + i] = sp[i];
     };
     int64_t next_trace = p.trace_every > 0 ? p.trace_every : INT64_MAX, trace_idx = 0;
 
@@ -303,7 +307,7 @@ int sparse_energy_device(isb_ens *e, double *d_E) {
 
 int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *d_nodes, int start,
                           int fluct_mode, const double *d_fluct, uint64_t seed, uint64_t step_offset, const double *d_T,
-                          int64_t steps_per_T, int64_t trace_every, double *d_E, double *d_M) {
+                          int64_t steps_per_T, int64_t trace_every, double *d_E, double *d_M, int8_t *d_S) {
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
     SparseModel *sm = (SparseModel *)m->sp;
@@ -331,7 +335,7 @@ int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const
     p.nsteps = nsteps; p.start = start; p.nodes = d_nodes;
     p.fluct_mode = fluct_mode; p.fluct = d_fluct; p.seed = seed; p.step_offset = step_offset;
     p.Tsched = d_T; p.steps_per_T = steps_per_T; p.trace_every = trace_every;
-    p.out_E = d_E; p.out_M = d_M; p.flips = e->d_flips; p.near_ties = e->d_counters; p.tie_eps = e->tie_eps;
+    p.out_E = d_E; p.out_M = d_M; p.out_S = d_S; p.ldS = m->n; p.flips = e->d_flips; p.near_ties = e->d_counters; p.tie_eps = e->tie_eps;
     p.chains_per_cta = chains;
     const size_t smem = per_chain * chains;
     cudaError_t ce;

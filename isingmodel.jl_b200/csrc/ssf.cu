@@ -202,7 +202,7 @@ int ssf_ensure_fields(isb_ens *e, int sign) {
 // ------------------------------------------------------------------ K1 launch
 int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *d_nodes, int start,
                    int fluct_mode, const double *d_fluct, uint64_t seed, uint64_t step_offset,
-                   const double *d_T, int64_t steps_per_T, int64_t trace_every, double *d_E, double *d_M) {
+                   const double *d_T, int64_t steps_per_T, int64_t trace_every, double *d_E, double *d_M, int8_t *d_S) {
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
     if (!m->fast_ok)
@@ -272,6 +272,8 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
     p.trace_every = trace_every;
     p.out_E = d_E;
     p.out_M = d_M;
+    p.out_S = d_S;
+    p.ldS = m->n;
     p.flips = e->d_flips;
     p.near_ties = e->d_counters;
     p.tie_eps = e->tie_eps;

@@ -50,6 +50,8 @@ struct SsfParams {
     int64_t steps_per_T;
     int64_t trace_every;
     double *out_E, *out_M;
+    int8_t *out_S;   // spin snapshots at the trace points: [ntr][R][ldS] (or NULL)
+    int64_t ldS;
     unsigned long long *flips;
     unsigned long long *near_ties;
     double tie_eps;
@@ -351,6 +353,12 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
         if (lane == 0) {
             if (p.out_E) p.out_E[idx * p.R + r] = -0.5 * sf - p.ecoef * sh;
             if (p.out_M) p.out_M[idx * p.R + r] = (double)m;
+        }
+        if (p.out_S) {
+            int8_t *so = p.out_S + (idx * p.R + r) * p.ldS;
+#pragma unroll
+            for (int k = 0; k < NPL; ++k)
+                if (k * 32 + lane < p.n) so[k * 32 + lane] = ((sw >> k) & 1u) ? (int8_t)1 : (int8_t)-1;
         }
     };
 

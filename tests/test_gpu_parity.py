@@ -454,3 +454,64 @@ def test_bip_tc_chain_resident_equals_per_half_step_launches(ctx, synth, monkeyp
             e.bip_run(0, 3, Fv=Fv, Fh=Fh, T=np.array([2.0, 1.0, 0.5]))
             out.append((e.get_spins(), e.get_hidden()))
         assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+# ---------------------------------------------------------------- edge cases
+def test_edge_cases(ctx, orc, synth):
+    L = _lib()
+    N, R = 40, 3
+    J, h = synth.sk_J(N, 1), synth.gaussian(2, N) * 0.1
+    S0 = synth.spins(3, R, N)
+    e = L.Ensemble(L.Model.dense(ctx, J, h, L.PREC_F64), R)
+    e.set_spins(S0)
+    # zero steps: nothing happens, flips are zero
+    out = e.ssf_run(1, 0, T=np.ones(1))
+    assert np.array_equal(e.get_spins(), S0) and out["flips"].tolist() == [0, 0, 0]
+    # trace stride longer than the run: no trace rows
+    out = e.ssf_run(1, 5, fluct=np.zeros(5), T=np.ones(5), trace_every=100)
+    assert out["E"] is None
+    # T = 0 (the annealing end point): deterministic quench, ties give +1; negative T is accepted like the reference
+    e.set_spins(S0)
+    e.ssf_run(2, 3 * N, fluct=synth.exponential(4, 3 * N), T=np.zeros(1), steps_per_T=3 * N)
+    s, *_ = orc.ssf_run(2, J, h, S0[0], 3 * N, fluct=synth.exponential(4, 3 * N), T=np.zeros(1), steps_per_T=3 * N)
+    assert np.array_equal(e.get_spins()[0], s)
+    e.set_spins(S0)
+    e.ssf_run(1, N, fluct=synth.logistic(5, N), T=np.array([-0.5]), steps_per_T=N)
+    s, *_ = orc.ssf_run(1, J, h, S0[1], N, fluct=synth.logistic(5, N), T=np.array([-0.5]), steps_per_T=N)
+    assert np.array_equal(e.get_spins()[1], s)
+    # a site list that hammers one site, and a sweep starting at the last site
+    e.set_spins(S0)
+    nodes = np.array([7] * 20 + [0, 39] * 5, dtype=np.int32)
+    fl = synth.logistic(6, 30)
+    e.ssf_run(1, 30, nodes=nodes, fluct=fl, T=np.full(30, 1.3))
+    s, *_ = orc.ssf_run(1, J, h, S0[2], 30, nodes=nodes, fluct=fl, T=np.full(30, 1.3))
+    assert np.array_equal(e.get_spins()[2], s)
+    e.set_spins(S0)
+    e.ssf_run(2, 2 * N + 1, start=N - 1, fluct=synth.exponential(7, 2 * N + 1), T=np.array([0.9]), steps_per_T=2 * N + 1)
+    s, *_ = orc.ssf_run(2, J, h, S0[0], 2 * N + 1, start=N - 1, fluct=synth.exponential(7, 2 * N + 1), T=np.array([0.9]),
+                        steps_per_T=2 * N + 1)
+    assert np.array_equal(e.get_spins()[0], s)
+    # one isolated spin in a field, one replica
+    e1 = L.Ensemble(L.Model.dense(ctx, np.zeros((1, 1)), np.array([0.3]), L.PREC_F64), 1)
+    e1.set_spins(np.array([[-1]], dtype=np.int8))
+    e1.ssf_run(0, 1)
+    assert e1.get_spins()[0, 0] == -1  # Hopfield: J.s - h = -0.3 < 0 (the minus-h quirk, SingleSpinFlip.jl:33-34)
+    e1.ssf_run(1, 1, fluct=np.zeros(1), T=np.ones(1))
+    assert e1.get_spins()[0, 0] == 1
+
+
+def test_many_replicas_more_than_two_waves(ctx, orc, synth):
+    """R far above chains-per-CTA x SMs (several waves of CTAs), checked on a sample of replicas."""
+    L = _lib()
+    N, R, nsteps = 96, 9000, 96 * 4
+    J, h = synth.sk_J(N, 9), np.zeros(N)
+    S0 = synth.spins(10, R, N)
+    T = np.array([1.2, 0.8, 0.5, 0.3])
+    e = L.Ensemble(L.Model.dense(ctx, J, h, L.PREC_F64), R)
+    e.set_spins(S0)
+    e.ssf_run(1, nsteps, seed=77, T=T, steps_per_T=N)
+    S = e.get_spins()
+    for r in (0, 1, 4499, 8998, 8999):
+        fl = ctx.philox_fluct(1, 77, 0, r, 1, nsteps)[0]
+        s, *_ = orc.ssf_run(1, J, h, S0[r], nsteps, fluct=fl, T=T, steps_per_T=N)
+        assert np.array_equal(s, S[r])

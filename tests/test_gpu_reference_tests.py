@@ -76,3 +76,44 @@ def test_multispinflip_embedding(pkg, ctx, orc, synth):
     Hb = pkg.SpinSystems.calcEnergy(ua.bipartite)
     sig, tau = ua.bipartite.spinSystem.spinConfiguration, ua.bipartite.spinSystem.hiddenLayer
     assert abs(Hb - orc.bip_energy(W, 0.5 * h, 0.5 * h, sig, tau)) < 1e-9
+
+
+def test_makesampler_replays_every_step(pkg, ctx, orc, synth):
+    """makeSampler_ yields n + 1 states; each equals the oracle's state after that many steps, and calcEnergy on
+    the yielded object (the demo's `map(calcEnergy, sampler)` idiom, demo.jl:108-115) matches at every step."""
+    N, n = 9, 150
+    J = synth.lattice_J(3, -1.0)
+    s0 = synth.spins(4, 1, N)[0]
+    sched = lambda k: 2.0 * 0.98 ** k  # noqa: E731
+    for cls, rule in ((pkg.SingleSpinFlip.GlauberDynamics, 1), (pkg.SingleSpinFlip.MetropolisMethod, 2),
+                      (pkg.SingleSpinFlip.AsynchronousHopfieldNetwork, 0)):
+        ss = pkg.SpinSystems.SpinSystem(s0.copy(), J, np.zeros(N))
+        ua = cls(ss) if rule == 0 else cls(ss, 2.0)
+        rng = np.random.default_rng(3)
+        states, energies, temps = [], [], []
+        for item in pkg.SamplingHelper.makeSampler_(ua, n, annealingSchedule=sched, rng=rng, chunk=64):
+            assert item is ua
+            states.append(item.spinSystem.spinConfiguration.copy())
+            energies.append(pkg.SpinSystems.calcEnergy(item))
+            temps.append(getattr(item, "temperature", None))
+        assert len(states) == n + 1
+        # the same draws, in the reference's order (nodes first, then fluctuations)
+        rng = np.random.default_rng(3)
+        nodes = rng.integers(0, N, n).astype(np.int32)
+        fl = ua.distribution.rand(rng, n)
+        T = np.array([sched(k) for k in range(n + 1)])
+        s = s0.copy()
+        assert np.array_equal(states[0], s0)
+        for k in range(n):
+            s, *_ = orc.ssf_run(rule, J, np.zeros(N), s, 1, nodes=nodes[k:k + 1], fluct=fl[k:k + 1], T=T[k + 1:k + 2])
+            assert np.array_equal(states[k + 1], s), k
+            assert abs(energies[k + 1] - orc.energy(J, np.zeros(N), s)) < 1e-9
+            if rule != 0:
+                assert temps[k + 1] == T[k + 1]
+        assert np.array_equal(ua.spinSystem.spinConfiguration, s)  # after the replay the live state is the final one
+        assert abs(pkg.SpinSystems.calcLocalMagneticField(ua, 2) - orc.local_field(J, np.zeros(N), s)[2]) < 1e-12
+    # strided sampler: n // stride + 1 (+1 for a remainder) items
+    ss = pkg.SpinSystems.SpinSystem(s0.copy(), J, np.zeros(N))
+    ua = pkg.SingleSpinFlip.GlauberDynamics(ss, 1.0)
+    items = sum(1 for _ in pkg.SamplingHelper.makeSampler_(ua, 103, rng=np.random.default_rng(1), stride=10, chunk=40))
+    assert items == 1 + 10 + 1
