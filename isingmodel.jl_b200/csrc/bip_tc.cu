@@ -254,12 +254,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 const TcLayer &L = p.L[job.layer];
                 // chain-resident mode: this half-step's A operand is what the CTA's own epilogue wrote during the
                 // previous half-step (generic-proxy stores, fenced to the async proxy before the arrive)
-                if (p.persist && job.hs_first && job.hs > 0) mbar_wait(hs_done, (uint32_t)(job.hs - 1) & 1u);
+                if (p.persist && job.hs_first && job.hs > 0) mbar_wait_sleep(hs_done, (uint32_t)(job.hs - 1) & 1u);
                 const uint32_t tx = (uint32_t)(TC_A_BYTES + L.bn * TC_BK * 2);
                 for (int kb = 0; kb < L.num_kb; ++kb) {
                     for (int t = 0; t < p.P; ++t, ++it) {
                         const int s = it % TC_STAGES;
-                        mbar_wait(&empty_bar[s], ((it / TC_STAGES) & 1) ^ 1);
+                        mbar_wait_sleep(&empty_bar[s], ((it / TC_STAGES) & 1) ^ 1);
                         unsigned char *sa = smem + (size_t)s * TC_STAGE_BYTES;
                         mbar_arrive_expect_tx(&full_bar[s], tx);
                         tma_load_3d(sa, &maps.A[job.layer], (kb % L.kb_per_blk) * TC_BK, job.m0, kb / L.kb_per_blk, &full_bar[s]);
@@ -277,12 +277,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 const uint32_t idesc = umma_idesc_bf16(L.bn);
                 const int iters = L.num_kb * p.P;
                 const int a = tl & 1;
-                mbar_wait(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                mbar_wait_sleep(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN_MAX);
                 for (int i = 0; i < iters; ++i, ++it) {
                     const int s = it % TC_STAGES;
-                    mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
+                    mbar_wait_sleep(&full_bar[s], (it / TC_STAGES) & 1);
                     tc_fence_after();
                     const unsigned char *sa = smem + (size_t)s * TC_STAGE_BYTES;
                     const uint64_t adesc = umma_desc_sw128(sa);
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             const uint64_t step_abs = p.step_abs0 + (uint64_t)(job.k - p.k0);
             const int nchunks = L.bn >> 4;
             const int a = tl & 1;
-            mbar_wait(&tfull_bar[a], (tl >> 1) & 1);
+            mbar_wait_sleep(&tfull_bar[a], (tl >> 1) & 1);
             tc_fence_after();
             const int lrow = quad * 32 + lane;
             const int r = job.m0 + lrow;
