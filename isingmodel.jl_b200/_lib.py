@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libising_b200.so")
+LIB_PATH = os.environ.get("ISING_B200_LIB") or os.path.join(_HERE, "libising_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 # enums of include/ising_b200.h

@@ -188,6 +188,12 @@ __host__ __device__ __forceinline__ uint32_t philox_step_word(uint64_t seed, uin
                                     (uint32_t)(seed >> 32));
     return philox_pick(p, (uint32_t)(step & 3));
 }
+__host__ __device__ __forceinline__ uint32_t philox_step_word_k(const PhiloxKeys &K, uint32_t domain, uint32_t replica,
+                                                                uint64_t step) {
+    const uint64_t q = step >> 2;
+    const Philox4 p = philox4x32_10k((uint32_t)q, (uint32_t)(q >> 32), replica, domain << 28, K);
+    return philox_pick(p, (uint32_t)(step & 3));
+}
 // Block of 4 words for units 4*uq .. 4*uq+3 of one layer at step `step` of replica `replica`
 // (bipartite runs): counter = (lo(step), hi(step), replica, domain<<28 | uq).
 __host__ __device__ __forceinline__ Philox4 philox_unit_block(uint64_t seed, uint32_t domain, uint32_t replica,

@@ -279,6 +279,7 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
     p.tie_eps = e->tie_eps;
     p.nw = nw;
     p.NG = NG;
+    p.keys = philox_keys(seed);
     p.od_ratio = 0.8f;
     if (const char *env_od = getenv("ISB_SSF_OD_RATIO")) p.od_ratio = (float)atof(env_od);
 

@@ -63,8 +63,10 @@ struct SsfParams {
     // (cost: one row per flip per chain).  After each epoch the CTA compares its flip count with the step
     // count and streams the next epoch iff flips >= od_ratio * steps (low temperatures go on-demand).
     float od_ratio;
+    PhiloxKeys keys;  // the ten Philox round keys of `seed` (read straight from the constant bank)
 };
-constexpr int SSF_EPOCH = 1024;
+constexpr int SSF_EPOCH = 1024;        // steps per streamed epoch
+constexpr int SSF_EPOCH_OD = 8 * 1024;  // steps per on-demand epoch: chains re-synchronise 8x less often
 
 // consumer warps (chains) per CTA for a chain that keeps `field_regs` 32-bit registers of local
 // fields per lane: 15 warps -> 128 registers/thread, 21 -> 96, 29 -> 64 (one CTA per SM, +1 producer warp)
@@ -93,8 +95,8 @@ struct alignas(sizeof(JT) * VEC) JPack {
     JT v[VEC];
 };
 
-// hf[k] with k known only at run time and WARP-UNIFORM (k = site / 32): a jump table, not a select tree and
-// not dynamic register indexing
+// hf[k] with k known only at run time and WARP-UNIFORM (k = site / 32): a switch that ptxas turns into a short
+// uniform branch tree (not dynamic register indexing, which would push the fields to local memory)
 template <typename HT, int NPL>
 __device__ __forceinline__ HT field_sel(const HT (&hf)[NPL], int k) {
     HT v = hf[0];
@@ -175,16 +177,19 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 uint32_t ph = 0;  // (slot, ph) of the next streamed group, kept incrementally (no 64-bit divisions)
                 int64_t issued = 0;
                 uint32_t ep = 0;
-                for (int64_t t0 = 0; t0 < p.nsteps; t0 += SSF_EPOCH, ++ep) {
-                    const int64_t esteps = p.nsteps - t0 < SSF_EPOCH ? p.nsteps - t0 : SSF_EPOCH;
+                int ep_len = SSF_EPOCH, prev_len = SSF_EPOCH;
+                for (int64_t t0 = 0; t0 < p.nsteps; t0 += ep_len, ++ep) {
                     bool stream = true;
                     if (adaptive && ep > 0) {
                         mbar_wait(ep_bar, (ep - 1) & 1u);  // every chain of the CTA has finished epoch ep - 1
-                        stream = (float)(*ep_flips) >= p.od_ratio * (float)SSF_EPOCH;
+                        stream = (float)(*ep_flips) >= p.od_ratio * (float)prev_len;
                         *ep_flips = 0u;
                         *ep_mode = stream ? 1 : 0;
                         mbar_arrive(go_bar);
                     }
+                    ep_len = stream ? SSF_EPOCH : SSF_EPOCH_OD;
+                    prev_len = ep_len;
+                    const int64_t esteps = p.nsteps - t0 < ep_len ? p.nsteps - t0 : ep_len;
                     if (!stream) {
                         if constexpr (!LIST) site = (int)(((int64_t)site + esteps) % p.n);
                         continue;
@@ -266,6 +271,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
     uint32_t cph = 0;
     bool stream = TMA;  // delivery mode of the current epoch
     int te = 0;
+    int ep_len = SSF_EPOCH;  // length of the current epoch (on-demand epochs are longer)
     uint32_t ep_idx = 0;
     unsigned int ep_nflips = 0;
     const bool adaptive = TMA && CL == 1 && p.od_ratio > 0.f;
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
             }
         }
     };
-    // called when te == SSF_EPOCH (t = global step count): finish the epoch, learn the next one's delivery mode
+    // called when te == ep_len (t = global step count): finish the epoch, learn the next one's delivery mode
     auto epoch_boundary = [&](int64_t t) {
         if constexpr (TMA) {
             if (stream) {
@@ -310,6 +316,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 mbar_wait(go_bar, ep_idx & 1u);
                 stream = *ep_mode != 0;
             }
+            ep_len = stream ? SSF_EPOCH : SSF_EPOCH_OD;
             ep_nflips = 0;
             ++ep_idx;
             te = 0;
@@ -380,7 +387,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
             if (p.n - site < len) len = p.n - site;
             if (p.nsteps - t < len) len = (int)(p.nsteps - t);
             if (next_trace - t < len) len = (int)(next_trace - t);
-            if (TMA && SSF_EPOCH - te < len) len = SSF_EPOCH - te;
+            if (TMA && ep_len - te < len) len = ep_len - te;
             const int off = lane - l_first;
             const bool mine = off >= 0 && off < len;
             // temperature of my step
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 const int64_t tl = t + off;
                 if (p.fluct_mode == 0) {
                     f = ssf_fluct_from_word(
-                        rule, philox_step_word(p.seed, DOM_SSF_FLUCT, (uint32_t)r, p.step_offset + (uint64_t)tl));
+                        rule, philox_step_word_k(p.keys, DOM_SSF_FLUCT, (uint32_t)r, p.step_offset + (uint64_t)tl));
                 } else if (p.fluct_mode == 1) {
                     f = __ldg(&p.fluct[tl]);
                 } else {
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 write_trace(trace_idx++);
                 next_trace += p.trace_every;
             }
-            if (TMA && te == SSF_EPOCH) epoch_boundary(t);
+            if (TMA && te == ep_len) epoch_boundary(t);
         }
     } else {
         // ---------------------------------------------------------- explicit site list, one step at a time
@@ -484,8 +491,8 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                     node_batch = __ldg(&p.nodes[tl]);
                     if (rule != 0) {
                         if (p.fluct_mode == 0) {
-                            f_batch = ssf_fluct_from_word(rule, philox_step_word(p.seed, DOM_SSF_FLUCT, (uint32_t)r,
-                                                                                p.step_offset + (uint64_t)tl));
+                            f_batch = ssf_fluct_from_word(rule, philox_step_word_k(p.keys, DOM_SSF_FLUCT, (uint32_t)r,
+                                                                                  p.step_offset + (uint64_t)tl));
                         } else if (p.fluct_mode == 1) {
                             f_batch = __ldg(&p.fluct[tl]);
                         } else {
@@ -528,7 +535,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 write_trace(trace_idx++);
                 next_trace += p.trace_every;
             }
-            if (TMA && te == SSF_EPOCH) epoch_boundary(t + 1);
+            if (TMA && te == ep_len) epoch_boundary(t + 1);
         }
     }
 
