@@ -379,7 +379,8 @@ def c5_main(args):
     nb, R = args.c5_n_per_gpu, args.c5_replicas
     n = nb * world
     nst = args.sca_steps or 10
-    sca = rowshard.RowShardedSCA(n, R, seed=5, q=1.0, prec=prec, device=local, fused=os.environ.get("ISB_C5_FUSED", "1") != "0")
+    sca = rowshard.RowShardedSCA(n, R, seed=5, q=1.0, prec=prec, device=local,
+                                 exchange=os.environ.get("ISB_C5_EXCHANGE") or None)
     S0 = synth.spins(21, R, n)   # the same initial configuration on every rank
     T = np.linspace(1.0, 0.05, nst)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -440,8 +441,10 @@ def c5_main(args):
             "config": {"workload": f"C5: dense SK J N={n} row-sharded over {world} GPU(s) ({nb} rows each), {R} replicas, "
                                    f"SCA annealing T 1->0.05, {nst} steps per bench step, all-gather of spins per half-step",
                        "n": n, "rows_per_gpu": nb, "replicas": R, "coupling_storage": prec_name,
-                       "collective": ("peer stores fused into the sampling epilogue (NVLink, symmetric memory) + barrier"
-                                      if sca.fused else "ncclAllGather via torch.distributed") if world > 1 else "none (1 GPU)",
+                       "collective": {"pipelined": "ncclAllGather per half-step, hidden under the other replica group's GEMM",
+                                      "nccl": "ncclAllGather per half-step (torch.distributed)",
+                                      "fused": "peer stores fused into the sampling epilogue (symmetric memory) + barrier",
+                                      "local": "none (1 GPU)"}[sca.exchange],
                        "l2": "flushed between timed steps; W block (>= 1 GiB) exceeds L2"},
             "roofline": {"bound": "tensor" if t_mma >= t_link else "nvlink", "achieved": ach, "peak": peak,
                          "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "kernel": "isb::bip_tc_kernel",

@@ -214,16 +214,19 @@ int isb_model_shard_block(const isb_model *m); /* nb, 0 for other models */
 /* One half-step of this rank's block (layer 1: hidden from the full visible layer, 0: visible from the full
  * hidden layer): own <- sgn+(2 (W[block,:] . in + bias) - F T [.* own]) for all R replicas.  All pointers are
  * DEVICE pointers on the context's device; the kernel is enqueued on the context's stream (isb_set_stream). */
-int isb_shard_halfstep_dev(isb_model *m, int R, int layer, int rule, const void *in_full_bf16,
-                           void *out_block_bf16, uint64_t seed, uint64_t step_abs, double T);
+/* R replicas whose global indices start at replica_offset (the host layer may split the replicas into groups
+ * and pipeline one group's exchange under the other group's GEMM: chains are independent). */
+int isb_shard_halfstep_dev(isb_model *m, int R, int replica_offset, int layer, int rule,
+                           const void *in_full_bf16, void *out_block_bf16, uint64_t seed, uint64_t step_abs,
+                           double T);
 /* The same half-step with the all-gather FUSED into the sampling epilogue: every sampled 16-unit run is also
  * stored, tile by tile while the next tile's MMAs run, straight into the gathered matrices of up to 7 peer GPUs
  * through peer-mapped (NVLink) device pointers.  peer_blocks_bf16[q] is the address, in THIS process, of the
  * [R][nb] slab of peer q's gathered layer that belongs to this rank (block-major layout: base_q + block*R*nb).
  * The caller separates half-steps with a cross-GPU barrier instead of an all-gather. */
-int isb_shard_halfstep_fused_dev(isb_model *m, int R, int layer, int rule, const void *in_full_bf16,
-                                 void *out_block_bf16, int n_peers, void *const *peer_blocks_bf16, uint64_t seed,
-                                 uint64_t step_abs, double T);
+int isb_shard_halfstep_fused_dev(isb_model *m, int R, int replica_offset, int layer, int rule,
+                                 const void *in_full_bf16, void *out_block_bf16, int n_peers,
+                                 void *const *peer_blocks_bf16, uint64_t seed, uint64_t step_abs, double T);
 
 /* ------------------------------------------------------------------ instrumentation */
 /* Device time (ms, CUDA events on the ensemble's stream) of the kernels of the last *_run call,

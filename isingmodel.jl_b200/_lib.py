@@ -86,8 +86,8 @@ SIGNATURES = {
     "isb_shard_model_sk": (_i, [_vp, _i, _i, _i, _u64, _d, _i, C.POINTER(_vp)]),
     "isb_sk_rows": (_i, [_vp, _i, _u64, _i, _i, _vp]),
     "isb_model_shard_block": (_i, [_vp]),
-    "isb_shard_halfstep_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _u64, _u64, _d]),
-    "isb_shard_halfstep_fused_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _u64, _u64, _d]),
+    "isb_shard_halfstep_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _u64, _u64, _d]),
+    "isb_shard_halfstep_fused_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _u64, _u64, _d]),
     "isb_ens_last_stats": (_i, [_vp, C.POINTER(_d), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "isb_ens_last_flips": (_i64, [_vp]),
     "isb_ens_last_near_ties": (_i64, [_vp]),
@@ -264,15 +264,16 @@ class Model:
                                         C.byref(m)), ctx.handle)
         return cls(ctx, m, "shard")
 
-    def shard_halfstep(self, R, layer, rule, in_full_ptr, out_block_ptr, seed, step_abs, T):
+    def shard_halfstep(self, R, layer, rule, in_full_ptr, out_block_ptr, seed, step_abs, T, replica_offset=0):
         """isb_shard_halfstep_dev with raw device pointers (ints)."""
-        check(load().isb_shard_halfstep_dev(self.handle, int(R), int(layer), int(rule), _vp(in_full_ptr),
+        check(load().isb_shard_halfstep_dev(self.handle, int(R), int(replica_offset), int(layer), int(rule), _vp(in_full_ptr),
                                             _vp(out_block_ptr), int(seed), int(step_abs), float(T)), self.ctx.handle)
 
-    def shard_halfstep_fused(self, R, layer, rule, in_full_ptr, out_block_ptr, peer_ptrs, seed, step_abs, T):
+    def shard_halfstep_fused(self, R, layer, rule, in_full_ptr, out_block_ptr, peer_ptrs, seed, step_abs, T,
+                             replica_offset=0):
         """isb_shard_halfstep_fused_dev: peer_ptrs = device addresses of this rank's slab in each peer's matrix."""
         arr = (C.c_void_p * max(1, len(peer_ptrs)))(*[int(x) for x in peer_ptrs])
-        check(load().isb_shard_halfstep_fused_dev(self.handle, int(R), int(layer), int(rule), _vp(in_full_ptr),
+        check(load().isb_shard_halfstep_fused_dev(self.handle, int(R), int(replica_offset), int(layer), int(rule), _vp(in_full_ptr),
                                                   _vp(out_block_ptr), len(peer_ptrs), C.cast(arr, _vp), int(seed),
                                                   int(step_abs), float(T)), self.ctx.handle)
 

@@ -86,6 +86,7 @@ struct TcParams {
     // `nsteps_seg` full steps (hidden then visible) on them without leaving the SM — chains are independent, so
     // no grid-wide synchronisation exists; only the CTA's own producer waits for its own epilogue.
     int persist, layer, m_tiles, rows_per_cta, nsteps_seg;
+    int r_off;               // global replica index of row 0 (a run may hold a slice of the replicas): Philox only
     int64_t nsteps, k0;      // steps of the whole run (fluctuation array pitch), first step of this launch
     const double *Tsched;
     int64_t steps_per_T;
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         // == philox_unit_block(seed, domain, r, step, unit >> 2) with the round keys hoisted
-                        const Philox4 blk = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), (uint32_t)r,
+                        const Philox4 blk = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), (uint32_t)(r + p.r_off),
                                                            (L.domain << 28) | (uint32_t)(((L.u_off + u0) >> 2) + q), keys);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -826,8 +827,8 @@ int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q)
     return make_float_bias(ctx, m->hb64, nb, &t->bias_vf);
 }
 
-int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *in_full, void *out_block, int n_peers,
-                          void *const *peer_blocks, uint64_t seed, uint64_t step_abs, double T) {
+int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, int rule, const void *in_full, void *out_block,
+                          int n_peers, void *const *peer_blocks, uint64_t seed, uint64_t step_abs, double T) {
     isb_ctx *ctx = m->ctx;
     TcModel *t = (TcModel *)m->tc;
     TcMaps maps;
@@ -849,6 +850,7 @@ int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *
     for (int q = 0; q < n_peers; ++q) p.L[layer].peer[q] = (__nv_bfloat16 *)peer_blocks[q];
     p.L[1 - layer] = p.L[layer];
     p.R = R;
+    p.r_off = replica_offset;
     p.P = t->P;
     p.rule = rule;
     p.fluct_mode = ISB_FLUCT_PHILOX;

@@ -126,8 +126,8 @@ void bip_tc_model_free(isb_model *m);
 int bip_tc_ens_init(isb_ens *e);
 void bip_tc_ens_free(isb_ens *e);
 int shard_model_init(isb_model *m, const double *Wrows /*[nb][n] or NULL*/, uint64_t seed, double q);
-int shard_halfstep_device(isb_model *m, int R, int layer, int rule, const void *in_full, void *out_block, int n_peers,
-                          void *const *peer_blocks, uint64_t seed, uint64_t step_abs, double T);
+int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, int rule, const void *in_full, void *out_block,
+                          int n_peers, void *const *peer_blocks, uint64_t seed, uint64_t step_abs, double T);
 int sk_rows_device(isb_ctx *ctx, int n, uint64_t seed, int row0, int nrows, double *d_out);
 int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv,
                       const double *d_Fh, uint64_t seed, uint64_t step_offset, const double *d_T,

@@ -45,6 +45,14 @@ function model_dense(J::Matrix{Float64}, h::Vector{Float64}; prec = PREC_AUTO)
                 context(), size(J, 1), J, stride(J, 2), h, prec, w, m), context())
     m[]
 end
+# SparseMatrixCSC couplings (what the reference's tests and demo pass) stay sparse: 0-based CSC across the ABI
+function model_sparse(n::Integer, colptr::Vector{Int64}, rowval::Vector{Int32}, nzval::Vector{Float64}, h::Vector{Float64})
+    m = Ref{Model}(C_NULL); w = Ref{Cint}(0)
+    check(ccall((:isb_model_sparse, libisb), Cint,
+                (Ctx, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ref{Cint}, Ref{Model}),
+                context(), n, colptr, rowval, nzval, h, w, m), context())
+    m[]
+end
 function model_bipartite(W::Matrix{Float64}, h::Vector{Float64}, b::Vector{Float64}; prec = PREC_F64)
     m = Ref{Model}(C_NULL)
     check(ccall((:isb_model_bipartite, libisb), Cint,
@@ -102,6 +110,7 @@ export SpinSystem, UpdatingAlgorithm, getSpinConfiguration, getCouplingCoefficie
 export calcEnergy, calcLocalMagneticField, SpinSystemOnBipartiteGraph, UpdatingAlgorithmOnBipartiteGraph
 export getHiddenLayer, getAuxiliaryBias, calcLocalAuxiliaryBias
 using LinearAlgebra
+using SparseArrays
 import ..CABI
 
 mutable struct SpinSystem
@@ -134,9 +143,16 @@ mutable struct SpinSystem
         if size(couplingCoefficients, 1) != numBias
             error("The size of the coupling-coefficient matrix does not match the size of the external-magnetic-field vector: $(row) ≠ $(numBias).")
         end
-        J = Matrix{Float64}(couplingCoefficients); h = Vector{Float64}(externalMagneticField)
+        h = Vector{Float64}(externalMagneticField)
         S = Matrix{Int8}(reshape(spinConfiguration, size(spinConfiguration, 1), :))
-        m = CABI.model_dense(J, h); e = CABI.ensemble(m, size(S, 2)); CABI.set_spins!(e, S)
+        if couplingCoefficients isa SparseMatrixCSC
+            J = SparseMatrixCSC{Float64,Int64}(couplingCoefficients)
+            m = CABI.model_sparse(size(J, 1), J.colptr .- 1, Int32.(J.rowval .- 1), J.nzval, h)
+        else
+            J = Matrix{Float64}(couplingCoefficients)
+            m = CABI.model_dense(J, h)
+        end
+        e = CABI.ensemble(m, size(S, 2)); CABI.set_spins!(e, S)
         new(spinConfiguration, J, h, m, e)
     end
 end

@@ -3,10 +3,21 @@
 The MultiSpinFlip SCA of an N-spin model is the bipartite SCA (reference: src/OnBipartiteGraph.jl:30-43) on the
 embedding W = (J + qI)/2, sigma = tau = s (demo.jl:82-90).  When W does not fit one GPU, rank g owns the output
 units [g*nb, (g+1)*nb) of both half-steps and W[block rows, :]; after every half-step the freshly sampled
-[R][nb] blocks are all-gathered (NCCL over NVLink) into the block-major [G][R][nb] matrix that is the next
-half-step's K operand.  torch is plumbing here: device buffers, the stream, and the all-gather.
-The library's noise is indexed by global (replica, step, unit), so the result does not depend on G: with
-``emulate_blocks=G`` one process plays all G ranks in turn on one GPU (used by the parity tests).
+[R][nb] blocks are exchanged into the block-major [G][R][nb] matrix that is the next half-step's K operand.
+torch is plumbing here: device buffers, streams, and the collective.
+
+Exchange modes (``exchange=``), all bit-identical, measured on 8 x B200 at N = 65536, R = 1024 (ms per half-step,
+bf16x1 / bf16x3; the MMA-only target is 0.81 / 2.43):
+  "nccl"      (default) one ncclAllGather after every half-step kernel                           1.12 / 3.11
+  "pipelined" the replicas are split into two groups and one group's all-gather runs on NCCL's stream under
+              the other group's GEMM (chains are independent).  NCCL's CTAs and the persistent GEMM CTAs (one
+              per SM, all of its shared memory) contend for the SMs: slower                       1.42 / 4.00
+  "fused"     the sampling epilogue stores every sampled run straight into all peers' gathered matrices
+              (symmetric memory, NVLink stores) and a cross-GPU barrier replaces the all-gather: the 32-byte
+              peer stores stall the epilogue warps: slower                                        1.67 / 3.51
+
+The library's noise is indexed by global (replica, step, unit), so the result depends neither on G nor on the
+grouping: with ``emulate_blocks=G`` one process plays all G ranks in turn on one GPU (parity tests).
 """
 from __future__ import annotations
 
@@ -15,10 +26,33 @@ import numpy as np
 from . import _lib
 
 
+class _Group:
+    """One slice of the replicas with its own gathered matrices and in-flight collective."""
+
+    def __init__(self, r0, R, G, nb, nblocks_local, dev, torch, symm=None, dist_group=None):
+        bf = torch.bfloat16
+        self.r0, self.R = r0, R
+        self.hv = self.hh = None
+        if symm is not None:
+            self.full_v = symm.empty((G, R, nb), dtype=bf, device=dev)
+            self.full_h = symm.empty((G, R, nb), dtype=bf, device=dev)
+            self.hv = symm.rendezvous(self.full_v, dist_group)
+            self.hh = symm.rendezvous(self.full_h, dist_group)
+            self.full_v.zero_()
+            self.full_h.zero_()
+        else:
+            self.full_v = torch.zeros((G, R, nb), dtype=bf, device=dev)
+            self.full_h = torch.zeros((G, R, nb), dtype=bf, device=dev)
+        # this rank's freshly sampled blocks, one per layer (they also hold the block's previous values)
+        self.blk_v = [torch.ones((R, nb), dtype=bf, device=dev) for _ in range(nblocks_local)]
+        self.blk_h = [torch.ones((R, nb), dtype=bf, device=dev) for _ in range(nblocks_local)]
+        self.pending = {0: None, 1: None}  # in-flight all-gather producing full_v (layer 0) / full_h (layer 1)
+
+
 class RowShardedSCA:
     def __init__(self, n: int, R: int, *, seed: int | None = None, q: float = 1.0, W=None, h=None, rule=_lib.BIP_SCA,
                  prec=_lib.PREC_BF16X3, emulate_blocks: int | None = None, device: int | None = None, group=None,
-                 fused: bool = True):
+                 exchange: str | None = None, fused: bool | None = None):
         import torch
         import torch.distributed as dist
 
@@ -35,6 +69,15 @@ class RowShardedSCA:
         if self.n % self.G:
             raise ValueError("n must be divisible by the number of blocks")
         self.nb = self.n // self.G
+        if fused is not None and exchange is None:  # older spelling
+            exchange = "fused" if fused else "nccl"
+        if exchange is None:
+            exchange = "nccl"
+        if not self.distributed:
+            exchange = "local"
+        if exchange == "pipelined" and self.R < 256:
+            exchange = "nccl"
+        self.exchange = exchange
         self.ctx = _lib.context(device)
         self.dev = torch.device("cuda", self.ctx.device)
         torch.cuda.set_device(self.dev)
@@ -47,32 +90,30 @@ class RowShardedSCA:
                 self.models.append(_lib.Model.shard_rows(self.ctx, self.n, self.G, g, Wg, hb, hb, prec))
             else:
                 self.models.append(_lib.Model.shard_sk(self.ctx, self.n, self.G, g, int(seed), q, prec))
-        bf = torch.bfloat16
-        # Fused exchange: the gathered matrices live in symmetric (peer-mapped) memory and every rank's sampling
-        # epilogue stores its block straight into all peers' copies over NVLink; a cross-GPU barrier then replaces
-        # the all-gather.  Falls back to ncclAllGather when symmetric memory is unavailable.
+        symm = None
         self.fused = False
-        self.full_v = self.full_h = None
-        if self.distributed and fused and 2 <= self.G <= 8:
+        if exchange == "fused" and 2 <= self.G <= 8:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                grp = group if group is not None else dist.group.WORLD
-                self.full_v = symm_mem.empty((self.G, self.R, self.nb), dtype=bf, device=self.dev)
-                self.full_h = symm_mem.empty((self.G, self.R, self.nb), dtype=bf, device=self.dev)
-                self._hv = symm_mem.rendezvous(self.full_v, grp)
-                self._hh = symm_mem.rendezvous(self.full_h, grp)
-                self.full_v.zero_()
-                self.full_h.zero_()
+                symm = symm_mem
                 self.fused = True
-            except Exception as exc:  # pragma: no cover - depends on the driver / torch build
+            except Exception as exc:  # pragma: no cover - depends on the torch build
                 self.fused_error = repr(exc)
-                self.full_v = self.full_h = None
-        if self.full_v is None:
-            self.full_v = torch.zeros((self.G, self.R, self.nb), dtype=bf, device=self.dev)
-            self.full_h = torch.zeros((self.G, self.R, self.nb), dtype=bf, device=self.dev)
-        # this rank's freshly sampled blocks, one per layer (they also hold the block's previous values)
-        self.blk_v = [torch.ones((self.R, self.nb), dtype=bf, device=self.dev) for _ in self.blocks]
-        self.blk_h = [torch.ones((self.R, self.nb), dtype=bf, device=self.dev) for _ in self.blocks]
+                self.exchange = exchange = "nccl"
+        grp = group if group is not None else (dist.group.WORLD if self.distributed else None)
+        if exchange == "pipelined":
+            half = (self.R // 2 + 127) // 128 * 128   # whole 128-replica tiles in the first group
+            slices = [(0, half), (half, self.R - half)]
+        else:
+            slices = [(0, self.R)]
+        try:
+            self.groups = [_Group(r0, Rg, self.G, self.nb, len(self.blocks), self.dev, torch, symm, grp)
+                           for r0, Rg in slices if Rg > 0]
+        except Exception as exc:  # pragma: no cover - symmetric memory unavailable on this driver
+            if not self.fused:
+                raise
+            self.fused, self.fused_error, self.exchange = False, repr(exc), "nccl"
+            self.groups = [_Group(0, self.R, self.G, self.nb, len(self.blocks), self.dev, torch)]
         self.launches = 0
         self.gather_bytes = 0
 
@@ -80,47 +121,72 @@ class RowShardedSCA:
     def set_spins(self, S):
         """S: (R, n) int8 +-1; the embedding starts from sigma = tau = s."""
         torch = self.torch
+        self._drain()
         S = torch.as_tensor(np.ascontiguousarray(S, dtype=np.int8), device=self.dev)
-        full = S.view(self.R, self.G, self.nb).permute(1, 0, 2).contiguous()
-        self.full_v.copy_(full.to(torch.bfloat16))
-        self.full_h.copy_(self.full_v)
-        for i, g in enumerate(self.blocks):
-            self.blk_v[i].copy_(self.full_v[g])
-            self.blk_h[i].copy_(self.full_v[g])
+        for gr in self.groups:
+            full = S[gr.r0:gr.r0 + gr.R].view(gr.R, self.G, self.nb).permute(1, 0, 2).contiguous().to(torch.bfloat16)
+            gr.full_v.copy_(full)
+            gr.full_h.copy_(full)
+            for i, g in enumerate(self.blocks):
+                gr.blk_v[i].copy_(full[g])
+                gr.blk_h[i].copy_(full[g])
         if self.fused:
             # no peer may store into this rank's matrices before they hold the initial configuration
             torch.cuda.synchronize(self.dev)
             self.dist.barrier(group=self.group)
 
+    def _drain(self):
+        for gr in self.groups:
+            for layer in (0, 1):
+                if gr.pending[layer] is not None:
+                    gr.pending[layer].wait()
+                    gr.pending[layer] = None
+
+    def _layer(self, which):
+        self._drain()
+        torch = self.torch
+        parts = []
+        for gr in self.groups:
+            full = gr.full_v if which == 0 else gr.full_h
+            s = (full > 0).to(torch.int8) * 2 - 1
+            parts.append(s.permute(1, 0, 2).reshape(gr.R, self.n))
+        return torch.cat(parts, 0).cpu().numpy()
+
     def get_spins(self):
-        """(R, n) int8 visible layer (identical on every rank after the all-gather)."""
-        s = (self.full_v > 0).to(self.torch.int8) * 2 - 1
-        return s.permute(1, 0, 2).reshape(self.R, self.n).cpu().numpy()
+        """(R, n) int8 visible layer (identical on every rank after the exchange)."""
+        return self._layer(0)
 
     def get_hidden(self):
-        s = (self.full_h > 0).to(self.torch.int8) * 2 - 1
-        return s.permute(1, 0, 2).reshape(self.R, self.n).cpu().numpy()
+        return self._layer(1)
 
-    # ---- one half-step: every owned block samples its units, then the blocks are exchanged
-    def _half(self, layer, seed, step_abs, T):
-        src, dst = (self.full_v, self.full_h) if layer == 1 else (self.full_h, self.full_v)
+    # ---- one half-step of one replica group: every owned block samples its units, then the blocks are exchanged
+    def _half(self, gr, layer, seed, step_abs, T):
+        src, dst = (gr.full_v, gr.full_h) if layer == 1 else (gr.full_h, gr.full_v)
+        src_layer = 0 if layer == 1 else 1
+        if gr.pending[src_layer] is not None:   # the gathered input of this half-step (stream-level wait)
+            gr.pending[src_layer].wait()
+            gr.pending[src_layer] = None
         if self.fused:
-            g, hdl = self.blocks[0], (self._hh if layer == 1 else self._hv)
-            slab = g * self.R * self.nb * 2  # byte offset of this rank's block in every gathered matrix
+            g, hdl = self.blocks[0], (gr.hh if layer == 1 else gr.hv)
+            slab = g * gr.R * self.nb * 2  # byte offset of this rank's block in every gathered matrix
             peers = [int(ptr) + slab for q, ptr in enumerate(hdl.buffer_ptrs) if q != hdl.rank]
-            self.models[0].shard_halfstep_fused(self.R, layer, self.rule, src.data_ptr(), dst.data_ptr() + slab, peers, seed,
-                                                step_abs, T)
+            self.models[0].shard_halfstep_fused(gr.R, layer, self.rule, src.data_ptr(), dst.data_ptr() + slab, peers,
+                                                seed, step_abs, T, replica_offset=gr.r0)
             self.launches += 1
-            self.gather_bytes += (self.G - 1) * self.R * self.nb * 2
+            self.gather_bytes += (self.G - 1) * gr.R * self.nb * 2
             hdl.barrier(channel=0)  # all peers' stores have landed before anyone reads the layer
             return
-        blk = self.blk_h if layer == 1 else self.blk_v
+        blk = gr.blk_h if layer == 1 else gr.blk_v
         for i, m in enumerate(self.models):
-            m.shard_halfstep(self.R, layer, self.rule, src.data_ptr(), blk[i].data_ptr(), seed, step_abs, T)
+            m.shard_halfstep(gr.R, layer, self.rule, src.data_ptr(), blk[i].data_ptr(), seed, step_abs, T,
+                             replica_offset=gr.r0)
             self.launches += 1
         if self.distributed:
-            # the one real exchange step of this path: [R][nb] per rank -> [G][R][nb] everywhere
-            self.dist.all_gather_into_tensor(dst.view(-1), blk[0].view(-1), group=self.group)
+            # the one real exchange step of this path: [R][nb] per rank -> [G][R][nb] everywhere.  async_op: the
+            # collective runs on NCCL's stream after this kernel; the next kernel of the OTHER group is enqueued
+            # right behind this one and overlaps it ("pipelined"); "nccl" waits for it at the next half-step.
+            gr.pending[layer] = self.dist.all_gather_into_tensor(dst.view(-1), blk[0].view(-1), group=self.group,
+                                                                 async_op=True)
             self.gather_bytes += (self.G - 1) * blk[0].numel() * 2
         else:
             for i, g in enumerate(self.blocks):
@@ -130,5 +196,8 @@ class RowShardedSCA:
         """nsteps synchronous SCA steps; T: array of nsteps temperatures (T[k] applies to step k)."""
         T = np.atleast_1d(np.asarray(T, dtype=np.float64))
         for k in range(int(nsteps)):
-            self._half(1, seed, step_offset + k, float(T[min(k, len(T) - 1)]))
-            self._half(0, seed, step_offset + k, float(T[min(k, len(T) - 1)]))
+            Tk = float(T[min(k, len(T) - 1)])
+            for layer in (1, 0):
+                for gr in self.groups:
+                    self._half(gr, layer, seed, step_offset + k, Tk)
+        self._drain()

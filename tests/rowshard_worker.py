@@ -16,21 +16,21 @@ def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n, R, seed, nsteps = 1024, 200, 17, 4
+    n, R, seed, nsteps = 1024, 600, 17, 4
     S0 = synth.spins(3, R, n)
     T = np.array([1.0, 0.8, 0.6, 0.4])
     emu = rowshard.RowShardedSCA(n, R, seed=seed, q=1.0, emulate_blocks=dist.get_world_size(), device=local)
     emu.set_spins(S0)
     emu.run(nsteps, T, seed=7)
     ok, modes = True, []
-    for fused in (False, True):   # ncclAllGather between half-steps / peer stores fused into the epilogue
-        sca = rowshard.RowShardedSCA(n, R, seed=seed, q=1.0, device=local, fused=fused)
+    for exchange in ("nccl", "pipelined", "fused"):   # all-gather per half-step / pipelined over two replica groups /
+        sca = rowshard.RowShardedSCA(n, R, seed=seed, q=1.0, device=local, exchange=exchange)  # peer stores in the epilogue
         assert sca.distributed and sca.G == dist.get_world_size()
-        for rep in range(2):      # a second run on the same object exercises the re-initialisation barrier
+        for rep in range(2):      # a second run on the same object exercises the re-initialisation path
             sca.set_spins(S0)
             sca.run(nsteps, T, seed=7)
             ok = ok and np.array_equal(sca.get_spins(), emu.get_spins()) and np.array_equal(sca.get_hidden(), emu.get_hidden())
-        modes.append("fused" if sca.fused else "nccl" + (":" + getattr(sca, "fused_error", "") if fused else ""))
+        modes.append(sca.exchange + (":" + getattr(sca, "fused_error", "") if exchange != sca.exchange else ""))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if dist.get_rank() == 0:
