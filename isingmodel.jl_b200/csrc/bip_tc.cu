@@ -38,7 +38,15 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KiB
 constexpr int TC_B_BYTES = TC_BN_MAX * TC_BK * 2;      // 32 KiB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_EPI_WARPS = 16;  // 4 per TMEM lane quadrant
+#ifndef ISB_TC_EPI_WARPS
+#define ISB_TC_EPI_WARPS 16
+#endif
+#ifndef ISB_TC_CW
+#define ISB_TC_CW 16
+#endif
+constexpr int TC_EPI_WARPS = ISB_TC_EPI_WARPS;  // a multiple of 4: equal shares of the four TMEM lane quadrants
+constexpr int TC_CW = ISB_TC_CW;                // accumulator columns (units) per epilogue chunk: 8 or 16
+static_assert(TC_EPI_WARPS % 4 == 0 && (TC_CW == 8 || TC_CW == 16), "epilogue shape");
 constexpr int TC_THREADS = 32 * (4 + TC_EPI_WARPS);
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
@@ -179,6 +187,13 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -311,7 +326,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2
             const float cE = Tf > 0.f ? -2.0f * 1.4426950408889634f / Tf : 0.f;  // e^{-2x/T} = 2^{cE x}
             const uint64_t step_abs = p.step_abs0 + (uint64_t)(job.k - p.k0);
-            const int nchunks = L.bn >> 4;
+            constexpr int CW = TC_CW;
+            const int nchunks = L.bn / CW;
             const int a = tl & 1;
             mbar_wait_sleep(&tfull_bar[a], (tl >> 1) & 1);
             tc_fence_after();
@@ -319,24 +335,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             const int r = job.m0 + lrow;
             const bool row_ok = r < p.R && (!p.persist || lrow < p.rows_per_cta);
             for (int c = half; c < nchunks; c += TC_EPI_WARPS / 4) {
-                uint32_t v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TC_BN_MAX + c * 16), v);
-                const int u0 = job.n_blk * L.bn + c * 16;
+                uint32_t v[CW];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TC_BN_MAX + c * CW);
+                if constexpr (CW == 16)
+                    tmem_ld16(taddr, reinterpret_cast<uint32_t(&)[16]>(v));
+                else
+                    tmem_ld8(taddr, reinterpret_cast<uint32_t(&)[8]>(v));
+                const int u0 = job.n_blk * L.bn + c * CW;
                 if (!row_ok || u0 >= L.nout) continue;
                 __nv_bfloat16 *ob = L.out_bf + (int64_t)r * L.ldo + u0;
-                const bool full = u0 + 16 <= L.nout;
+                const bool full = u0 + CW <= L.nout;
                 // MomentumAnnealing multiplies the noise by the unit's own previous value: it is still in the
                 // output matrix (bf16 +-1; pad columns read as 0 and are never stored)
-                uint32_t oldw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                uint32_t oldw[CW / 2];
+#pragma unroll
+                for (int j = 0; j < CW / 2; ++j) oldw[j] = 0;
                 if (p.rule == ISB_BIP_MA) {
-                    const uint4 o0 = *reinterpret_cast<const uint4 *>(ob), o1 = *reinterpret_cast<const uint4 *>(ob + 8);
-                    oldw[0] = o0.x; oldw[1] = o0.y; oldw[2] = o0.z; oldw[3] = o0.w;
-                    oldw[4] = o1.x; oldw[5] = o1.y; oldw[6] = o1.z; oldw[7] = o1.w;
+#pragma unroll
+                    for (int q = 0; q < CW / 8; ++q) {
+                        const uint4 o = *reinterpret_cast<const uint4 *>(ob + 8 * q);
+                        oldw[4 * q] = o.x; oldw[4 * q + 1] = o.y; oldw[4 * q + 2] = o.z; oldw[4 * q + 3] = o.w;
+                    }
                 }
-                uint32_t sgn[16];  // bit 31 set <=> the unit goes to -1
+                uint32_t wb[CW / 2];  // packed bf16 +-1 = 0x3F80 | sign
+#pragma unroll
+                for (int j = 0; j < CW / 2; ++j) wb[j] = 0x3F803F80u;
                 if (EXTF) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < CW; ++j) {
                         const int u = u0 + j;
                         double x = 0.0;
                         if (u < L.nout) {
@@ -346,22 +372,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                             if (p.rule == ISB_BIP_MA) ft = ((oldw[j >> 1] >> (16 * (j & 1) + 15)) & 1u) ? -ft : ft;
                             x = __dsub_rn(__dmul_rn(2.0, __dadd_rn((double)__uint_as_float(v[j]), L.bias[u])), ft);
                         }
-                        sgn[j] = (x < 0.0) ? 0x80000000u : 0u;
+                        if (x < 0.0) wb[j >> 1] |= 0x8000u << (16 * (j & 1));
                     }
                 } else {
-                    float bf[16];
+                    float bf[CW];
                     if (full) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
+                        for (int q = 0; q < CW / 4; ++q) {
                             const float4 b4 = __ldg(reinterpret_cast<const float4 *>(L.bias_f + u0) + q);
                             bf[4 * q] = b4.x; bf[4 * q + 1] = b4.y; bf[4 * q + 2] = b4.z; bf[4 * q + 3] = b4.w;
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) bf[j] = u0 + j < L.nout ? __ldg(L.bias_f + u0 + j) : 0.f;
+                        for (int j = 0; j < CW; ++j) bf[j] = u0 + j < L.nout ? __ldg(L.bias_f + u0 + j) : 0.f;
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < CW / 4; ++q) {
                         // == philox_unit_block(seed, domain, r, step, unit >> 2) with the round keys hoisted
                         const Philox4 blk = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), (uint32_t)(r + p.r_off),
                                                            (L.domain << 28) | (uint32_t)(((L.u_off + u0) >> 2) + q), keys);
@@ -382,24 +408,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                                 const float l = cS * __log2f(u);
                                 t = x + (((oldw[j >> 1] >> (16 * (j & 1) + 15)) & 1u) ? -l : l);
                             }
-                            sgn[j] = __float_as_uint(t) & 0x80000000u;  // t < 0 (t is never NaN: u > 0, x finite; -0 cannot arise)
+                            // sign bit of t (t is never NaN: u > 0, x finite; -0 cannot arise) -> sign bit of the bf16
+                            wb[j >> 1] |= (j & 1) ? (__float_as_uint(t) & 0x80000000u) : ((__float_as_uint(t) & 0x80000000u) >> 16);
                         }
                     }
                 }
-                // bf16 +-1 = 0x3F80 | sign
-                uint32_t wb[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) wb[j] = 0x3F803F80u | (sgn[2 * j] >> 16) | sgn[2 * j + 1];
                 if (full) {
-                    *reinterpret_cast<uint4 *>(ob) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
-                    *reinterpret_cast<uint4 *>(ob + 8) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
-                    for (int q = 0; q < L.npeer; ++q) {  // peer stores over NVLink overlap the next tile's MMAs
-                        __nv_bfloat16 *pb = L.peer[q] + (int64_t)r * L.ldo + u0;
-                        *reinterpret_cast<uint4 *>(pb) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
-                        *reinterpret_cast<uint4 *>(pb + 8) = make_uint4(wb[4], wb[5], wb[6], wb[7]);
+#pragma unroll
+                    for (int q = 0; q < CW / 8; ++q)
+                        *reinterpret_cast<uint4 *>(ob + 8 * q) = make_uint4(wb[4 * q], wb[4 * q + 1], wb[4 * q + 2], wb[4 * q + 3]);
+                    for (int pq = 0; pq < L.npeer; ++pq) {  // peer stores over NVLink overlap the next tile's MMAs
+                        __nv_bfloat16 *pb = L.peer[pq] + (int64_t)r * L.ldo + u0;
+#pragma unroll
+                        for (int q = 0; q < CW / 8; ++q)
+                            *reinterpret_cast<uint4 *>(pb + 8 * q) = make_uint4(wb[4 * q], wb[4 * q + 1], wb[4 * q + 2], wb[4 * q + 3]);
                     }
                 } else {
-                    for (int j = 0; j < 16 && u0 + j < L.nout; ++j)
+                    for (int j = 0; j < CW && u0 + j < L.nout; ++j)
                         ob[j] = __ushort_as_bfloat16((unsigned short)((wb[j >> 1] >> (16 * (j & 1))) & 0xFFFFu));
                 }
             }
