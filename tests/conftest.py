@@ -13,6 +13,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The tests load the in-tree libising_b200.so; build it (incremental make, nvcc cross-compiles without a GPU)
+    when it is missing, e.g. on a fresh checkout where build() has not run yet."""
+    lib = os.path.join(ROOT, "isingmodel.jl_b200", "libising_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "isingmodel.jl_b200", "csrc"), "-j", "8"],
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=False)
+
+
 @pytest.fixture(scope="session")
 def pkg():
     import isingmodel_jl_b200
