@@ -71,7 +71,7 @@ enum {
                          every partial sum is exactly representable (integer / dyadic J), and
                          equal up to decisions closer to zero than ~1e-13 otherwise             */
     ISB_PREC_F32 = 1, /* J and fields in float; decisions still taken in double                 */
-    ISB_PREC_AUTO = 2,/* F64 fields; J stored as float iff that is lossless                      */
+    ISB_PREC_AUTO = 2,/* the library's choice for the model kind (dense / sparse J: F64 throughout)   */
     ISB_PREC_BF16X3 = 3, /* bipartite tensor path: W split into 3 bf16 terms, fp32 accumulation */
     ISB_PREC_BF16X1 = 4, /* bipartite tensor path: W rounded to one bf16 term (exact when W is)  */
     ISB_PREC_BF16X2 = 5  /* bipartite tensor path: 2 bf16 terms (16 mantissa bits: the split error, 2^-17

@@ -218,7 +218,11 @@ int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const doub
     m->npad = npad;
     m->npl = npl;
     m->fast_ok = fast;
-    m->j_is_f32 = prec == ISB_PREC_F32 || (prec == ISB_PREC_AUTO && lossless_f32);
+    // Float storage of J only together with float fields: measured on B200, float rows under Float64 fields are
+    // SLOWER than double rows (227 vs 196 ms on the C2 schedule) — the 32 F2F conversions per row cost more than the
+    // halved shared-memory traffic saves.  ISB_PREC_AUTO therefore means Float64 throughout for dense models.
+    m->j_is_f32 = prec == ISB_PREC_F32;
+    (void)lossless_f32;
     const size_t nn = (size_t)npad * npad;
     int rc = ISB_OK;
     do {

@@ -13,8 +13,6 @@ namespace isb {
 
 cudaError_t launch_ssf_dd(const SsfParams &p, int npl, bool list, bool tma, int cl, int grid, int threads,
                           size_t smem, cudaStream_t st);
-cudaError_t launch_ssf_df(const SsfParams &p, int npl, bool list, bool tma, int cl, int grid, int threads,
-                          size_t smem, cudaStream_t st);
 cudaError_t launch_ssf_ff(const SsfParams &p, int npl, bool list, bool tma, int cl, int grid, int threads,
                           size_t smem, cudaStream_t st);
 
@@ -286,10 +284,8 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
     const bool list = order != ISB_ORDER_SEQUENTIAL;
     const int threads = 32 * (nw + 1);
     cudaError_t ce;
-    if (hd && !jf)
+    if (hd)
         ce = launch_ssf_dd(p, npl, list, tma, cl, ctas, threads, smem, ctx->stream);
-    else if (hd && jf)
-        ce = launch_ssf_df(p, npl, list, tma, cl, ctas, threads, smem, ctx->stream);
     else
         ce = launch_ssf_ff(p, npl, list, tma, cl, ctas, threads, smem, ctx->stream);
     if (ce != cudaSuccess)

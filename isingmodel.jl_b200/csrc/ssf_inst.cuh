@@ -1,5 +1,5 @@
 // ssf_inst.cuh — instantiates ssf_kernel for one (field type, coupling type) pair; included by
-// ssf_inst_dd.cu / ssf_inst_df.cu / ssf_inst_ff.cu so the three pairs compile in parallel.
+// ssf_inst_dd.cu (Float64 fields and couplings) / ssf_inst_ff.cu (float fields and couplings), compiled in parallel.
 #pragma once
 #include "ssf_kernel.cuh"
 
