@@ -94,33 +94,70 @@ __global__ void __launch_bounds__(BIPX_THREADS) bip_half_kernel(const BipHalfPar
     }
 }
 
-// E_r = -sum_i sigma_i (sum_j W_ij tau_j) - sum_i h_i sigma_i - sum_j b_j tau_j ; one CTA per chain.
-__global__ void bip_energy_kernel(const double *__restrict__ Wt /*[nh][nv]*/, const double *__restrict__ h,
-                                  const double *__restrict__ b, const int8_t *sig, int64_t lds, const int8_t *tau,
-                                  int64_t ldh, int nv, int nh, double *E) {
-    extern __shared__ int8_t tsh[];  // [nh]
-    __shared__ double red[32];
-    const int r = blockIdx.x;
-    for (int j = threadIdx.x; j < nh; j += blockDim.x) tsh[j] = tau[(int64_t)r * ldh + j];
-    __syncthreads();
-    double part = 0.0;
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-        double row = 0.0;
-        for (int j = 0; j < nh; ++j) row += Wt[(int64_t)j * nv + i] * (double)tsh[j];
-        const double si = (double)sig[(int64_t)r * lds + i];
-        part -= si * row + h[i] * si;
+// E_r = -sum_i sigma_i (sum_j W_ij tau_j) - sum_i h_i sigma_i - sum_j b_j tau_j.
+// Pass 1: CTA (x, y) covers 128 visible units of BIPX_CH chains (one coalesced read of a W row serves all of
+// them, as in bip_half_kernel) and writes one partial sum per chain; pass 2 adds the partials of a chain in a
+// fixed order (no atomics: the energies are reproducible bit for bit).
+__global__ void __launch_bounds__(BIPX_THREADS)
+bip_energy_partial_kernel(const double *__restrict__ Wt /*[nh][nv]*/, const double *__restrict__ h,
+                          const double *__restrict__ b, const int8_t *sig, int64_t lds, const int8_t *tau, int64_t ldh,
+                          int nv, int nh, int R, double *partial /*[gridDim.x][R]*/) {
+    extern __shared__ unsigned char tmask[];  // [nh] bit c = hidden spin of chain c is +1
+    __shared__ double red[BIPX_THREADS / 32][BIPX_CH];
+    const int r0 = blockIdx.y * BIPX_CH;
+    const int nch = min(BIPX_CH, R - r0);
+    for (int j = threadIdx.x; j < nh; j += blockDim.x) {
+        unsigned m = 0;
+        for (int c = 0; c < nch; ++c) m |= (tau[(int64_t)(r0 + c) * ldh + j] > 0 ? 1u : 0u) << c;
+        tmask[j] = (unsigned char)m;
     }
-    for (int j = threadIdx.x; j < nh; j += blockDim.x) part -= b[j] * (double)tsh[j];
-    part = warp_sum(part);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double part[BIPX_CH];
+#pragma unroll
+    for (int c = 0; c < BIPX_CH; ++c) part[c] = 0.0;
+    if (i < nv) {
+        double row[BIPX_CH];
+#pragma unroll
+        for (int c = 0; c < BIPX_CH; ++c) row[c] = 0.0;
+        for (int j = 0; j < nh; ++j) {
+            const double w = __ldg(Wt + (int64_t)j * nv + i);
+            const unsigned m = tmask[j];
+#pragma unroll
+            for (int c = 0; c < BIPX_CH; ++c) row[c] += ((m >> c) & 1u) ? w : -w;
+        }
+        const double hi = h[i];
+        for (int c = 0; c < nch; ++c) {
+            const double si = (double)sig[(int64_t)(r0 + c) * lds + i];
+            part[c] = -(si * row[c] + hi * si);
+        }
+    }
+    if (blockIdx.x == 0)  // the hidden-bias term, once per chain
+        for (int j = threadIdx.x; j < nh; j += blockDim.x) {
+            const double bj = b[j];
+            const unsigned m = tmask[j];
+#pragma unroll
+            for (int c = 0; c < BIPX_CH; ++c) part[c] -= ((m >> c) & 1u) ? bj : -bj;
+        }
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) red[w] = part;
-    __syncthreads();
-    if (w == 0) {
-        const int nwarp = blockDim.x >> 5;
-        part = lane < nwarp ? red[lane] : 0.0;
-        part = warp_sum(part);
-        if (lane == 0) E[r] = part;
+#pragma unroll
+    for (int c = 0; c < BIPX_CH; ++c) {
+        const double v = warp_sum(part[c]);
+        if (lane == 0) red[w][c] = v;
     }
+    __syncthreads();
+    if (threadIdx.x < nch) {
+        double acc = 0.0;
+        for (int ww = 0; ww < BIPX_THREADS / 32; ++ww) acc += red[ww][threadIdx.x];
+        partial[(int64_t)blockIdx.x * R + r0 + threadIdx.x] = acc;
+    }
+}
+__global__ void bip_energy_reduce_kernel(const double *partial, int nparts, int R, double *E) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double acc = 0.0;
+    for (int k = 0; k < nparts; ++k) acc += partial[(int64_t)k * R + r];
+    E[r] = acc;
 }
 
 __global__ void philox_bip_fluct_kernel(int rule, uint64_t seed, uint64_t step_offset, uint32_t domain, int nunits,
@@ -151,9 +188,16 @@ int philox_bip_fluct_device(isb_ctx *ctx, int rule, uint64_t seed, uint64_t step
 
 int bip_energy_device(isb_ens *e, double *d_E) {
     isb_model *m = e->model;
-    bip_energy_kernel<<<e->R, 256, m->nh, m->ctx->stream>>>(m->Wt64, m->hb64, m->bb64, e->spins, e->lds, e->hidden,
-                                                            e->ldh, m->nv, m->nh, d_E);
-    ISB_CUDA(m->ctx, cudaGetLastError());
+    isb_ctx *ctx = m->ctx;
+    const int nparts = (m->nv + BIPX_THREADS - 1) / BIPX_THREADS;
+    double *partial;
+    int rc = dev_reserve(ctx, SCR_TC0, (size_t)nparts * e->R * sizeof(double), (void **)&partial);
+    if (rc) return rc;
+    dim3 grid(nparts, (e->R + BIPX_CH - 1) / BIPX_CH);
+    bip_energy_partial_kernel<<<grid, BIPX_THREADS, m->nh, ctx->stream>>>(m->Wt64, m->hb64, m->bb64, e->spins, e->lds,
+                                                                          e->hidden, e->ldh, m->nv, m->nh, e->R, partial);
+    bip_energy_reduce_kernel<<<(e->R + 255) / 256, 256, 0, ctx->stream>>>(partial, nparts, e->R, d_E);
+    ISB_CUDA(ctx, cudaGetLastError());
     return ISB_OK;
 }
 
