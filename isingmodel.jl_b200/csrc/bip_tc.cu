@@ -389,8 +389,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
 #pragma unroll
                     for (int q = 0; q < CW / 4; ++q) {
                         // == philox_unit_block(seed, domain, r, step, unit >> 2) with the round keys hoisted
+#ifdef ISB_TC_PROBE_NO_PHILOX  // timing probe only: how much of a half-step is the noise generation?
+                        const Philox4 blk{(uint32_t)step_abs * 2654435761u + (uint32_t)r, (uint32_t)(u0 + q) * 40503u, (uint32_t)r << 7, keys.k0[3]};
+#else
                         const Philox4 blk = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), (uint32_t)(r + p.r_off),
                                                            (L.domain << 28) | (uint32_t)(((L.u_off + u0) >> 2) + q), keys);
+#endif
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int j = q * 4 + e;
