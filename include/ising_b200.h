@@ -181,6 +181,14 @@ int isb_bip_run(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const doub
                 const double *Fh, uint64_t seed, uint64_t step_offset, const double *Tsched,
                 int64_t nT, int64_t steps_per_T, int64_t trace_every, double *out_E);
 
+/* isb_bip_run that also records both layers of every chain at each trace point (out_Sv: [ntr][R][ldSv],
+ * out_Sh: [ntr][R][ldSh] int8; either may be NULL): the snapshots behind the streaming sampler of
+ * makeSampler!(::UpdatingAlgorithmOnBipartiteGraph, n) (src/SamplingHelper.jl:124-132). */
+int isb_bip_run_snap(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *Fv, const double *Fh,
+                     uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT, int64_t steps_per_T,
+                     int64_t trace_every, double *out_E, int8_t *out_Sv, int64_t ldSv, int8_t *out_Sh,
+                     int64_t ldSh);
+
 /* Fluctuations as ISB_FLUCT_PHILOX draws them in isb_bip_run: layer 0 = visible, 1 = hidden;
  * out[(r - r0)][k][unit]. */
 int isb_philox_bip_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64_t step_offset,

@@ -169,14 +169,28 @@ def makeSampler_(updatingAlgorithm, maxMCSteps, annealingSchedule=None, rng=None
                 ss._set_snapshot(None)
                 k += full
                 continue
-            m = min(stride, maxMCSteps - k)
+            # bipartite / multi-spin: the same replay from kernel-recorded snapshots of both layers
             b = _bip(ua)
-            b.spinSystem._ensemble().bip_run(b._rule, m, Fv=Fv[k:k + m], Fh=Fh[k:k + m], T=T[k + 1:k + 1 + m])
-            b.spinSystem._dev_newer = True
+            ss = b.spinSystem
+            per_yield = max(1, stride)
+            m = min(maxMCSteps - k, max(per_yield, (chunk // per_yield) * per_yield))
+            full = (m // per_yield) * per_yield
+            if full == 0:
+                full = m
+                per_yield = m
+            E, Sv, Sh = ss._ensemble().bip_run(b._rule, full, Fv=Fv[k:k + full], Fh=Fh[k:k + full], T=T[k + 1:k + 1 + full],
+                                               trace_every=per_yield, want_S=True)
+            ss._dev_newer = True
+            for j in range(full // per_yield):
+                ss._set_snapshot(Sv[j], Sh[j], E[j])
+                if b is not ua:
+                    ua.spinSystem._set_snapshot(Sv[j])
+                ua.temperature = float(T[k + (j + 1) * per_yield])     # :128
+                yield ua                                               # :130
+            ss._set_snapshot(None)
             if b is not ua:
+                ua.spinSystem._set_snapshot(None)
                 ua._sync_back()
-            k += m
-            ua.temperature = float(T[k])                           # :128
-            yield ua                                               # :130
+            k += full
 
     return gen()

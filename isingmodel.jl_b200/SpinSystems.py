@@ -236,10 +236,28 @@ class SpinSystemOnBipartiteGraph:
         self._device, self._prec = device, prec
         self._model = self._ens = None
         self._dev_newer = False
+        self._snap = None       # (visible2d, hidden2d, energies or None) while a recorded trajectory is replayed
+        self._query_ens = None
+        self._query_loaded = None
 
     @property
     def replicas(self):
         return self._host_s.shape[0]
+
+    def _set_snapshot(self, visible2d, hidden2d=None, energies=None):
+        self._snap = None if visible2d is None else (visible2d, hidden2d, energies)
+
+    def _query_ensemble(self):
+        ens = self._ensemble()
+        if self._snap is None:
+            return ens
+        if self._query_ens is None:
+            self._query_ens = _lib.Ensemble(self._model, self.replicas)
+        if self._query_loaded is not self._snap[0]:
+            self._query_ens.set_spins(self._snap[0])
+            self._query_ens.set_hidden(self._snap[1])
+            self._query_loaded = self._snap[0]
+        return self._query_ens
 
     def _ensemble(self):
         if self._ens is None:
@@ -258,10 +276,12 @@ class SpinSystemOnBipartiteGraph:
 
     def _invalidate_model(self):
         self._pull()
-        self._ens = self._model = None
+        self._ens = self._model = self._query_ens = self._query_loaded = None
 
     @property
     def spinConfiguration(self):
+        if self._snap is not None:
+            return _squeeze(self, self._snap[0])
         self._pull()
         return _squeeze(self, self._host_s)
 
@@ -277,6 +297,8 @@ class SpinSystemOnBipartiteGraph:
 
     @property
     def hiddenLayer(self):
+        if self._snap is not None:
+            return _squeeze(self, self._snap[1])
         self._pull()
         return _squeeze(self, self._host_t)
 
@@ -379,8 +401,8 @@ def calcEnergy(x):
     """src/SpinSystems.jl:68-73 / :139-145 (on the GPU: isb_ens_energy)."""
     ss = _ss(x)
     snap = getattr(ss, "_snap", None)
-    if snap is not None and snap[1] is not None:
-        E = snap[1]  # recorded by the kernel at this trace point
+    if snap is not None and snap[-1] is not None:
+        E = snap[-1]  # recorded by the kernel at this trace point
     elif snap is not None:
         E = ss._query_ensemble().energy()
     else:
@@ -403,7 +425,7 @@ def calcLocalMagneticField(x, nodeIndex=None):
 def calcLocalAuxiliaryBias(x):
     """src/SpinSystems.jl:154-159 (isb_ens_local_aux_bias)."""
     ss = _ss(x)
-    A = ss._ensemble().local_aux_bias()
+    A = (ss._query_ensemble() if getattr(ss, "_snap", None) is not None else ss._ensemble()).local_aux_bias()
     return A[0] if ss._single else A
 
 

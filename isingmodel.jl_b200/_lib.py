@@ -81,6 +81,7 @@ SIGNATURES = {
     "isb_philox_nodes": (_i, [_vp, _i, _u64, _u64, _i64, _vp]),
     "isb_philox_raw": (_i, [_vp, _vp, _vp, _i, _vp]),
     "isb_bip_run": (_i, [_vp, _i, _i64, _i, _vp, _vp, _u64, _u64, _vp, _i64, _i64, _i64, _vp]),
+    "isb_bip_run_snap": (_i, [_vp, _i, _i64, _i, _vp, _vp, _u64, _u64, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _i64]),
     "isb_philox_bip_fluct": (_i, [_vp, _i, _i, _u64, _u64, _i, _i, _i, _i, _i64, _vp]),
     "isb_shard_model_rows": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
     "isb_shard_model_sk": (_i, [_vp, _i, _i, _i, _u64, _d, _i, C.POINTER(_vp)]),
@@ -392,8 +393,9 @@ class Ensemble:
         return {"flips": flips, "E": E, "M": M, "S": S}
 
     def bip_run(self, rule, nsteps, *, Fv=None, Fh=None, fluct_per_replica=False, seed=0, step_offset=0, T=None,
-                steps_per_T=1, trace_every=0):
-        """isb_bip_run. Fv: [nsteps][nv] (shared) or [R][nsteps][nv]; returns E[ntr][R] or None."""
+                steps_per_T=1, trace_every=0, want_S=False):
+        """isb_bip_run / isb_bip_run_snap. Fv: [nsteps][nv] (shared) or [R][nsteps][nv]; returns E[ntr][R] or None,
+        or (E, Sv[ntr][R][nv], Sh[ntr][R][nh]) with want_S."""
         nsteps = int(nsteps)
         if Fv is None and Fh is None:
             mode, fv, fh = FLUCT_PHILOX, None, None
@@ -407,10 +409,12 @@ class Ensemble:
         Ta = None if T is None else np.ascontiguousarray(np.atleast_1d(T), dtype=np.float64)
         ntr = nsteps // trace_every if trace_every > 0 else 0
         E = np.zeros((ntr, self.R)) if ntr else None
-        self._chk(load().isb_bip_run(self.handle, rule, nsteps, mode, ptr(fv), ptr(fh), int(seed), int(step_offset),
-                                     ptr(Ta), 0 if Ta is None else Ta.size, int(steps_per_T), int(trace_every),
-                                     ptr(E)))
-        return E
+        Sv = np.zeros((ntr, self.R, self.nv), dtype=np.int8) if (ntr and want_S) else None
+        Sh = np.zeros((ntr, self.R, self.nh), dtype=np.int8) if (ntr and want_S) else None
+        self._chk(load().isb_bip_run_snap(self.handle, rule, nsteps, mode, ptr(fv), ptr(fh), int(seed), int(step_offset),
+                                          ptr(Ta), 0 if Ta is None else Ta.size, int(steps_per_T), int(trace_every),
+                                          ptr(E), ptr(Sv), self.nv, ptr(Sh), self.nh))
+        return (E, Sv, Sh) if want_S else E
 
     def last_stats(self):
         ms, nl, hi, do = _d(0), _i64(0), _i64(0), _i64(0)

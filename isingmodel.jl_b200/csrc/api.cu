@@ -758,6 +758,13 @@ int isb_philox_raw(isb_ctx *ctx, const uint32_t *ctr, const uint32_t key[2], int
 int isb_bip_run(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *Fv, const double *Fh,
                 uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT, int64_t steps_per_T,
                 int64_t trace_every, double *out_E) {
+    return isb_bip_run_snap(e, rule, nsteps, fluct_mode, Fv, Fh, seed, step_offset, Tsched, nT, steps_per_T, trace_every,
+                            out_E, nullptr, 0, nullptr, 0);
+}
+
+int isb_bip_run_snap(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *Fv, const double *Fh,
+                     uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT, int64_t steps_per_T,
+                     int64_t trace_every, double *out_E, int8_t *out_Sv, int64_t ldSv, int8_t *out_Sh, int64_t ldSh) {
     if (!e) return ISB_ERR_ARG;
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
@@ -787,18 +794,32 @@ int isb_bip_run(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const doub
     }
     ISB_TRY(isb::dev_reserve(ctx, isb::SCR_T, (size_t)nT * sizeof(double), (void **)&d_T));
     ISB_TRY(h2d(ctx, d_T, Tsched, (size_t)nT * sizeof(double), &e->last_h2d));
-    const int64_t ntr = (trace_every > 0 && out_E) ? nsteps / trace_every : 0;
-    if (ntr > 0) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_E, (size_t)ntr * e->R * sizeof(double), (void **)&d_E));
+    if ((out_Sv && ldSv < m->nv) || (out_Sh && ldSh < m->nh)) return fail(ctx, ISB_ERR_SIZE, "%s: snapshot pitch too small", who);
+    const int64_t ntr = (trace_every > 0 && (out_E || out_Sv || out_Sh)) ? nsteps / trace_every : 0;
+    if (ntr > 0 && out_E) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_E, (size_t)ntr * e->R * sizeof(double), (void **)&d_E));
+    int8_t *d_Sv = nullptr, *d_Sh = nullptr;
+    if (ntr > 0 && out_Sv) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_S, (size_t)ntr * e->R * m->nv, (void **)&d_Sv));
+    if (ntr > 0 && out_Sh) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_S2, (size_t)ntr * e->R * m->nh, (void **)&d_Sh));
 
     ISB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (m->prec == ISB_PREC_F64)
         ISB_TRY(isb::bip_run_exact_device(e, rule, nsteps, fluct_mode, d_Fv, d_Fh, seed, step_offset, d_T, steps_per_T,
-                                          trace_every, d_E));
+                                          trace_every, d_E, d_Sv, d_Sh));
     else
         ISB_TRY(isb::bip_run_tc_device(e, rule, nsteps, fluct_mode, d_Fv, d_Fh, seed, step_offset, d_T, steps_per_T,
-                                       trace_every, d_E));
+                                       trace_every, d_E, d_Sv, d_Sh));
     ISB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     if (d_E) ISB_TRY(d2h(ctx, out_E, d_E, (size_t)ntr * e->R * sizeof(double), &e->last_d2h));
+    if (d_Sv) {
+        ISB_CUDA(ctx, cudaMemcpy2DAsync(out_Sv, (size_t)ldSv, d_Sv, (size_t)m->nv, (size_t)m->nv, (size_t)ntr * e->R,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+        e->last_d2h += ntr * e->R * m->nv;
+    }
+    if (d_Sh) {
+        ISB_CUDA(ctx, cudaMemcpy2DAsync(out_Sh, (size_t)ldSh, d_Sh, (size_t)m->nh, (size_t)m->nh, (size_t)ntr * e->R,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+        e->last_d2h += ntr * e->R * m->nh;
+    }
     cudaError_t ce = cudaStreamSynchronize(ctx->stream);
     if (ce != cudaSuccess) return fail(ctx, ISB_ERR_CUDA, "%s: kernel failed: %s", who, cudaGetErrorString(ce));
     float ms = 0.f;

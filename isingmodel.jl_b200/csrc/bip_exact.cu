@@ -229,9 +229,23 @@ int bip_field_device(isb_ens *e, int layer, double *d_out, int64_t ld) {
     return ISB_OK;
 }
 
+
+// copies the canonical int8 layers into the snapshot buffers of trace point `ntr` ([ntr][R][n], dense pitch)
+int bip_snapshot(isb_ens *e, int64_t ntr, int8_t *d_Sv, int8_t *d_Sh) {
+    isb_model *m = e->model;
+    isb_ctx *ctx = m->ctx;
+    if (d_Sv)
+        ISB_CUDA(ctx, cudaMemcpy2DAsync(d_Sv + ntr * e->R * m->nv, (size_t)m->nv, e->spins, (size_t)e->lds, (size_t)m->nv,
+                                        (size_t)e->R, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_Sh)
+        ISB_CUDA(ctx, cudaMemcpy2DAsync(d_Sh + ntr * e->R * m->nh, (size_t)m->nh, e->hidden, (size_t)e->ldh, (size_t)m->nh,
+                                        (size_t)e->R, cudaMemcpyDeviceToDevice, ctx->stream));
+    return ISB_OK;
+}
+
 int bip_run_exact_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv,
                          const double *d_Fh, uint64_t seed, uint64_t step_offset, const double *d_T,
-                         int64_t steps_per_T, int64_t trace_every, double *d_E) {
+                         int64_t steps_per_T, int64_t trace_every, double *d_E, int8_t *d_Sv, int8_t *d_Sh) {
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
     int64_t ntr = 0;
@@ -253,10 +267,14 @@ int bip_run_exact_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, c
             ISB_CUDA(ctx, cudaGetLastError());
             e->last_launches += 1;
         }
-        if (d_E && trace_every > 0 && (k + 1) % trace_every == 0) {
-            int rc = bip_energy_device(e, d_E + ntr * e->R);
+        if ((d_E || d_Sv || d_Sh) && trace_every > 0 && (k + 1) % trace_every == 0) {
+            if (d_E) {
+                int rc = bip_energy_device(e, d_E + ntr * e->R);
+                if (rc) return rc;
+                e->last_launches += 2;
+            }
+            int rc = bip_snapshot(e, ntr, d_Sv, d_Sh);
             if (rc) return rc;
-            e->last_launches += 1;
             ++ntr;
         }
     }

@@ -897,7 +897,7 @@ int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, in
 
 int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv, const double *d_Fh,
                       uint64_t seed, uint64_t step_offset, const double *d_T, int64_t steps_per_T, int64_t trace_every,
-                      double *d_E) {
+                      double *d_E, int8_t *d_Sv, int8_t *d_Sh) {
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
     TcModel *t = (TcModel *)m->tc;
@@ -916,7 +916,7 @@ int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, cons
         return ISB_OK;
     };
     int64_t ntr = 0;
-    const bool tracing = d_E && trace_every > 0;
+    const bool tracing = (d_E || d_Sv || d_Sh) && trace_every > 0;
     for (int64_t k0 = 0; k0 < nsteps;) {
         const int64_t nseg = tracing ? std::min<int64_t>(trace_every - (k0 % trace_every), nsteps - k0)
                                      : std::min<int64_t>(nsteps - k0, 1 << 20);
@@ -926,9 +926,13 @@ int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, cons
         if (tracing && k0 % trace_every == 0) {
             rc = sync_canonical();
             if (rc) return rc;
-            rc = bip_energy_device(e, d_E + ntr * e->R);
+            if (d_E) {
+                rc = bip_energy_device(e, d_E + ntr * e->R);
+                if (rc) return rc;
+                e->last_launches += 2;
+            }
+            rc = bip_snapshot(e, ntr, d_Sv, d_Sh);
             if (rc) return rc;
-            e->last_launches += 1;
             ++ntr;
         }
     }

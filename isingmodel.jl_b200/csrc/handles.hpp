@@ -114,7 +114,8 @@ int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const
 // bip_exact.cu
 int bip_run_exact_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv,
                          const double *d_Fh, uint64_t seed, uint64_t step_offset, const double *d_T,
-                         int64_t steps_per_T, int64_t trace_every, double *d_E);
+                         int64_t steps_per_T, int64_t trace_every, double *d_E, int8_t *d_Sv, int8_t *d_Sh);
+int bip_snapshot(isb_ens *e, int64_t ntr, int8_t *d_Sv, int8_t *d_Sh);
 int bip_energy_device(isb_ens *e, double *d_E);
 int bip_field_device(isb_ens *e, int layer, double *d_out, int64_t ld);  // layer 0: W tau + h, 1: W' sigma + b
 int philox_bip_fluct_device(isb_ctx *ctx, int rule, uint64_t seed, uint64_t step_offset, int layer,
@@ -131,6 +132,6 @@ int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, in
 int sk_rows_device(isb_ctx *ctx, int n, uint64_t seed, int row0, int nrows, double *d_out);
 int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv,
                       const double *d_Fh, uint64_t seed, uint64_t step_offset, const double *d_T,
-                      int64_t steps_per_T, int64_t trace_every, double *d_E);
+                      int64_t steps_per_T, int64_t trace_every, double *d_E, int8_t *d_Sv, int8_t *d_Sh);
 
 }  // namespace isb

@@ -117,3 +117,28 @@ def test_makesampler_replays_every_step(pkg, ctx, orc, synth):
     ua = pkg.SingleSpinFlip.GlauberDynamics(ss, 1.0)
     items = sum(1 for _ in pkg.SamplingHelper.makeSampler_(ua, 103, rng=np.random.default_rng(1), stride=10, chunk=40))
     assert items == 1 + 10 + 1
+
+
+def test_makesampler_bipartite_replays_every_step(pkg, ctx, orc, synth):
+    """The bipartite sampler (src/SamplingHelper.jl:110-133): n + 1 yields, both layers and the energy after every
+    step equal the oracle's, with the reference's draw order (all visible fluctuations first, then all hidden)."""
+    nv, nh, n = 6, 4, 40
+    W, h, b = synth.bipartite_W(nv, nh, 3, 0.8)
+    s0, t0 = synth.spins(4, 1, nv)[0], synth.spins(5, 1, nh)[0]
+    sched = lambda k: 1.5 * 0.95 ** k  # noqa: E731
+    for cls, rule in ((pkg.OnBipartiteGraph.StochasticCellularAutomata, 0), (pkg.OnBipartiteGraph.MomentumAnnealing, 1)):
+        ss = pkg.OnBipartiteGraph.SpinSystemOnBipartiteGraph(s0.copy(), t0.copy(), W, h, b)
+        ua = cls(ss, 1.5)
+        rng = np.random.default_rng(11)
+        states = [(u.spinSystem.spinConfiguration.copy(), u.spinSystem.hiddenLayer.copy(), pkg.SpinSystems.calcEnergy(u))
+                  for u in pkg.SamplingHelper.makeSampler_(ua, n, annealingSchedule=sched, rng=rng, chunk=16)]
+        assert len(states) == n + 1
+        rng = np.random.default_rng(11)
+        Fv = ua.distribution.rand(rng, (n, nv))
+        Fh = ua.distribution.rand(rng, (n, nh))
+        s, t = s0.copy(), t0.copy()
+        for k in range(n):
+            s, t, _ = orc.bip_run(rule, W, h, b, s, t, 1, Fv[k:k + 1], Fh[k:k + 1], np.array([sched(k + 1)]))
+            assert np.array_equal(states[k + 1][0], s) and np.array_equal(states[k + 1][1], t), k
+            assert abs(states[k + 1][2] - orc.bip_energy(W, h, b, s, t)) < 1e-9
+        assert np.array_equal(ss.spinConfiguration, s) and np.array_equal(ss.hiddenLayer, t)
