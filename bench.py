@@ -443,6 +443,7 @@ def c5_main(args):
                        "n": n, "rows_per_gpu": nb, "replicas": R, "coupling_storage": prec_name,
                        "collective": {"pipelined": "ncclAllGather per half-step, hidden under the other replica group's GEMM",
                                       "nccl": "ncclAllGather per half-step (torch.distributed)",
+                                      "copy": "copy-engine pushes into symmetric memory + barrier, hidden under the other replica group's GEMM",
                                       "fused": "peer stores fused into the sampling epilogue (symmetric memory) + barrier",
                                       "local": "none (1 GPU)"}[sca.exchange],
                        "l2": "flushed between timed steps; W block (>= 1 GiB) exceeds L2"},

@@ -8,7 +8,10 @@ torch is plumbing here: device buffers, streams, and the collective.
 
 Exchange modes (``exchange=``), all bit-identical, measured on 8 x B200 at N = 65536, R = 1024 (ms per half-step,
 bf16x1 / bf16x3; the MMA-only target is 0.81 / 2.43):
-  "nccl"      (default) one ncclAllGather after every half-step kernel                           1.12 / 3.11
+  "copy"      (default) two replica groups; every rank pushes its freshly sampled block into all ranks' gathered
+              matrices with the COPY ENGINES (symmetric memory, cudaMemcpyAsync on a side stream, then a
+              cross-GPU barrier) while the other group's GEMM owns the SMs: the exchange hides     0.92 / 2.88
+  "nccl"      one ncclAllGather after every half-step kernel (fallback)                          1.11 / 3.11
   "pipelined" the replicas are split into two groups and one group's all-gather runs on NCCL's stream under
               the other group's GEMM (chains are independent).  NCCL's CTAs and the persistent GEMM CTAs (one
               per SM, all of its shared memory) contend for the SMs: slower                       1.42 / 4.00
@@ -72,10 +75,10 @@ class RowShardedSCA:
         if fused is not None and exchange is None:  # older spelling
             exchange = "fused" if fused else "nccl"
         if exchange is None:
-            exchange = "nccl"
+            exchange = "copy"
         if not self.distributed:
             exchange = "local"
-        if exchange == "pipelined" and self.R < 256:
+        if exchange in ("pipelined", "copy") and self.R < 256:
             exchange = "nccl"
         self.exchange = exchange
         self.ctx = _lib.context(device)
@@ -92,6 +95,15 @@ class RowShardedSCA:
                 self.models.append(_lib.Model.shard_sk(self.ctx, self.n, self.G, g, int(seed), q, prec))
         symm = None
         self.fused = False
+        self.cstream = None
+        if exchange == "copy":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                symm = symm_mem
+                self.cstream = torch.cuda.Stream(device=self.dev)
+            except Exception as exc:  # pragma: no cover
+                self.fused_error = repr(exc)
+                self.exchange = exchange = "nccl"
         if exchange == "fused" and 2 <= self.G <= 8:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
@@ -101,7 +113,7 @@ class RowShardedSCA:
                 self.fused_error = repr(exc)
                 self.exchange = exchange = "nccl"
         grp = group if group is not None else (dist.group.WORLD if self.distributed else None)
-        if exchange == "pipelined":
+        if exchange in ("pipelined", "copy"):
             half = (self.R // 2 + 127) // 128 * 128   # whole 128-replica tiles in the first group
             slices = [(0, half), (half, self.R - half)]
         else:
@@ -110,8 +122,9 @@ class RowShardedSCA:
             self.groups = [_Group(r0, Rg, self.G, self.nb, len(self.blocks), self.dev, torch, symm, grp)
                            for r0, Rg in slices if Rg > 0]
         except Exception as exc:  # pragma: no cover - symmetric memory unavailable on this driver
-            if not self.fused:
+            if not self.fused and self.cstream is None:
                 raise
+            self.cstream = None
             self.fused, self.fused_error, self.exchange = False, repr(exc), "nccl"
             self.groups = [_Group(0, self.R, self.G, self.nb, len(self.blocks), self.dev, torch)]
         self.launches = 0
@@ -130,7 +143,7 @@ class RowShardedSCA:
             for i, g in enumerate(self.blocks):
                 gr.blk_v[i].copy_(full[g])
                 gr.blk_h[i].copy_(full[g])
-        if self.fused:
+        if self.fused or self.cstream is not None:
             # no peer may store into this rank's matrices before they hold the initial configuration
             torch.cuda.synchronize(self.dev)
             self.dist.barrier(group=self.group)
@@ -139,8 +152,15 @@ class RowShardedSCA:
         for gr in self.groups:
             for layer in (0, 1):
                 if gr.pending[layer] is not None:
-                    gr.pending[layer].wait()
+                    self._wait(gr.pending[layer])
                     gr.pending[layer] = None
+
+    def _wait(self, pending):
+        """Make the compute stream wait for an in-flight exchange (an NCCL work object or a CUDA event)."""
+        if hasattr(pending, "wait") and not isinstance(pending, self.torch.cuda.Event):
+            pending.wait()
+        else:
+            self.torch.cuda.current_stream(self.dev).wait_event(pending)
 
     def _layer(self, which):
         self._drain()
@@ -164,7 +184,7 @@ class RowShardedSCA:
         src, dst = (gr.full_v, gr.full_h) if layer == 1 else (gr.full_h, gr.full_v)
         src_layer = 0 if layer == 1 else 1
         if gr.pending[src_layer] is not None:   # the gathered input of this half-step (stream-level wait)
-            gr.pending[src_layer].wait()
+            self._wait(gr.pending[src_layer])
             gr.pending[src_layer] = None
         if self.fused:
             g, hdl = self.blocks[0], (gr.hh if layer == 1 else gr.hv)
@@ -181,7 +201,24 @@ class RowShardedSCA:
             m.shard_halfstep(gr.R, layer, self.rule, src.data_ptr(), blk[i].data_ptr(), seed, step_abs, T,
                              replica_offset=gr.r0)
             self.launches += 1
-        if self.distributed:
+        if self.cstream is not None:
+            # copy-engine exchange on the side stream: push this rank's block into every rank's gathered matrix
+            torch = self.torch
+            hdl = gr.hh if layer == 1 else gr.hv
+            g = self.blocks[0]
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(self.cstream):
+                self.cstream.wait_event(ready)
+                for q in range(self.G):
+                    peer = hdl.get_buffer(q, (self.G, gr.R, self.nb), torch.bfloat16)
+                    peer[g].copy_(blk[0], non_blocking=True)
+                hdl.barrier(channel=0)
+                done = torch.cuda.Event()
+                done.record(self.cstream)
+            gr.pending[layer] = done
+            self.gather_bytes += (self.G - 1) * blk[0].numel() * 2
+        elif self.distributed:
             # the one real exchange step of this path: [R][nb] per rank -> [G][R][nb] everywhere.  async_op: the
             # collective runs on NCCL's stream after this kernel; the next kernel of the OTHER group is enqueued
             # right behind this one and overlaps it ("pipelined"); "nccl" waits for it at the next half-step.

@@ -23,7 +23,7 @@ def main():
     emu.set_spins(S0)
     emu.run(nsteps, T, seed=7)
     ok, modes = True, []
-    for exchange in ("nccl", "pipelined", "fused"):   # all-gather per half-step / pipelined over two replica groups /
+    for exchange in ("nccl", "pipelined", "copy", "fused"):   # all-gather per half-step / pipelined over two replica groups /
         sca = rowshard.RowShardedSCA(n, R, seed=seed, q=1.0, device=local, exchange=exchange)  # peer stores in the epilogue
         assert sca.distributed and sca.G == dist.get_world_size()
         for rep in range(2):      # a second run on the same object exercises the re-initialisation path
