@@ -246,6 +246,11 @@ int64_t isb_ens_last_flips(const isb_ens *e);
 /* Decisions of the last run whose |2h - fT| was below tie_eps (near-tie audit). */
 int64_t isb_ens_last_near_ties(const isb_ens *e);
 int isb_ens_set_tie_eps(isb_ens *e, double eps);
+/* Per-replica temperature factors (scale: R entries, NULL clears them): replica r runs every later *_run call at
+ * T_r(k) = Tsched[k] * scale[r].  R reference objects that differ only in their `temperature` field
+ * (src/SingleSpinFlip.jl:40,59; src/OnBipartiteGraph.jl:12,47) are one ensemble: temperature scans, parallel
+ * tempering (swap = permute the factors, the spins stay where they are). */
+int isb_ens_set_temperature_scale(isb_ens *e, const double *scale);
 
 #ifdef __cplusplus
 }

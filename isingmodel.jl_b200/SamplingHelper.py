@@ -78,6 +78,8 @@ def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offse
     if isinstance(ua, SingleSpinUpdatingAlgorithm):
         ss = ua.spinSystem
         ens = ss._ensemble()
+        if getattr(ua, "temperatureScale", None) is not None:
+            ens.set_temperature_scale(ua.temperatureScale)   # per-replica temperatures (tempering.set_temperatures)
         R, n = ss._host_spins.shape
         nodes = fluct = None
         per_rep = False

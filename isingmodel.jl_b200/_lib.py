@@ -93,6 +93,7 @@ SIGNATURES = {
     "isb_ens_last_flips": (_i64, [_vp]),
     "isb_ens_last_near_ties": (_i64, [_vp]),
     "isb_ens_set_tie_eps": (_i, [_vp, _d]),
+    "isb_ens_set_temperature_scale": (_i, [_vp, _vp]),
 }
 
 _lib = None
@@ -358,6 +359,13 @@ class Ensemble:
         A = np.zeros((self.R, self.nh), dtype=np.float64)
         self._chk(load().isb_ens_local_aux_bias(self.handle, ptr(A), self.nh))
         return A
+
+    def set_temperature_scale(self, scale):
+        """Per-replica temperature factors (R values) for every later run; None clears them."""
+        a = None if scale is None else np.ascontiguousarray(scale, dtype=np.float64)
+        if a is not None and a.size != self.R:
+            raise IsbError(ERR_SIZE, f"temperature scale has {a.size} entries for {self.R} replicas")
+        self._chk(load().isb_ens_set_temperature_scale(self.handle, ptr(a)))
 
     def set_tie_eps(self, eps: float):
         self._chk(load().isb_ens_set_tie_eps(self.handle, float(eps)))

@@ -466,6 +466,7 @@ void isb_ens_destroy(isb_ens *e) {
     cudaFree(e->fields);
     cudaFree(e->d_flips);
     cudaFree(e->d_counters);
+    cudaFree(e->d_tscale);
     isb_model *m = e->model;
     delete e;
     model_release(m);
@@ -945,6 +946,22 @@ int isb_ens_last_stats(const isb_ens *e, double *kernel_ms, int64_t *launches, i
 }
 int64_t isb_ens_last_flips(const isb_ens *e) { return e ? e->last_flips : 0; }
 int64_t isb_ens_last_near_ties(const isb_ens *e) { return e ? e->last_near_ties : 0; }
+int isb_ens_set_temperature_scale(isb_ens *e, const double *scale) {
+    if (!e) return ISB_ERR_ARG;
+    isb_ctx *ctx = e->model->ctx;
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!scale) {
+        ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(e->d_tscale);
+        e->d_tscale = nullptr;
+        return ISB_OK;
+    }
+    if (!all_finite(scale, (size_t)e->R)) return fail(ctx, ISB_ERR_NONFINITE, "isb_ens_set_temperature_scale: non-finite factor");
+    if (!e->d_tscale) ISB_CUDA(ctx, cudaMalloc(&e->d_tscale, (size_t)e->R * sizeof(double)));
+    ISB_CUDA(ctx, cudaMemcpyAsync(e->d_tscale, scale, (size_t)e->R * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
 int isb_ens_set_tie_eps(isb_ens *e, double eps) {
     if (!e) return ISB_ERR_ARG;
     if (!(eps >= 0.0)) return fail(e->model->ctx, ISB_ERR_ARG, "isb_ens_set_tie_eps: eps must be >= 0");

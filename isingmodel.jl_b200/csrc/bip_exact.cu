@@ -38,6 +38,7 @@ struct BipHalfParams {
     const double *F;     // SHARED: [nsteps][nout]; PER_REPLICA: [R][nsteps][nout]
     int64_t nsteps, k;   // step index within this run
     const double *Tsched;
+    const double *tscale;     // per-replica temperature factors [R] or NULL
     int64_t steps_per_T;
     uint64_t seed, step_abs;  // Philox: absolute step = step_offset + k
     uint32_t domain;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(BIPX_THREADS) bip_half_kernel(const BipHalfPar
             f = p.F[((int64_t)r * p.nsteps + p.k) * p.nout + j];
         }
         int8_t *o = p.out + (int64_t)r * p.ldout + j;
-        double ft = __dmul_rn(f, T);
+        double ft = __dmul_rn(f, p.tscale ? __dmul_rn(T, p.tscale[r]) : T);
         if (p.rule == ISB_BIP_MA) ft = __dmul_rn(ft, (double)*o);
         const double x = __dsub_rn(__dmul_rn(2.0, __dadd_rn(acc[c], bj)), ft);
         *o = (x < 0.0) ? (int8_t)-1 : (int8_t)1;  // heaviside(0) = 1, src/SpinSystems.jl:163-171
@@ -259,6 +260,7 @@ int bip_run_exact_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, c
             p.nsteps = nsteps;
             p.k = k;
             p.Tsched = d_T;
+            p.tscale = e->d_tscale;
             p.steps_per_T = steps_per_T;
             p.seed = seed;
             p.step_abs = step_offset + (uint64_t)k;

@@ -97,6 +97,7 @@ struct TcParams {
     int r_off;               // global replica index of row 0 (a run may hold a slice of the replicas): Philox only
     int64_t nsteps, k0;      // steps of the whole run (fluctuation array pitch), first step of this launch
     const double *Tsched;
+    const double *tscale;    // per-replica temperature factors [R] or NULL
     int64_t steps_per_T;
     double T_direct;         // temperature when Tsched is NULL
     uint64_t seed, step_abs0;  // Philox step of k0
@@ -321,10 +322,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
         uint32_t tl = 0;
         while (jobs.next(p, job)) {
             const TcLayer &L = p.L[job.layer];
-            const double Td = p.Tsched ? p.Tsched[job.k / p.steps_per_T] : p.T_direct;
-            const float Tf = (float)Td;
-            const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2
-            const float cE = Tf > 0.f ? -2.0f * 1.4426950408889634f / Tf : 0.f;  // e^{-2x/T} = 2^{cE x}
             const uint64_t step_abs = p.step_abs0 + (uint64_t)(job.k - p.k0);
             constexpr int CW = TC_CW;
             const int nchunks = L.bn / CW;
@@ -334,6 +331,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             const int lrow = quad * 32 + lane;
             const int r = job.m0 + lrow;
             const bool row_ok = r < p.R && (!p.persist || lrow < p.rows_per_cta);
+            // temperature of this thread's replica (per-replica factors make it a per-row quantity)
+            double Td = p.Tsched ? p.Tsched[job.k / p.steps_per_T] : p.T_direct;
+            if (p.tscale && row_ok) Td = __dmul_rn(Td, p.tscale[r]);
+            const float Tf = (float)Td;
+            const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2
+            const float cE = Tf > 0.f ? -2.0f * 1.4426950408889634f / Tf : 0.f;  // e^{-2x/T} = 2^{cE x}
             for (int c = half; c < nchunks; c += TC_EPI_WARPS / 4) {
                 uint32_t v[CW];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TC_BN_MAX + c * CW);
@@ -742,6 +745,7 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     p.fluct_mode = fluct_mode;
     p.nsteps = nsteps;
     p.Tsched = d_T;
+    p.tscale = e->d_tscale;
     p.steps_per_T = steps_per_T;
     p.seed = seed;
     p.m_tiles = m_tiles;

@@ -64,6 +64,7 @@ struct isb_ens {
     unsigned long long *d_flips = nullptr;   // [R]
     unsigned long long *d_counters = nullptr; // [0] near ties
     double tie_eps = 0.0;
+    double *d_tscale = nullptr;  // optional per-replica temperature factors [R]: T_r(k) = Tsched[k] * tscale[r]
     // last-run statistics
     double last_ms = 0.0;
     int64_t last_launches = 0, last_h2d = 0, last_d2h = 0, last_flips = 0, last_near_ties = 0;

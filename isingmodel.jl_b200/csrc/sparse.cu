@@ -42,6 +42,7 @@ struct SpParams {
     const double *fluct;
     uint64_t seed, step_offset;
     const double *Tsched;
+    const double *tscale;
     int64_t steps_per_T;
     int64_t trace_every;
     double *out_E, *out_M;
@@ -69,6 +70,7 @@ __global__ void ssf_sparse_kernel(const SpParams p) {
     __syncwarp();
     const int rule = p.rule;
     const bool metro = rule == 2, audit = p.tie_eps > 0.0;
+    const double tsc = p.tscale ? __ldg(&p.tscale[r]) : 1.0;
     unsigned long long nflips = 0, nties = 0;
 
     // fld[j] += d * J[i][j] over the neighbours of site i (distinct j: no conflicts), spin flipped by lane 0
@@ -117,7 +119,7 @@ __global__ void ssf_sparse_kernel(const SpParams p) {
             if (next_trace - t < len) len = (int)(next_trace - t);
             const bool mine = lane < len;
             const int64_t tl = t + lane;
-            const double Tl = mine ? __ldg(&p.Tsched[tl / p.steps_per_T]) : 0.0;
+            const double Tl = mine ? __dmul_rn(__ldg(&p.Tsched[tl / p.steps_per_T]), tsc) : 0.0;
             const double ftl = __dmul_rn(mine ? fluct_at(tl) : 0.0, Tl);
             const int i = site + (mine ? lane : 0);
             bool mybit = sp[i] > 0;
@@ -152,7 +154,7 @@ __global__ void ssf_sparse_kernel(const SpParams p) {
     } else {
         for (int64_t t = 0; t < p.nsteps; ++t) {
             const int i = __ldg(&p.nodes[t]);
-            const double T = __ldg(&p.Tsched[t / p.steps_per_T]);
+            const double T = __dmul_rn(__ldg(&p.Tsched[t / p.steps_per_T]), tsc);
             const double ft = __dmul_rn(fluct_at(t), T);
             const bool mybit = sp[i] > 0;
             const double x = __dsub_rn(2.0 * fld[i], metro ? (mybit ? ft : -ft) : ft);
@@ -334,7 +336,7 @@ int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const
     p.ecoef = rule == ISB_RULE_HOPFIELD ? 1.5 : 0.5;
     p.nsteps = nsteps; p.start = start; p.nodes = d_nodes;
     p.fluct_mode = fluct_mode; p.fluct = d_fluct; p.seed = seed; p.step_offset = step_offset;
-    p.Tsched = d_T; p.steps_per_T = steps_per_T; p.trace_every = trace_every;
+    p.Tsched = d_T; p.tscale = e->d_tscale; p.steps_per_T = steps_per_T; p.trace_every = trace_every;
     p.out_E = d_E; p.out_M = d_M; p.out_S = d_S; p.ldS = m->n; p.flips = e->d_flips; p.near_ties = e->d_counters; p.tie_eps = e->tie_eps;
     p.chains_per_cta = chains;
     const size_t smem = per_chain * chains;

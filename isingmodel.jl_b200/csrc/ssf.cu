@@ -266,6 +266,7 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
     p.seed = seed;
     p.step_offset = step_offset;
     p.Tsched = d_T;
+    p.tscale = e->d_tscale;
     p.steps_per_T = steps_per_T;
     p.trace_every = trace_every;
     p.out_E = d_E;

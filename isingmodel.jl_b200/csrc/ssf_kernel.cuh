@@ -47,6 +47,7 @@ struct SsfParams {
     const double *fluct;
     uint64_t seed, step_offset;
     const double *Tsched;
+    const double *tscale;  // per-replica temperature factors [R] or NULL
     int64_t steps_per_T;
     int64_t trace_every;
     double *out_E, *out_M;
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
     const bool metro = p.rule == 2;
     const int rule = p.rule;
     const bool audit = p.tie_eps > 0.0;
+    const double tsc = p.tscale ? __ldg(&p.tscale[r]) : 1.0;  // T_r = Tsched * tsc (x 1.0 is exact)
     unsigned long long nflips = 0, nties = 0;
     // Ring position of this chain within the current (streamed) epoch: qcur = group of the epoch being read
     // (-1: none yet), held = it has not been released; cslot / cph walk the ring across epochs (only streamed
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                     f = __ldg(&p.fluct[(int64_t)r * p.nsteps + tl]);
                 }
             }
-            const double ftl = __dmul_rn(f, Tl);
+            const double ftl = __dmul_rn(f, __dmul_rn(Tl, tsc));
             bool mybit = (sw >> k) & 1u;
             // hk mirrors hf[k] (my own site's field) for this block; both receive identical updates
             HT hk = field_sel<HT, NPL>(hf, k);
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
             const int site = __shfl_sync(FULL, node_batch, j);
             const double f = __shfl_sync(FULL, f_batch, j);
             const int k = site >> 5, l = site & 31;
-            const double ft = __dmul_rn(f, Tcur);
+            const double ft = __dmul_rn(f, __dmul_rn(Tcur, tsc));
             const bool mybit = (sw >> k) & 1u;
             const double h2 = 2.0 * (double)field_sel<HT, NPL>(hf, k);
             const double fts = metro ? (mybit ? ft : -ft) : ft;

@@ -151,3 +151,73 @@ def test_energy_distribution_matches_exact_result(ctx, synth, path, rule):
     exact = mean_energy(L_, T)
     err = Em.std() / np.sqrt(R)
     assert abs(Em.mean() - exact) < 5 * err + 1e-3 * abs(exact), (Em.mean(), exact, err)
+
+
+def test_per_replica_temperatures_bit_exact(ctx, orc, synth):
+    """isb_ens_set_temperature_scale: replica r runs at Tsched * scale[r]; each replica equals the oracle run at
+    that temperature (dense, sparse and Float64 bipartite kernels)."""
+    import scipy.sparse as sp
+    L = _lib()
+    N, R, nsteps = 64, 9, 64 * 5
+    J, h = synth.sk_J(N, 21), synth.gaussian(22, N) * 0.1
+    S0 = synth.spins(23, R, N)
+    fl = synth.logistic(24, (R, nsteps))
+    T = synth.geometric_schedule(1.5, 0.5, 5)
+    scale = np.linspace(0.4, 2.0, R)
+    for model in (L.Model.dense(ctx, J, h, L.PREC_F64), L.Model.sparse(ctx, sp.csc_matrix(J), h)):
+        e = L.Ensemble(model, R)
+        e.set_spins(S0)
+        e.set_temperature_scale(scale)
+        out = e.ssf_run(1, nsteps, fluct=fl, fluct_per_replica=True, T=T, steps_per_T=N)
+        S = e.get_spins()
+        for r in range(R):
+            s, flips, *_ = orc.ssf_run(1, J, h, S0[r], nsteps, fluct=fl[r], T=T * scale[r], steps_per_T=N)
+            assert np.array_equal(s, S[r]) and flips == out["flips"][r]
+        e.set_temperature_scale(None)   # cleared: back to the shared schedule
+        e.set_spins(S0)
+        e.ssf_run(1, nsteps, fluct=fl, fluct_per_replica=True, T=T, steps_per_T=N)
+        s, *_ = orc.ssf_run(1, J, h, S0[0], nsteps, fluct=fl[0], T=T, steps_per_T=N)
+        assert np.array_equal(s, e.get_spins()[0])
+    nv, nh = 40, 24
+    W, hv, bh = synth.bipartite_W(nv, nh, 25, 0.4)
+    Sv, Sh = synth.spins(26, R, nv), synth.spins(27, R, nh)
+    Fv, Fh = synth.logistic(28, (R, 3, nv), 1), synth.logistic(28, (R, 3, nh), 2)
+    e = L.Ensemble(L.Model.bipartite(ctx, W, hv, bh, L.PREC_F64), R)
+    e.set_spins(Sv)
+    e.set_hidden(Sh)
+    e.set_temperature_scale(scale)
+    e.bip_run(0, 3, Fv=Fv, Fh=Fh, fluct_per_replica=True, T=np.array([1.0, 0.8, 0.6]))
+    for r in range(R):
+        s, t, _ = orc.bip_run(0, W, hv, bh, Sv[r], Sh[r], 3, Fv[r], Fh[r], np.array([1.0, 0.8, 0.6]) * scale[r])
+        assert np.array_equal(s, e.get_spins()[r]) and np.array_equal(t, e.get_hidden()[r])
+    # tensor-core path with integer couplings: per-replica temperatures, exact against the Float64 path
+    Wi = np.round(W * 6.0)
+    res = []
+    for prec in (L.PREC_F64, L.PREC_BF16X1):
+        e = L.Ensemble(L.Model.bipartite(ctx, Wi, np.round(hv * 6), np.round(bh * 6), prec), R)
+        e.set_spins(Sv)
+        e.set_hidden(Sh)
+        e.set_temperature_scale(scale)
+        e.bip_run(0, 3, Fv=Fv, Fh=Fh, fluct_per_replica=True, T=np.array([2.0, 1.5, 1.0]))
+        res.append((e.get_spins(), e.get_hidden()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+def test_parallel_tempering_samples_each_temperature(pkg, ctx, synth):
+    """Replica exchange on the 8 x 8 torus: the mean energy found at every temperature level agrees with Kaufman's
+    exact value, and temperatures really travel between replicas."""
+    import scipy.sparse as sp
+    from exact_ising import mean_energy
+    Lside, levels, ladders = 8, np.array([1.9, 2.2, 2.5, 2.9, 3.5]), 200
+    N, R = Lside * Lside, ladders * 5
+    ss = pkg.SpinSystems.SpinSystem(synth.spins(31, R, N), sp.csc_matrix(synth.lattice_J(Lside)), np.zeros(N))
+    ua = pkg.SingleSpinFlip.MetropolisMethod(ss, 1.0)
+    pt = pkg.tempering.ParallelTempering(ua, levels, seed=5)
+    pt.run(150, sweeps=2)                       # equilibrate
+    E = pt.run(150, sweeps=2)                   # [rounds][levels][ladders]
+    assert (pt.accepted > 0).all() and (pt.accepted < pt.proposed).all()
+    for lvl, T in enumerate(levels):
+        per_ladder = E[:, lvl, :].mean(0)
+        err = per_ladder.std() / np.sqrt(ladders)
+        exact = mean_energy(Lside, T)
+        assert abs(per_ladder.mean() - exact) < 5 * err + 2e-3 * abs(exact), (T, per_ladder.mean(), exact, err)
