@@ -156,6 +156,15 @@ int isb_ssf_run_snap(isb_ens *e, int rule, int64_t nsteps, int order, const int3
                      const double *Tsched, int64_t nT, int64_t steps_per_T, int64_t trace_every,
                      double *out_E, double *out_M, int64_t *out_flips, int8_t *out_S, int64_t ldS);
 
+/* isb_ssf_run that histograms the visited configurations on the device instead of returning them: the demo's
+ * "frequency of each spin configuration" plot (demo.jl:159-168: every state the sampler yields is mapped to the
+ * integer whose binary digits are (1 - s_i)/2, site 1 the most significant).  hist has 2^N entries (N <= 24) and
+ * is ACCUMULATED into (the caller zeroes it): every replica's configuration at every trace point adds one count. */
+int isb_ssf_run_hist(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *nodes, int start,
+                     int fluct_mode, const double *fluct, uint64_t seed, uint64_t step_offset,
+                     const double *Tsched, int64_t nT, int64_t steps_per_T, int64_t trace_every,
+                     int64_t *hist);
+
 /* Fluctuations exactly as ISB_FLUCT_PHILOX generates them inside isb_ssf_run, for parity tests:
  * out[r*nsteps + k], r in [r0, r0+nr). rule selects the transform. prec as the model's. */
 int isb_philox_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64_t step_offset,

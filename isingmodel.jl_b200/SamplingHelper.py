@@ -54,7 +54,7 @@ def _schedule(ua, maxMCSteps, annealingSchedule):
 
 
 def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offset=0, order="random",
-         trace_every=0, per_replica_noise=True, temperatures=None, steps_per_T=1, start=0):
+         trace_every=0, per_replica_noise=True, temperatures=None, steps_per_T=1, start=0, hist=None):
     """The whole ``makeSampler!`` loop in one library call.  Returns a dict of traces.
 
     rng given  -> site list and fluctuations are drawn on the host in the reference's order
@@ -64,6 +64,8 @@ def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offse
                   first site ``start``).
     temperatures / steps_per_T -> the schedule already evaluated on the host: entry k // steps_per_T is the
                   temperature of step k (0-based); replaces ``annealingSchedule`` (e.g. one entry per sweep).
+    hist       -> int64[2^N] (single-spin algorithms, N <= 24): the configuration of every replica at every
+                  ``trace_every``-th step is counted into it on the device (see ``tempering.configurationHistogram``).
     """
     if maxMCSteps < 0:
         warnings.warn(f"{maxMCSteps} is negative.")  # SamplingHelper.jl:29-31
@@ -92,7 +94,7 @@ def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offse
         o = _lib.ORDER_SEQUENTIAL if order == "sequential" else (_lib.ORDER_LIST if nodes is not None else _lib.ORDER_RANDOM)
         out = ens.ssf_run(ua._rule, maxMCSteps, order=o, nodes=nodes, start=start, fluct=fluct,
                           fluct_per_replica=per_rep, seed=seed, step_offset=step_offset, T=Tsteps,
-                          steps_per_T=steps_per_T, trace_every=trace_every)
+                          steps_per_T=steps_per_T, trace_every=trace_every, hist=hist)
         ss._dev_newer = True
         if T is not None and maxMCSteps > 0:
             ua.temperature = float(T[-1])
@@ -100,6 +102,8 @@ def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offse
     b = _bip(ua)
     ss = b.spinSystem
     ens = ss._ensemble()
+    if getattr(ua, "temperatureScale", None) is not None:
+        ens.set_temperature_scale(ua.temperatureScale)
     Fv = Fh = None
     if rng is not None:
         # reference layout: (units, steps) column-major == [steps][units] row-major

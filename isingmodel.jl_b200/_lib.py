@@ -77,6 +77,7 @@ SIGNATURES = {
     "isb_ssf_run": (_i, [_vp, _i, _i64, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "isb_ssf_run_snap": (_i, [_vp, _i, _i64, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp,
                               _i64]),
+    "isb_ssf_run_hist": (_i, [_vp, _i, _i64, _i, _vp, _i, _i, _vp, _u64, _u64, _vp, _i64, _i64, _i64, _vp]),
     "isb_philox_fluct": (_i, [_vp, _i, _i, _u64, _u64, _i, _i, _i64, _vp]),
     "isb_philox_nodes": (_i, [_vp, _i, _u64, _u64, _i64, _vp]),
     "isb_philox_raw": (_i, [_vp, _vp, _vp, _i, _vp]),
@@ -372,8 +373,9 @@ class Ensemble:
 
     def ssf_run(self, rule, nsteps, *, order=ORDER_SEQUENTIAL, nodes=None, start=0, fluct=None,
                 fluct_per_replica=False, seed=0, step_offset=0, T=None, steps_per_T=1, trace_every=0,
-                want_E=True, want_M=True, want_S=False):
-        """isb_ssf_run / isb_ssf_run_snap. Returns dict(flips[R], E[ntr][R] | None, M[ntr][R] | None, S[ntr][R][N] | None)."""
+                want_E=True, want_M=True, want_S=False, hist=None):
+        """isb_ssf_run / isb_ssf_run_snap. Returns dict(flips[R], E[ntr][R] | None, M[ntr][R] | None, S[ntr][R][N] | None).
+        With ``hist`` (int64[2^N], accumulated into) the call is isb_ssf_run_hist and returns {"hist": hist}."""
         nsteps = int(nsteps)
         nodes_a = None if nodes is None else np.ascontiguousarray(nodes, dtype=np.int32)
         if nodes_a is not None:
@@ -390,6 +392,13 @@ class Ensemble:
                 raise IsbError(ERR_SIZE, f"fluctuation array has {fl.size} entries, expected {need}")
         Ta = None if T is None else np.ascontiguousarray(np.atleast_1d(T), dtype=np.float64)
         ntr = nsteps // trace_every if trace_every > 0 else 0
+        if hist is not None:
+            if hist.dtype != np.int64 or not hist.flags.c_contiguous or hist.size != 1 << min(self.nv, 62):
+                raise IsbError(ERR_SIZE, "hist must be a contiguous int64 array with 2^N entries")
+            self._chk(load().isb_ssf_run_hist(self.handle, rule, nsteps, order, ptr(nodes_a), int(start), mode, ptr(fl),
+                                              int(seed), int(step_offset), ptr(Ta), 0 if Ta is None else Ta.size,
+                                              int(steps_per_T), int(trace_every), ptr(hist)))
+            return {"hist": hist}
         E = np.zeros((ntr, self.R)) if (ntr and want_E) else None
         M = np.zeros((ntr, self.R)) if (ntr and want_M) else None
         S = np.zeros((ntr, self.R, self.nv), dtype=np.int8) if (ntr and want_S) else None

@@ -603,17 +603,43 @@ static void begin_stats(isb_ens *e) {
     e->last_flips = e->last_near_ties = 0;
 }
 
+static int ssf_run_impl(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *nodes, int start, int fluct_mode,
+                        const double *fluct, uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT,
+                        int64_t steps_per_T, int64_t trace_every, double *out_E, double *out_M, int64_t *out_flips,
+                        int8_t *out_S, int64_t ldS, int64_t *hist);
+
 int isb_ssf_run(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *nodes, int start, int fluct_mode,
                 const double *fluct, uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT,
                 int64_t steps_per_T, int64_t trace_every, double *out_E, double *out_M, int64_t *out_flips) {
-    return isb_ssf_run_snap(e, rule, nsteps, order, nodes, start, fluct_mode, fluct, seed, step_offset, Tsched, nT,
-                            steps_per_T, trace_every, out_E, out_M, out_flips, nullptr, 0);
+    return ssf_run_impl(e, rule, nsteps, order, nodes, start, fluct_mode, fluct, seed, step_offset, Tsched, nT,
+                        steps_per_T, trace_every, out_E, out_M, out_flips, nullptr, 0, nullptr);
 }
 
 int isb_ssf_run_snap(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *nodes, int start, int fluct_mode,
                      const double *fluct, uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT,
                      int64_t steps_per_T, int64_t trace_every, double *out_E, double *out_M, int64_t *out_flips,
                      int8_t *out_S, int64_t ldS) {
+    return ssf_run_impl(e, rule, nsteps, order, nodes, start, fluct_mode, fluct, seed, step_offset, Tsched, nT,
+                        steps_per_T, trace_every, out_E, out_M, out_flips, out_S, ldS, nullptr);
+}
+
+int isb_ssf_run_hist(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *nodes, int start, int fluct_mode,
+                     const double *fluct, uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT,
+                     int64_t steps_per_T, int64_t trace_every, int64_t *hist) {
+    if (!e) return ISB_ERR_ARG;
+    isb_ctx *ctx = e->model->ctx;
+    if (!hist) return fail(ctx, ISB_ERR_ARG, "isb_ssf_run_hist: hist is NULL");
+    if (general_graph(e->model) && e->model->n > 24)
+        return fail(ctx, ISB_ERR_SIZE, "isb_ssf_run_hist: N = %d > 24 (the histogram has 2^N bins)", e->model->n);
+    if (trace_every <= 0) return fail(ctx, ISB_ERR_ARG, "isb_ssf_run_hist: trace_every must be positive");
+    return ssf_run_impl(e, rule, nsteps, order, nodes, start, fluct_mode, fluct, seed, step_offset, Tsched, nT,
+                        steps_per_T, trace_every, nullptr, nullptr, nullptr, nullptr, 0, hist);
+}
+
+static int ssf_run_impl(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *nodes, int start, int fluct_mode,
+                        const double *fluct, uint64_t seed, uint64_t step_offset, const double *Tsched, int64_t nT,
+                        int64_t steps_per_T, int64_t trace_every, double *out_E, double *out_M, int64_t *out_flips,
+                        int8_t *out_S, int64_t ldS, int64_t *hist) {
     if (!e) return ISB_ERR_ARG;
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
@@ -674,7 +700,12 @@ int isb_ssf_run_snap(isb_ens *e, int rule, int64_t nsteps, int order, const int3
     if (ntr > 0 && out_E) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_E, (size_t)ntr * e->R * sizeof(double), (void **)&d_E));
     if (ntr > 0 && out_M) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_M, (size_t)ntr * e->R * sizeof(double), (void **)&d_M));
     int8_t *d_S = nullptr;
-    if (ntr > 0 && out_S) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_S, (size_t)ntr * e->R * m->n, (void **)&d_S));
+    if (ntr > 0 && (out_S || hist)) ISB_TRY(isb::dev_reserve(ctx, isb::SCR_S, (size_t)ntr * e->R * m->n, (void **)&d_S));
+    unsigned long long *d_hist = nullptr;
+    if (d_S && hist) {
+        ISB_TRY(isb::dev_reserve(ctx, isb::SCR_HIST, sizeof(unsigned long long) << m->n, (void **)&d_hist));
+        ISB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) << m->n, ctx->stream));
+    }
     ISB_CUDA(ctx, cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
 
     ISB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -688,15 +719,24 @@ int isb_ssf_run_snap(isb_ens *e, int rule, int64_t nsteps, int order, const int3
     else
         ISB_TRY(isb::ssf_run_device(e, rule, nsteps, order, d_nodes, start, fluct_mode, d_fluct, seed, step_offset, d_T,
                                     steps_per_T, (d_E || d_M || d_S) ? trace_every : 0, d_E, d_M, d_S));
+    if (d_hist) {
+        ISB_TRY(isb::config_histogram_device(ctx, d_S, ntr * e->R, m->n, d_hist));
+        e->last_launches += 1;
+    }
     ISB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 
     std::vector<unsigned long long> fl((size_t)e->R);
+    std::vector<unsigned long long> hh;
+    if (d_hist) {
+        hh.resize((size_t)1 << m->n);
+        ISB_TRY(d2h(ctx, hh.data(), d_hist, hh.size() * sizeof(unsigned long long), &e->last_d2h));
+    }
     unsigned long long counters[4] = {0, 0, 0, 0};
     ISB_TRY(d2h(ctx, fl.data(), e->d_flips, (size_t)e->R * sizeof(unsigned long long), &e->last_d2h));
     ISB_TRY(d2h(ctx, counters, e->d_counters, sizeof counters, &e->last_d2h));
     if (d_E) ISB_TRY(d2h(ctx, out_E, d_E, (size_t)ntr * e->R * sizeof(double), &e->last_d2h));
     if (d_M) ISB_TRY(d2h(ctx, out_M, d_M, (size_t)ntr * e->R * sizeof(double), &e->last_d2h));
-    if (d_S) {
+    if (d_S && out_S) {
         ISB_CUDA(ctx, cudaMemcpy2DAsync(out_S, (size_t)ldS, d_S, (size_t)m->n, (size_t)m->n, (size_t)ntr * e->R,
                                         cudaMemcpyDeviceToHost, ctx->stream));
         e->last_d2h += (int64_t)ntr * e->R * m->n;
@@ -711,6 +751,7 @@ int isb_ssf_run_snap(isb_ens *e, int rule, int64_t nsteps, int order, const int3
         if (out_flips) out_flips[r] = (int64_t)fl[r];
     }
     e->last_near_ties = (int64_t)counters[0];
+    for (size_t b = 0; b < hh.size(); ++b) hist[b] += (int64_t)hh[b];
     return ISB_OK;
 }
 

@@ -22,7 +22,7 @@ struct isb_ctx {
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
-    isb_devbuf scratch[12];      // grow-only device staging buffers (see isb::dev_reserve)
+    isb_devbuf scratch[13];      // grow-only device staging buffers (see isb::dev_reserve)
 };
 
 enum { ISB_KIND_DENSE = 0, ISB_KIND_BIPARTITE = 1, ISB_KIND_SHARD = 2, ISB_KIND_SPARSE = 3 };
@@ -77,7 +77,7 @@ int fail(isb_ctx *ctx, int code, const char *fmt, ...);
 // Grow-only device scratch buffer `slot` of the context, at least `bytes` long.
 int dev_reserve(isb_ctx *ctx, int slot, size_t bytes, void **out);
 enum { SCR_NODES = 0, SCR_FLUCT = 1, SCR_T = 2, SCR_E = 3, SCR_M = 4, SCR_FLUCT2 = 5, SCR_OUT = 6, SCR_TMP = 7,
-       SCR_TC0 = 8, SCR_TC1 = 9, SCR_S = 10, SCR_S2 = 11 };
+       SCR_TC0 = 8, SCR_TC1 = 9, SCR_S = 10, SCR_S2 = 11, SCR_HIST = 12 };
 
 #define ISB_CUDA(ctx, call)                                                                      \
     do {                                                                                         \
@@ -102,6 +102,8 @@ int philox_raw_device(isb_ctx *ctx, const uint32_t *d_ctr, uint32_t k0, uint32_t
 int dense_energy_device(isb_ens *e, double *d_E);
 int dense_field_device(isb_ens *e, double *d_F, int64_t ld);  // natural J s + h in double
 int magnetization_device(isb_ens *e, double *d_M);
+// counts[index(config)] += 1 for each of the `count` configurations in d_S ([count][n] int8), n <= 24
+int config_histogram_device(isb_ctx *ctx, const int8_t *d_S, int64_t count, int n, unsigned long long *d_hist);
 
 // sparse.cu
 int sparse_model_init(isb_model *m, int n, const int64_t *colptr, const int32_t *rowval, const double *nzval, int *warn);

@@ -178,6 +178,41 @@ int magnetization_device(isb_ens *e, double *d_M) {
     return ISB_OK;
 }
 
+// Configuration histogram (demo.jl:159-168): index = sum_i ((1 - s_i)/2) << (n-1-i).  Small state spaces are
+// counted in shared memory first (every replica hits the same few bins), large ones go straight to global atomics.
+template <bool SMEM>
+__global__ void config_histogram_kernel(const int8_t *__restrict__ S, int64_t count, int n,
+                                        unsigned long long *__restrict__ hist) {
+    extern __shared__ unsigned int bins[];
+    const unsigned nb = 1u << n;
+    if (SMEM) {
+        for (unsigned b = threadIdx.x; b < nb; b += blockDim.x) bins[b] = 0u;
+        __syncthreads();
+    }
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < count; c += (int64_t)gridDim.x * blockDim.x) {
+        const int8_t *s = S + c * n;
+        unsigned idx = 0;
+        for (int i = 0; i < n; ++i) idx = (idx << 1) | (s[i] < 0 ? 1u : 0u);
+        if (SMEM) atomicAdd(&bins[idx], 1u);
+        else atomicAdd(&hist[idx], 1ull);
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (unsigned b = threadIdx.x; b < nb; b += blockDim.x)
+            if (bins[b]) atomicAdd(&hist[b], (unsigned long long)bins[b]);
+    }
+}
+int config_histogram_device(isb_ctx *ctx, const int8_t *d_S, int64_t count, int n, unsigned long long *d_hist) {
+    if (count == 0) return ISB_OK;
+    const int blocks = (int)std::min<int64_t>((count + 255) / 256, 148 * 8);
+    if (n <= 12)
+        config_histogram_kernel<true><<<blocks, 256, sizeof(unsigned int) << n, ctx->stream>>>(d_S, count, n, d_hist);
+    else
+        config_histogram_kernel<false><<<blocks, 256, 0, ctx->stream>>>(d_S, count, n, d_hist);
+    ISB_CUDA(ctx, cudaGetLastError());
+    return ISB_OK;
+}
+
 // (Re)compute the cached local fields for the given h sign (+1: J s + h, -1: J s - h).
 int ssf_ensure_fields(isb_ens *e, int sign) {
     if (e->fields_rule_sign == sign) return ISB_OK;

@@ -262,7 +262,9 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
     const bool metro = p.rule == 2;
     const int rule = p.rule;
     const bool audit = p.tie_eps > 0.0;
-    const double tsc = p.tscale ? __ldg(&p.tscale[r]) : 1.0;  // T_r = Tsched * tsc (x 1.0 is exact)
+    // T_r = Tsched * tscale[r] (x 1.0 is exact); the factor is re-read whenever a schedule entry is fetched rather than
+    // kept live: two more registers in the sweep loop cost 3 % on C2
+#define ISB_TSC() (p.tscale ? __ldg(&p.tscale[r]) : 1.0)
     unsigned long long nflips = 0, nties = 0;
     // Ring position of this chain within the current (streamed) epoch: qcur = group of the epoch being read
     // (-1: none yet), held = it has not been released; cslot / cph walk the ring across epochs (only streamed
@@ -398,13 +400,13 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 const uint64_t a_hi = tr + (uint64_t)(len - 1);
                 if (a_hi < spT) {
                     if ((int64_t)ti != cached_ti) {
-                        cachedT = __ldg(&p.Tsched[ti]);
+                        cachedT = __dmul_rn(__ldg(&p.Tsched[ti]), ISB_TSC());  // scaled once per schedule entry
                         cached_ti = (int64_t)ti;
                     }
                     Tl = cachedT;
                 } else {
                     const uint64_t a = tr + (uint64_t)(mine ? off : 0);
-                    Tl = __ldg(&p.Tsched[ti + a / spT]);
+                    Tl = __dmul_rn(__ldg(&p.Tsched[ti + a / spT]), ISB_TSC());
                 }
             }
             // fluctuation of my step
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                     f = __ldg(&p.fluct[(int64_t)r * p.nsteps + tl]);
                 }
             }
-            const double ftl = __dmul_rn(f, __dmul_rn(Tl, tsc));
+            const double ftl = __dmul_rn(f, Tl);
             bool mybit = (sw >> k) & 1u;
             // hk mirrors hf[k] (my own site's field) for this block; both receive identical updates
             HT hk = field_sel<HT, NPL>(hf, k);
@@ -504,13 +506,13 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 }
             }
             if ((int64_t)ti != cached_ti) {
-                Tcur = __ldg(&p.Tsched[ti]);
+                Tcur = __dmul_rn(__ldg(&p.Tsched[ti]), ISB_TSC());
                 cached_ti = (int64_t)ti;
             }
             const int site = __shfl_sync(FULL, node_batch, j);
             const double f = __shfl_sync(FULL, f_batch, j);
             const int k = site >> 5, l = site & 31;
-            const double ft = __dmul_rn(f, __dmul_rn(Tcur, tsc));
+            const double ft = __dmul_rn(f, Tcur);
             const bool mybit = (sw >> k) & 1u;
             const double h2 = 2.0 * (double)field_sel<HT, NPL>(hf, k);
             const double fts = metro ? (mybit ? ft : -ft) : ft;

@@ -24,6 +24,36 @@ def set_temperatures(ua, temperatures):
     ss._ensemble().set_temperature_scale(ua.temperatureScale)
 
 
+def configurationIndex(spins):
+    """The demo's labelling of a configuration (demo.jl:161-165): the integer whose binary digits are (1 - s_i)/2,
+    first site most significant.  ``spins``: [..., N] of +-1."""
+    s = np.asarray(spins)
+    bits = ((1 - s) // 2).astype(np.int64)
+    w = 1 << np.arange(s.shape[-1] - 1, -1, -1, dtype=np.int64)
+    return bits @ w
+
+
+def configurationHistogram(ua, maxMCSteps, *, stride=1, burn_in=0, seed=0, order="random", chunk=1 << 16):
+    """Counts of the configurations visited by every replica (the histogram cell of demo.jl:159-168, which maps
+    all states of ``makeSampler!(GlauberDynamics(ss, T), 50000)`` through ``configurationIndex``), taken every
+    ``stride`` steps after ``burn_in`` steps, accumulated on the device (isb_ssf_run_hist).  Returns int64[2^N]."""
+    n = ua.spinSystem._host_spins.shape[1]
+    hist = np.zeros(1 << n, dtype=np.int64)
+    off = 0
+    if burn_in:
+        SamplingHelper.run_(ua, burn_in, seed=seed, order=order, temperatures=np.array([ua.temperature]),
+                            steps_per_T=burn_in)
+        off = burn_in
+    chunk = max(stride, chunk // stride * stride)
+    done = 0
+    while done < maxMCSteps:
+        m = min(chunk, maxMCSteps - done)
+        SamplingHelper.run_(ua, m, seed=seed, step_offset=off + done, order=order, start=(done % n) if order == "sequential" else 0,
+                            temperatures=np.array([ua.temperature]), steps_per_T=m, trace_every=stride, hist=hist)
+        done += m
+    return hist
+
+
 class ParallelTempering:
     """``ladders`` independent temperature ladders of ``len(levels)`` replicas each (replica index =
     ladder * len(levels) + slot).  ``run`` alternates ``sweeps`` sequential sweeps of every replica at its current

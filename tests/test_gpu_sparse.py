@@ -221,3 +221,35 @@ def test_parallel_tempering_samples_each_temperature(pkg, ctx, synth):
         err = per_ladder.std() / np.sqrt(ladders)
         exact = mean_energy(Lside, T)
         assert abs(per_ladder.mean() - exact) < 5 * err + 2e-3 * abs(exact), (T, per_ladder.mean(), exact, err)
+
+
+def test_configuration_histogram(pkg, ctx, synth):
+    """demo.jl:159-168: the frequency of each spin configuration under Glauber dynamics at T = N/4 on the 3 x 3
+    periodic antiferromagnet.  The device histogram equals the histogram of the recorded snapshots bit for bit
+    (both counting paths), and the frequencies are the Boltzmann distribution."""
+    L = _lib()
+    tp = pkg.tempering
+    assert tp.configurationIndex(np.array([[1, 1, -1], [-1, 1, 1]])).tolist() == [1, 4]
+    for n, R in ((9, 64), (14, 48)):          # shared-memory bins / global atomics
+        J = synth.lattice_J(3, -1.0) if n == 9 else synth.sk_J(n, 41)
+        e = L.Ensemble(L.Model.dense(ctx, J, np.zeros(n), L.PREC_F64), R)
+        S0 = synth.spins(42, R, n)
+        e.set_spins(S0)
+        out = e.ssf_run(1, 600, order=L.ORDER_RANDOM, seed=7, T=np.array([2.0]), steps_per_T=600, trace_every=3, want_S=True)
+        want = np.bincount(tp.configurationIndex(out["S"]).ravel(), minlength=1 << n)
+        e.set_spins(S0)
+        hist = np.zeros(1 << n, dtype=np.int64)
+        e.ssf_run(1, 600, order=L.ORDER_RANDOM, seed=7, T=np.array([2.0]), steps_per_T=600, trace_every=3, hist=hist)
+        assert np.array_equal(hist, want) and hist.sum() == 200 * R
+    n, R, T = 9, 512, 9 / 4
+    J = synth.lattice_J(3, -1.0)
+    ss = pkg.SpinSystems.SpinSystem(synth.spins(43, R, n), J, np.zeros(n))
+    hist = tp.configurationHistogram(pkg.SingleSpinFlip.GlauberDynamics(ss, T), 9 * 400, stride=9, burn_in=9 * 50, seed=3)
+    assert hist.sum() == 400 * R
+    states = 1 - 2 * ((np.arange(512)[:, None] >> np.arange(8, -1, -1)) & 1)       # index -> spins, site 0 = MSB
+    E = -0.5 * np.einsum("ki,ij,kj->k", states, J, states)
+    p = np.exp(-E / T)
+    p /= p.sum()
+    tv = 0.5 * np.abs(hist / hist.sum() - p).sum()
+    assert tv < 0.05, tv
+    assert 0.5 * np.abs(1 / 512 - p).sum() > 0.2       # the target is far from uniform, so the bound above is a real check
