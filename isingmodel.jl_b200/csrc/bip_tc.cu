@@ -48,7 +48,11 @@ constexpr int TC_EPI_WARPS = ISB_TC_EPI_WARPS;  // a multiple of 4: equal shares
 constexpr int TC_CW = ISB_TC_CW;                // accumulator columns (units) per epilogue chunk: 8 or 16
 static_assert(TC_EPI_WARPS % 4 == 0 && (TC_CW == 8 || TC_CW == 16), "epilogue shape");
 constexpr int TC_THREADS = 32 * (4 + TC_EPI_WARPS);
-constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int TC_HALVES = TC_EPI_WARPS / 4;     // epilogue warps per TMEM lane quadrant
+constexpr int TC_GW = TC_CW * TC_HALVES;        // accumulator columns the epilogue warps cover per round
+constexpr int TC_SIG_MAX = 32;                  // chain-resident mode: progress barriers per layer
+constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers*/;
+static_assert((2 * TC_STAGES + 6 + 2 * TC_SIG_MAX) * 8 <= 1024, "barrier block");
 
 struct TcModel {
     int P = 1;
@@ -94,6 +98,11 @@ struct TcParams {
     // `nsteps_seg` full steps (hidden then visible) on them without leaving the SM — chains are independent, so
     // no grid-wide synchronisation exists; only the CTA's own producer waits for its own epilogue.
     int persist, layer, m_tiles, rows_per_cta, nsteps_seg;
+    // chain-resident mode: the epilogue publishes its progress through the layer it is writing (one mbarrier per
+    // tile and per round of TC_GW columns, sig_gpt[layer] rounds per tile), and the producer of the next half-step
+    // waits K block by K block instead of for the whole layer.  The last `sig_fine` tiles of a half-step publish
+    // after every round (one proxy fence each), the earlier tiles once at their end.
+    int sig_gpt[2], sig_fine;
     int r_off;               // global replica index of row 0 (a run may hold a slice of the replicas): Philox only
     int64_t nsteps, k0;      // steps of the whole run (fluctuation array pitch), first step of this launch
     const double *Tsched;
@@ -237,8 +246,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
     uint64_t *empty_bar = bars + TC_STAGES;        // [TC_STAGES]
     uint64_t *tfull_bar = bars + 2 * TC_STAGES;    // [2]
     uint64_t *tempty_bar = bars + 2 * TC_STAGES + 2;  // [2]
-    uint64_t *hs_done = bars + 2 * TC_STAGES + 4;  // persistent mode: epilogue -> producer, "half-step written"
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 5);
+    uint64_t *sig_bar = bars + 2 * TC_STAGES + 6;  // [2][TC_SIG_MAX] chain-resident mode: epilogue -> producer progress
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -251,7 +260,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], TC_EPI_WARPS);
         }
-        mbar_init(hs_done, TC_EPI_WARPS);
+        if (p.persist)
+            for (int i = 0; i < 2 * TC_SIG_MAX; ++i) mbar_init(&sig_bar[i], TC_EPI_WARPS);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -270,10 +280,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             while (jobs.next(p, job)) {
                 const TcLayer &L = p.L[job.layer];
                 // chain-resident mode: this half-step's A operand is what the CTA's own epilogue wrote during the
-                // previous half-step (generic-proxy stores, fenced to the async proxy before the arrive)
-                if (p.persist && job.hs_first && job.hs > 0) mbar_wait_sleep(hs_done, (uint32_t)(job.hs - 1) & 1u);
+                // previous half-step (generic-proxy stores, fenced to the async proxy before the arrive).  Only the
+                // first tile of a half-step can run into it; K block kb needs the input units [64 kb, 64 kb + 64).
+                const bool dep = p.persist && job.hs_first && job.hs > 0;
+                const int pl = 1 - job.layer;   // the layer sampled by the previous half-step = this one's input
+                const uint32_t dep_par = (uint32_t)((job.hs >> 1) - (job.layer == 1 ? 1 : 0)) & 1u;
+                int waited = -1;
                 const uint32_t tx = (uint32_t)(TC_A_BYTES + L.bn * TC_BK * 2);
-                for (int kb = 0; kb < L.num_kb; ++kb) {
+#ifdef ISB_TC_PROBE_K1  // timing probe only: one K block per tile = the epilogue's cost without the contraction
+                const int num_kb = 1;
+#else
+                const int num_kb = L.num_kb;
+#endif
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (dep) {
+                        const int ul = min(kb * TC_BK + TC_BK - 1, p.L[pl].nout - 1);
+                        const int idx = (ul / p.L[pl].bn) * p.sig_gpt[pl] + (ul % p.L[pl].bn) / TC_GW;
+                        if (idx > waited) {
+                            mbar_wait_sleep(&sig_bar[pl * TC_SIG_MAX + idx], dep_par);
+                            waited = idx;
+                        }
+                    }
                     for (int t = 0; t < p.P; ++t, ++it) {
                         const int s = it % TC_STAGES;
                         mbar_wait_sleep(&empty_bar[s], ((it / TC_STAGES) & 1) ^ 1);
@@ -292,7 +319,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             while (jobs.next(p, job)) {
                 const TcLayer &L = p.L[job.layer];
                 const uint32_t idesc = umma_idesc_bf16(L.bn);
+#ifdef ISB_TC_PROBE_K1
+                const int iters = p.P;
+#else
                 const int iters = L.num_kb * p.P;
+#endif
                 const int a = tl & 1;
                 mbar_wait_sleep(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
@@ -337,7 +368,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             const float Tf = (float)Td;
             const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2
             const float cE = Tf > 0.f ? -2.0f * 1.4426950408889634f / Tf : 0.f;  // e^{-2x/T} = 2^{cE x}
-            for (int c = half; c < nchunks; c += TC_EPI_WARPS / 4) {
+            const int gpt = p.sig_gpt[job.layer];
+            const bool fine = p.persist && job.n_blk >= L.n_tiles - p.sig_fine;
+            uint64_t *sig = sig_bar + job.layer * TC_SIG_MAX + job.n_blk * gpt;
+            // Fast path for the common case (SCA, in-kernel noise, every replica of the warp at T > 0, no peer copies,
+            // a chunk of CW real units): a branch-free body with everything tile-invariant hoisted.  The sampling
+            // epilogue is bound by the fma pipe (Philox's IMAD.WIDE issue at 1 per 4 cycles, FADD/FMUL/FFMA at 1 per
+            // 2), so the rule is evaluated with three fma-pipe operations per unit:
+            //   u (1 + e^{-2x/T}) > 1,  u = (w + 1/2) 2^-32    <=>    (float)w (1 + 2^{cE x}) > 2^32
+            // (x = acc + bias: FADD; cE x: FMUL; the left side: one FFMA; the compare and the sign packing run on the
+            // ALU pipe, the conversion and the exponential on the XU).
+            const bool fastp = !EXTF && CW == 16 && p.rule == ISB_BIP_SCA && L.npeer == 0 && !__any_sync(0xFFFFFFFFu, !(Tf > 0.f));
+            const int tile_u0 = job.n_blk * L.bn;
+            const int nfull = fastp ? min(L.bn, L.nout - tile_u0) / CW : 0;   // chunks the fast path takes
+            const float *bias_t = L.bias_f + tile_u0;
+            __nv_bfloat16 *out_t = L.out_bf + (int64_t)(row_ok ? r : job.m0) * L.ldo + tile_u0;
+            const uint32_t taddr_t = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TC_BN_MAX);
+            const uint32_t pc2 = (uint32_t)(r + p.r_off), pc3 = (L.domain << 28) | (uint32_t)((L.u_off + tile_u0) >> 2);
+            for (int g = 0; g * TC_HALVES < nchunks; ++g) {
+              const int c = g * TC_HALVES + half;
+              if (c < nfull) {
+                uint32_t v[16];
+                tmem_ld16(taddr_t + (uint32_t)(c * 16), v);
+                float bf[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias_t + c * 16) + q);
+                    bf[4 * q] = b4.x; bf[4 * q + 1] = b4.y; bf[4 * q + 2] = b4.z; bf[4 * q + 3] = b4.w;
+                }
+                Philox4 blk[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    blk[q] = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), pc2, pc3 + (uint32_t)(c * 4 + q), keys);
+                uint32_t wb[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) wb[j] = 0x3F803F80u;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float wf = (float)philox_pick(blk[j >> 2], (uint32_t)(j & 3));
+                    const float x = __uint_as_float(v[j]) + bf[j];
+                    if (fmaf(wf, ex2_approx(cE * x), wf) > 4294967296.0f) wb[j >> 1] |= 0x8000u << (16 * (j & 1));
+                }
+                if (row_ok) {
+                    uint4 *o = reinterpret_cast<uint4 *>(out_t + c * 16);
+                    o[0] = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+                    o[1] = make_uint4(wb[4], wb[5], wb[6], wb[7]);
+                }
+              } else if (c < nchunks) do {
                 uint32_t v[CW];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TC_BN_MAX + c * CW);
                 if constexpr (CW == 16)
@@ -345,7 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 else
                     tmem_ld8(taddr, reinterpret_cast<uint32_t(&)[8]>(v));
                 const int u0 = job.n_blk * L.bn + c * CW;
-                if (!row_ok || u0 >= L.nout) continue;
+                if (!row_ok || u0 >= L.nout) break;
                 __nv_bfloat16 *ob = L.out_bf + (int64_t)r * L.ldo + u0;
                 const bool full = u0 + CW <= L.nout;
                 // MomentumAnnealing multiplies the noise by the unit's own previous value: it is still in the
@@ -389,19 +466,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
 #pragma unroll
                         for (int j = 0; j < CW; ++j) bf[j] = u0 + j < L.nout ? __ldg(L.bias_f + u0 + j) : 0.f;
                     }
+                    // the chunk's noise words first, in one branch-free block: the CW/4 Philox calls are independent
+                    // dependency chains (IMAD.WIDE -> LOP3 -> IMAD.WIDE ...) that only overlap when they are adjacent
+                    Philox4 blk[CW / 4];
 #pragma unroll
                     for (int q = 0; q < CW / 4; ++q) {
                         // == philox_unit_block(seed, domain, r, step, unit >> 2) with the round keys hoisted
 #ifdef ISB_TC_PROBE_NO_PHILOX  // timing probe only: how much of a half-step is the noise generation?
-                        const Philox4 blk{(uint32_t)step_abs * 2654435761u + (uint32_t)r, (uint32_t)(u0 + q) * 40503u, (uint32_t)r << 7, keys.k0[3]};
+                        blk[q] = Philox4{(uint32_t)step_abs * 2654435761u + (uint32_t)r, (uint32_t)(u0 + q) * 40503u, (uint32_t)r << 7, keys.k0[3]};
 #else
-                        const Philox4 blk = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), (uint32_t)(r + p.r_off),
-                                                           (L.domain << 28) | (uint32_t)(((L.u_off + u0) >> 2) + q), keys);
+                        blk[q] = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), (uint32_t)(r + p.r_off),
+                                                (L.domain << 28) | (uint32_t)(((L.u_off + u0) >> 2) + q), keys);
 #endif
+                    }
+#pragma unroll
+                    for (int q = 0; q < CW / 4; ++q) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int j = q * 4 + e;
-                            const uint32_t w = philox_pick(blk, (uint32_t)e);
+                            const uint32_t w = philox_pick(blk[q], (uint32_t)e);
                             const float x = __uint_as_float(v[j]) + bf[j];
                             const float u = fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (w+1/2) 2^-32
                             float t;
@@ -434,16 +517,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                     for (int j = 0; j < CW && u0 + j < L.nout; ++j)
                         ob[j] = __ushort_as_bfloat16((unsigned short)((wb[j >> 1] >> (16 * (j & 1))) & 0xFFFFu));
                 }
+              } while (0);
+              if (fine) {
+                // the columns this CTA just wrote are the next half-step's TMA operand: order the generic-proxy
+                // stores before the async-proxy reads, then tell the producer
+                fence_proxy_async_global();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sig[g]);
+              }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[a]);
-            if (p.persist && job.hs_last) {
-                // the layer this CTA just wrote is the next half-step's TMA operand: order the generic-proxy
-                // stores before the async-proxy reads, then tell the producer
+            if (p.persist && !fine) {
                 fence_proxy_async_global();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(hs_done);
+                if (lane == 0)
+                    for (int g = 0; g < gpt; ++g) mbar_arrive(&sig[g]);
             }
             ++tl;
         }
@@ -749,8 +839,14 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     p.steps_per_T = steps_per_T;
     p.seed = seed;
     p.m_tiles = m_tiles;
+    for (int l = 0; l < 2; ++l) {
+        p.sig_gpt[l] = (p.L[l].bn + TC_GW - 1) / TC_GW;
+        if (p.L[l].n_tiles * p.sig_gpt[l] > TC_SIG_MAX) persist = false;  // more progress barriers than the CTA holds
+    }
     if (persist) {
         p.persist = 1;
+        p.sig_fine = 1;
+        if (const char *env = getenv("ISB_TC_FINE")) p.sig_fine = std::max(0, atoi(env));
         p.rows_per_cta = rows;
         p.nsteps_seg = (int)nseg;
         p.k0 = k0;

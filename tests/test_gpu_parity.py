@@ -430,16 +430,21 @@ def test_bip_tc_chain_resident_equals_per_half_step_launches(ctx, synth, monkeyp
     T = synth.geometric_schedule(1.5, 0.4, nsteps)
     for rule in (0, 1):
         res = []
-        for persist in ("0", "1"):
+        # chain-resident mode with progress published per tile ("0"), per round of columns in the last tile ("1")
+        # and in every tile ("99")
+        for persist, fine in (("0", "1"), ("1", "0"), ("1", "1"), ("1", "99")):
             monkeypatch.setenv("ISB_TC_PERSIST", persist)
+            monkeypatch.setenv("ISB_TC_FINE", fine)
             e = L.Ensemble(L.Model.bipartite(ctx, W, h, b, L.PREC_BF16X3), R)
             e.set_spins(S0)
             e.set_hidden(T0)
             E = e.bip_run(rule, nsteps, seed=42, step_offset=7, T=T, trace_every=2)
             res.append((e.get_spins(), e.get_hidden(), E, e.last_stats()["launches"]))
-        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
-        assert np.array_equal(res[0][2], res[1][2])
-        assert res[1][3] < res[0][3]  # fewer launches in chain-resident mode
+        for other in res[1:]:
+            assert np.array_equal(res[0][0], other[0]) and np.array_equal(res[0][1], other[1])
+            assert np.array_equal(res[0][2], other[2])
+            assert other[3] < res[0][3]  # fewer launches in chain-resident mode
+    monkeypatch.delenv("ISB_TC_FINE")
     # caller-supplied fluctuations through the chain-resident kernel vs the oracle-checked exact path at T = 0
     monkeypatch.setenv("ISB_TC_PERSIST", "1")
     if R <= 1000:
