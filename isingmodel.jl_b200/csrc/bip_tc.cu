@@ -34,7 +34,11 @@ namespace isb {
 constexpr int TC_BM = 128;      // replicas per tile (UMMA M)
 constexpr int TC_BK = 64;       // K elements per stage (128 bytes of bf16 = one swizzle span)
 constexpr int TC_BN_MAX = 256;  // units per tile (UMMA N), runtime BN <= 256, multiple of 16
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 4;     // smem ring slots, single CTAs (16 KiB of A + 32 KiB of B each)
+#ifndef ISB_TC_STAGES2
+#define ISB_TC_STAGES2 6
+#endif
+constexpr int TC_STAGES2 = ISB_TC_STAGES2;  // CTA pairs: a slot holds 16 KiB of A + half a B tile (16 KiB)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KiB
 constexpr int TC_B_BYTES = TC_BN_MAX * TC_BK * 2;      // 32 KiB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
@@ -53,6 +57,8 @@ constexpr int TC_GW = TC_CW * TC_HALVES;        // accumulator columns the epilo
 constexpr int TC_SIG_MAX = 32;                  // chain-resident mode: progress barriers per layer
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers*/;
 static_assert((2 * TC_STAGES + 6 + 2 * TC_SIG_MAX) * 8 <= 1024, "barrier block");
+static_assert((2 * TC_STAGES2 + 6 + 2 * TC_SIG_MAX) * 8 <= 1024, "barrier block");
+static_assert(TC_STAGES2 * (TC_A_BYTES + TC_B_BYTES / 2) <= TC_STAGES * TC_STAGE_BYTES, "pair ring fits the same smem");
 
 struct TcModel {
     int P = 1;
@@ -98,6 +104,10 @@ struct TcParams {
     // `nsteps_seg` full steps (hidden then visible) on them without leaving the SM — chains are independent, so
     // no grid-wide synchronisation exists; only the CTA's own producer waits for its own epilogue.
     int persist, layer, m_tiles, rows_per_cta, nsteps_seg;
+    // cg == 2: CTA pairs (cta_group::2).  The two CTAs of a cluster run one M = 256 MMA together: CTA `rank` owns the
+    // replicas [m0 + 128 rank, + 128) of the pair's tile and loads the rows [rank bn/2, + bn/2) of the coupling tile,
+    // so every SM ingests half of W per tile.  m_tiles counts tiles of 128 cg replicas.
+    int cg;
     // chain-resident mode: the epilogue publishes its progress through the layer it is writing (one mbarrier per
     // tile and per round of TC_GW columns, sig_gpt[layer] rounds per tile), and the producer of the next half-step
     // waits K block by K block instead of for the whole layer.  The last `sig_fine` tiles of a half-step publish
@@ -119,9 +129,10 @@ struct TcJob {
     bool hs_first, hs_last;
 };
 struct TcJobIter {
-    int tile, layer, n_blk, step;
-    __device__ __forceinline__ void init(const TcParams &p) {
-        tile = blockIdx.x;
+    int tile, layer, n_blk, step, crank;
+    __device__ __forceinline__ void init(const TcParams &p, int cta_rank_in_pair) {
+        tile = blockIdx.x / p.cg;
+        crank = cta_rank_in_pair;
         layer = 1;
         n_blk = 0;
         step = 0;
@@ -131,12 +142,12 @@ struct TcJobIter {
             const int nt = p.L[p.layer].n_tiles;
             if (tile >= p.m_tiles * nt) return false;
             j.layer = p.layer;
-            j.m0 = (tile / nt) * TC_BM;
+            j.m0 = (tile / nt) * (TC_BM * p.cg) + crank * TC_BM;
             j.n_blk = tile % nt;
             j.hs = 0;
             j.k = p.k0;
             j.hs_first = j.hs_last = false;
-            tile += gridDim.x;
+            tile += gridDim.x / p.cg;
             return true;
         }
         if (step >= p.nsteps_seg) return false;
@@ -175,27 +186,83 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+// 2-CTA variants (CG = 2, the two CTAs of a cluster on one TPC): each CTA loads its own A rows and HALF of the B
+// tile; the bytes of both CTAs complete on the leader's (cluster rank 0) full barrier, whose address `leader_bar`
+// is a shared::cluster address obtained with mapa.
+__device__ __forceinline__ uint32_t mapa_rank0(const void *smem_ptr) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(ra) : "r"(smem_u32(smem_ptr)));
+    return ra;
 }
+// Arrive on the leader's barrier (a shared::cluster address from mapa_rank0).  No .release.cluster here: the arrivals
+// this kernel sends to the peer order nothing the generic proxy wrote (TMA bytes are tracked by complete_tx, TMEM reads
+// are fenced by tcgen05.fence), and a cluster-scope release per ring slot throttled the producer loop.
+__device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    if constexpr (CG == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
+    if constexpr (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+    else  // issued by the leader CTA only: M = 256 (128 rows of A per CTA), each CTA holds half of B's rows
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
 }
+// CG = 2: the arrive is multicast to the barrier at the same offset in both CTAs of the pair
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
+    if constexpr (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                     : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         smem_u32(bar)),
+                     "h"((uint16_t)3)
+                     : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -219,9 +286,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem_tile) {
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = bn
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int bn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = m (128, or 256 for a CTA pair), N = bn
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -232,45 +299,84 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
+// Waits of the tcgen05 kernel.  Single CTAs: every completion is local and the suspending try_wait (20 us hint)
+// leaves the issue slots to the epilogue warps.  CTA pairs: the barriers complete through the peer (remote arrives,
+// multicast commits, the peer's TMA bytes) and the suspended waiters were measured to wake late (the pair kernel ran
+// at half the single-CTA rate), so pairs poll.
+template <int CG>
+__device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
+#ifdef ISB_TC_PAIR_SLEEP
+    mbar_wait_sleep(bar, parity);
+#else
+    if constexpr (CG == 2)
+        mbar_wait(bar, parity);
+    else
+        mbar_wait_sleep(bar, parity);
+#endif
+}
+
+// The producer and the MMA issuer are one thread each: they poll (two threads' issue slots are nothing), so that the
+// dependency chain epilogue -> producer -> TMA -> MMA of a half-step boundary carries no wake-up latency.
+template <int CG>
+__device__ __forceinline__ void tc_wait1(uint64_t *bar, uint32_t parity) {
+#ifdef ISB_TC_SLEEP_ALL
+    tc_wait<CG>(bar, parity);
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+
 struct TcMaps {
     CUtensorMap A[2];     // input spin matrix of layer update [1] (visible layer) and [0] (hidden layer)
     CUtensorMap B[2][3];  // coupling terms of the two orientations
 };
 
-template <bool EXTF>
+template <bool EXTF, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+    constexpr int NST = CG == 2 ? TC_STAGES2 : TC_STAGES;     // ring slots
+    constexpr int STB = TC_A_BYTES + TC_B_BYTES / CG;         // bytes per slot
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
-    uint64_t *full_bar = bars;                     // [TC_STAGES]
-    uint64_t *empty_bar = bars + TC_STAGES;        // [TC_STAGES]
-    uint64_t *tfull_bar = bars + 2 * TC_STAGES;    // [2]
-    uint64_t *tempty_bar = bars + 2 * TC_STAGES + 2;  // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 5);
-    uint64_t *sig_bar = bars + 2 * TC_STAGES + 6;  // [2][TC_SIG_MAX] chain-resident mode: epilogue -> producer progress
+    uint64_t *full_bar = bars;                     // [NST]
+    uint64_t *empty_bar = bars + NST;        // [NST]
+    uint64_t *tfull_bar = bars + 2 * NST;    // [2]
+    uint64_t *tempty_bar = bars + 2 * NST + 2;  // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 5);
+    uint64_t *sig_bar = bars + 2 * NST + 6;  // [2][TC_SIG_MAX] chain-resident mode: epilogue -> producer progress
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = CG == 2 ? (int)cluster_ctarank() : 0;  // rank in the CTA pair; 0 = leader (issues the MMAs)
+    const bool leader = crank == 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
+#ifdef ISB_TC_PAIR_NOARRIVE  // A/B probe: only the leader arrives (with both CTAs' byte count)
             mbar_init(&full_bar[s], 1);
+#else
+            mbar_init(&full_bar[s], CG);   // pair: the leader's barrier takes one arrive per CTA and both CTAs' bytes
+#endif
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], TC_EPI_WARPS);
+            mbar_init(&tempty_bar[a], CG * TC_EPI_WARPS);  // pair: the epilogue warps of both CTAs release the leader's
         }
         if (p.persist)
             for (int i = 0; i < 2 * TC_SIG_MAX; ++i) mbar_init(&sig_bar[i], TC_EPI_WARPS);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) tmem_alloc<CG>(tmem_slot, 512);
     tc_fence_before();
-    __syncthreads();
+    // pair: no remote arrive, multicast commit or 2-CTA MMA may touch the peer before its barriers / TMEM exist
+    if constexpr (CG == 2)
+        cluster_sync_all();
+    else
+        __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     TcJobIter jobs;
-    jobs.init(p);
+    jobs.init(p, crank);
     TcJob job;
 
     if (warp == 0) {
@@ -286,7 +392,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 const int pl = 1 - job.layer;   // the layer sampled by the previous half-step = this one's input
                 const uint32_t dep_par = (uint32_t)((job.hs >> 1) - (job.layer == 1 ? 1 : 0)) & 1u;
                 int waited = -1;
-                const uint32_t tx = (uint32_t)(TC_A_BYTES + L.bn * TC_BK * 2);
+                const int bnc = L.bn / CG;      // rows of the coupling tile this CTA loads
+                const uint32_t tx = (uint32_t)(TC_A_BYTES + bnc * TC_BK * 2);
 #ifdef ISB_TC_PROBE_K1  // timing probe only: one K block per tile = the epilogue's cost without the contraction
                 const int num_kb = 1;
 #else
@@ -297,50 +404,67 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                         const int ul = min(kb * TC_BK + TC_BK - 1, p.L[pl].nout - 1);
                         const int idx = (ul / p.L[pl].bn) * p.sig_gpt[pl] + (ul % p.L[pl].bn) / TC_GW;
                         if (idx > waited) {
-                            mbar_wait_sleep(&sig_bar[pl * TC_SIG_MAX + idx], dep_par);
+                            tc_wait1<CG>(&sig_bar[pl * TC_SIG_MAX + idx], dep_par);
                             waited = idx;
                         }
                     }
                     for (int t = 0; t < p.P; ++t, ++it) {
-                        const int s = it % TC_STAGES;
-                        mbar_wait_sleep(&empty_bar[s], ((it / TC_STAGES) & 1) ^ 1);
-                        unsigned char *sa = smem + (size_t)s * TC_STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[s], tx);
-                        tma_load_3d(sa, &maps.A[job.layer], (kb % L.kb_per_blk) * TC_BK, job.m0, kb / L.kb_per_blk, &full_bar[s]);
-                        tma_load_2d(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * TC_BK, job.n_blk * L.bn, &full_bar[s]);
+                        const int s = it % NST;
+                        tc_wait1<CG>(&empty_bar[s], ((it / NST) & 1) ^ 1);
+                        unsigned char *sa = smem + (size_t)s * STB;
+                        if constexpr (CG == 1) {
+                            mbar_arrive_expect_tx(&full_bar[s], tx);
+                            tma_load_3d(sa, &maps.A[job.layer], (kb % L.kb_per_blk) * TC_BK, job.m0, kb / L.kb_per_blk, &full_bar[s]);
+                            tma_load_2d(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * TC_BK, job.n_blk * L.bn, &full_bar[s]);
+                        } else {
+                            const uint32_t lbar = mapa_rank0(&full_bar[s]);
+                            if (leader)
+                                mbar_arrive_expect_tx(&full_bar[s], 2u * tx);
+#ifndef ISB_TC_PAIR_NOARRIVE
+                            else
+                                mbar_arrive_cluster_addr(lbar);
+#endif
+                            tma_load_3d_cg2(sa, &maps.A[job.layer], (kb % L.kb_per_blk) * TC_BK, job.m0, kb / L.kb_per_blk, lbar);
+                            tma_load_2d_cg2(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * TC_BK, job.n_blk * L.bn + crank * bnc, lbar);
+                        }
                     }
                 }
             }
+            if constexpr (CG == 2) {
+                // the leader's commits also arrive on this CTA's empty barriers: do not retire (or let the peer retire)
+                // before the last of them has landed
+                for (int i = 0; i < NST; ++i, ++it) tc_wait1<CG>(&empty_bar[it % NST], ((it / NST) & 1) ^ 1);
+            }
         }
     } else if (warp == 1) {
-        // ================================================================ MMA issuer
-        if (lane == 0) {
+        // ================================================================ MMA issuer (pair: the leader CTA's only)
+        if (lane == 0 && leader) {
             uint32_t it = 0, tl = 0;
             while (jobs.next(p, job)) {
                 const TcLayer &L = p.L[job.layer];
-                const uint32_t idesc = umma_idesc_bf16(L.bn);
+                const uint32_t idesc = umma_idesc_bf16(TC_BM * CG, L.bn);
 #ifdef ISB_TC_PROBE_K1
                 const int iters = p.P;
 #else
                 const int iters = L.num_kb * p.P;
 #endif
                 const int a = tl & 1;
-                mbar_wait_sleep(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                tc_wait1<CG>(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN_MAX);
                 for (int i = 0; i < iters; ++i, ++it) {
-                    const int s = it % TC_STAGES;
-                    mbar_wait_sleep(&full_bar[s], (it / TC_STAGES) & 1);
+                    const int s = it % NST;
+                    tc_wait1<CG>(&full_bar[s], (it / NST) & 1);
                     tc_fence_after();
-                    const unsigned char *sa = smem + (size_t)s * TC_STAGE_BYTES;
+                    const unsigned char *sa = smem + (size_t)s * STB;
                     const uint64_t adesc = umma_desc_sw128(sa);
                     const uint64_t bdesc = umma_desc_sw128(sa + TC_A_BYTES);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k)  // advance 16 bf16 = 32 B = 2 descriptor units along K
-                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
-                    umma_commit(&empty_bar[s]);  // slot free when these MMAs have read it
+                        umma_bf16<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+                    umma_commit<CG>(&empty_bar[s]);  // slot free (in both CTAs of a pair) when these MMAs have read it
                 }
-                umma_commit(&tfull_bar[a]);      // accumulator complete
+                umma_commit<CG>(&tfull_bar[a]);      // accumulator complete (each CTA holds its 128 replicas x bn units)
                 ++tl;
             }
         }
@@ -357,17 +481,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             constexpr int CW = TC_CW;
             const int nchunks = L.bn / CW;
             const int a = tl & 1;
-            mbar_wait_sleep(&tfull_bar[a], (tl >> 1) & 1);
-            tc_fence_after();
             const int lrow = quad * 32 + lane;
             const int r = job.m0 + lrow;
             const bool row_ok = r < p.R && (!p.persist || lrow < p.rows_per_cta);
-            // temperature of this thread's replica (per-replica factors make it a per-row quantity)
-            double Td = p.Tsched ? p.Tsched[job.k / p.steps_per_T] : p.T_direct;
-            if (p.tscale && row_ok) Td = __dmul_rn(Td, p.tscale[r]);
+            // temperature of this thread's replica (per-replica factors make it a per-row quantity); fetched BEFORE the
+            // wait for the accumulator, so that the schedule load (an L2 round trip per tile) overlaps the MMAs instead
+            // of sitting on the MMA -> epilogue -> next half-step critical path
+            double Td = p.Tsched ? __ldg(&p.Tsched[job.k / p.steps_per_T]) : p.T_direct;
+            if (p.tscale && row_ok) Td = __dmul_rn(Td, __ldg(&p.tscale[r]));
             const float Tf = (float)Td;
             const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2
             const float cE = Tf > 0.f ? -2.0f * 1.4426950408889634f / Tf : 0.f;  // e^{-2x/T} = 2^{cE x}
+            tc_wait<CG>(&tfull_bar[a], (tl >> 1) & 1);
+            tc_fence_after();
             const int gpt = p.sig_gpt[job.layer];
             const bool fine = p.persist && job.n_blk >= L.n_tiles - p.sig_fine;
             uint64_t *sig = sig_bar + job.layer * TC_SIG_MAX + job.n_blk * gpt;
@@ -385,7 +511,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             __nv_bfloat16 *out_t = L.out_bf + (int64_t)(row_ok ? r : job.m0) * L.ldo + tile_u0;
             const uint32_t taddr_t = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TC_BN_MAX);
             const uint32_t pc2 = (uint32_t)(r + p.r_off), pc3 = (L.domain << 28) | (uint32_t)((L.u_off + tile_u0) >> 2);
+#ifdef ISB_TC_PROBE_NO_EPI  // timing probe only: the contraction without the sampling epilogue
+            for (int g = 0; false;) {
+#else
             for (int g = 0; g * TC_HALVES < nchunks; ++g) {
+#endif
               const int c = g * TC_HALVES + half;
               if (c < nfull) {
                 uint32_t v[16];
@@ -528,7 +658,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[a]);
+            if (lane == 0) {
+                if (CG == 2 && !leader)
+                    mbar_arrive_cluster_addr(mapa_rank0(&tempty_bar[a]));
+                else
+                    mbar_arrive(&tempty_bar[a]);
+            }
             if (p.persist && !fine) {
                 fence_proxy_async_global();
                 __syncwarp();
@@ -539,10 +674,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2)
+        cluster_sync_all();  // neither CTA frees its TMEM or retires while the pair's MMAs / remote arrives can be in flight
+    else
+        __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc<CG>(tmem_base, 512);
     }
 }
 
@@ -645,7 +783,7 @@ static unsigned short bf16_rne(double x, double *back) {
 
 // Tile width for a one-launch-per-half-step GEMM: the launch takes waves x bn "column units" of MMA time, so
 // minimise ceil(m_tiles * ceil(nout / bn) / SMs) * bn over the legal widths (multiples of 16 up to 256).
-static int pick_bn_waves(int nout, int m_tiles, int num_sms) {
+static int pick_bn_waves(int nout, int m_tiles, int num_sms /* CTAs, or CTA pairs, that run tiles concurrently */) {
     int best = 0;
     long best_cost = 0;
     for (int bn = 256; bn >= 64; bn -= 16) {
@@ -665,14 +803,25 @@ static int pick_bn(int nout) {
     return bn < 16 ? 16 : bn;
 }
 
+// Row pitch (elements) of a K-major bf16 operand with k valid columns.  A TMA box reads 128-256 rows at this pitch at
+// once: a pitch that is a multiple of 1 KiB would put all of them on a few L2 slices, so such pitches get one more
+// 128-byte line (ISB_TC_PAD=0 disables the padding, for A/B measurements).
+static int tc_pitch(int k) {
+    int ld = (k + 15) / 16 * 16;
+    bool pad = true;
+    if (const char *env = getenv("ISB_TC_PAD")) pad = atoi(env) != 0;
+    if (pad && (ld * 2) % 1024 == 0) ld += 64;
+    return ld;
+}
+
 int bip_tc_model_init(isb_model *m, const double *W /*[nv][nh] row-major*/) {
     isb_ctx *ctx = m->ctx;
     TcModel *t = new TcModel();
     m->tc = t;
     t->P = m->prec == ISB_PREC_BF16X3 ? 3 : (m->prec == ISB_PREC_BF16X2 ? 2 : 1);
     const int nv = m->nv, nh = m->nh;
-    t->ldkv = (nv + 15) / 16 * 16;
-    t->ldkh = (nh + 15) / 16 * 16;
+    t->ldkv = tc_pitch(nv);
+    t->ldkh = tc_pitch(nh);
     t->bn_h = pick_bn(nh);
     t->bn_v = pick_bn(nv);
     t->rows_t = nh; t->cols_t = nv; t->rows_n = nv; t->cols_n = nh;
@@ -744,7 +893,8 @@ void bip_tc_ens_free(isb_ens *e) {
 }
 
 static int make_map(isb_ctx *ctx, CUtensorMap *map, const void *base, int rows, int cols, int64_t ld, int box_rows);
-// Coupling tensor maps of orientation `orient` (1: Wt, hidden update; 0: Wn, visible update) for tile width bn
+// Coupling tensor maps of orientation `orient` (1: Wt, hidden update; 0: Wn, visible update) whose box holds `bn`
+// rows of W (the tile width, or half of it when a CTA pair shares the tile)
 static int get_maps_b(isb_ctx *ctx, TcModel *t, int orient, int bn, CUtensorMap out[3]) {
     const int dflt = orient == 1 ? t->bn_h : t->bn_v;
     if (bn == dflt) {
@@ -788,16 +938,38 @@ static void fill_layer(TcLayer &L, int nout, int kin, int bn, __nv_bfloat16 *out
     L.npeer = 0;
 }
 
-static int launch_tc(isb_ctx *ctx, const TcMaps &maps, const TcParams &p, int grid, bool extf) {
-    if (extf) {
-        ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        bip_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(maps, p);
-    } else {
-        ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        bip_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(maps, p);
-    }
-    ISB_CUDA(ctx, cudaGetLastError());
+// CTA pairs (cta_group::2) or single CTAs?  Pairs halve the coupling bytes every SM pulls from L2 (the measured wall
+// of the 1-CTA kernel: ~67 B/clk/SM against the 94 B/clk a 128 x 256 x 64 tile needs at full MMA rate).
+// ISB_TC_CG=1|2 overrides.
+static int tc_cta_group() {
+    int cg = 1;
+    if (const char *env = getenv("ISB_TC_CG")) cg = atoi(env) == 2 ? 2 : 1;
+    return cg;
+}
+
+template <bool EXTF, int CG>
+static int launch_tc_inst(isb_ctx *ctx, const TcMaps &maps, const TcParams &p, int grid) {
+    ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<EXTF, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CG > 1 ? 1 : 0;
+    ISB_CUDA(ctx, cudaLaunchKernelEx(&cfg, bip_tc_kernel<EXTF, CG>, maps, p));
     return ISB_OK;
+}
+
+// grid = CTAs (a multiple of p.cg)
+static int launch_tc(isb_ctx *ctx, const TcMaps &maps, const TcParams &p, int grid, bool extf) {
+    if (p.cg == 2) return extf ? launch_tc_inst<true, 2>(ctx, maps, p, grid) : launch_tc_inst<false, 2>(ctx, maps, p, grid);
+    return extf ? launch_tc_inst<true, 1>(ctx, maps, p, grid) : launch_tc_inst<false, 1>(ctx, maps, p, grid);
 }
 
 // Steps [k0, k0 + nseg) of a run: one chain-resident launch when the replicas fill the SMs, else 2 * nseg
@@ -809,7 +981,8 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     isb_ctx *ctx = m->ctx;
     TcModel *t = (TcModel *)m->tc;
     TcEns *s = (TcEns *)e->tc;
-    const int m_tiles = (e->R + TC_BM - 1) / TC_BM;
+    const int cg = tc_cta_group();
+    const int m_tiles = (e->R + TC_BM * cg - 1) / (TC_BM * cg);
     const bool extf = fluct_mode != ISB_FLUCT_PHILOX;
     // chain-resident mode pays off when every SM gets a (nearly) full 128-row block of replicas to itself
     int rows = (e->R + ctx->num_sms - 1) / ctx->num_sms;
@@ -817,16 +990,17 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     bool persist = rows >= 96;
     if (const char *env = getenv("ISB_TC_PERSIST")) persist = atoi(env) != 0 && e->R >= 1;
     // tile widths: least padding per CTA in chain-resident mode, fewest (waves x width) otherwise
-    const int bn_h = persist ? t->bn_h : pick_bn_waves(m->nh, m_tiles, ctx->num_sms);
-    const int bn_v = persist ? t->bn_v : pick_bn_waves(m->nv, m_tiles, ctx->num_sms);
+    const int bn_h = persist ? t->bn_h : pick_bn_waves(m->nh, m_tiles, ctx->num_sms / cg);
+    const int bn_v = persist ? t->bn_v : pick_bn_waves(m->nv, m_tiles, ctx->num_sms / cg);
     TcMaps maps;
     maps.A[1] = s->mapSv;
     maps.A[0] = s->mapSh;
-    int rcm = get_maps_b(ctx, t, 1, bn_h, maps.B[1]);
+    int rcm = get_maps_b(ctx, t, 1, bn_h / cg, maps.B[1]);
     if (rcm) return rcm;
-    rcm = get_maps_b(ctx, t, 0, bn_v, maps.B[0]);
+    rcm = get_maps_b(ctx, t, 0, bn_v / cg, maps.B[0]);
     if (rcm) return rcm;
     TcParams p{};
+    p.cg = cg;
     fill_layer(p.L[1], m->nh, m->nv, bn_h, s->Sh, t->ldkh, m->bb64, t->bias_hf, d_Fh, DOM_BIP_HIDDEN);
     fill_layer(p.L[0], m->nv, m->nh, bn_v, s->Sv, t->ldkv, m->hb64, t->bias_vf, d_Fv, DOM_BIP_VISIBLE);
     p.R = e->R;
@@ -851,7 +1025,7 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
         p.nsteps_seg = (int)nseg;
         p.k0 = k0;
         p.step_abs0 = step_offset + (uint64_t)k0;
-        const int grid = (e->R + rows - 1) / rows;
+        const int grid = ((e->R + rows - 1) / rows + cg - 1) / cg * cg;  // an odd last CTA gets a peer without replicas
         int rc = launch_tc(ctx, maps, p, grid, extf);
         if (rc) return rc;
         e->last_launches += 1;
@@ -863,7 +1037,7 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
             p.layer = layer;
             p.k0 = k;
             p.step_abs0 = step_offset + (uint64_t)k;
-            const int grid = std::min(p.L[layer].n_tiles * p.m_tiles, ctx->num_sms);
+            const int grid = std::min(p.L[layer].n_tiles * p.m_tiles, ctx->num_sms / cg) * cg;
             int rc = launch_tc(ctx, maps, p, grid, extf);
             if (rc) return rc;
             e->last_launches += 1;
@@ -964,8 +1138,10 @@ int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, in
     int rc = make_map_a(ctx, &maps.A[layer], in_full, m->shard_G, R, m->shard_nb, m->shard_nb);
     if (rc) return rc;
     maps.A[1 - layer] = maps.A[layer];
-    const int bn = pick_bn_waves(m->shard_nb, (R + TC_BM - 1) / TC_BM, ctx->num_sms);
-    rc = get_maps_b(ctx, t, 1, bn, maps.B[1]);  // W is symmetric: one orientation serves both half-steps
+    const int cg = tc_cta_group();
+    const int m_tiles = (R + TC_BM * cg - 1) / (TC_BM * cg);
+    const int bn = pick_bn_waves(m->shard_nb, m_tiles, ctx->num_sms / cg);
+    rc = get_maps_b(ctx, t, 1, bn / cg, maps.B[1]);  // W is symmetric: one orientation serves both half-steps
     if (rc) return rc;
     for (int i = 0; i < 3; ++i) maps.B[0][i] = maps.B[1][i];
     TcParams p{};
@@ -990,8 +1166,9 @@ int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, in
     p.step_abs0 = step_abs;
     p.persist = 0;
     p.layer = layer;
-    p.m_tiles = (R + TC_BM - 1) / TC_BM;
-    const int grid = std::min(p.L[layer].n_tiles * p.m_tiles, ctx->num_sms);
+    p.cg = cg;
+    p.m_tiles = m_tiles;
+    const int grid = std::min(p.L[layer].n_tiles * p.m_tiles, ctx->num_sms / cg) * cg;
     return launch_tc(ctx, maps, p, grid, false);
 }
 
@@ -1017,15 +1194,18 @@ int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, cons
     };
     int64_t ntr = 0;
     const bool tracing = (d_E || d_Sv || d_Sh) && trace_every > 0;
+    bool canonical_fresh = false;  // the int8 spins already hold the state of the last executed step
     for (int64_t k0 = 0; k0 < nsteps;) {
         const int64_t nseg = tracing ? std::min<int64_t>(trace_every - (k0 % trace_every), nsteps - k0)
                                      : std::min<int64_t>(nsteps - k0, 1 << 20);
         int rc = launch_steps(e, rule, fluct_mode, d_Fv, d_Fh, nsteps, k0, nseg, d_T, steps_per_T, seed, step_offset);
         if (rc) return rc;
         k0 += nseg;
+        canonical_fresh = false;
         if (tracing && k0 % trace_every == 0) {
             rc = sync_canonical();
             if (rc) return rc;
+            canonical_fresh = true;
             if (d_E) {
                 rc = bip_energy_device(e, d_E + ntr * e->R);
                 if (rc) return rc;
@@ -1036,7 +1216,7 @@ int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, cons
             ++ntr;
         }
     }
-    return sync_canonical();
+    return canonical_fresh ? ISB_OK : sync_canonical();
 }
 
 }  // namespace isb

@@ -461,6 +461,35 @@ def test_bip_tc_chain_resident_equals_per_half_step_launches(ctx, synth, monkeyp
         assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
 
 
+@pytest.mark.parametrize("R,nv,nh", [(300, 160, 96), (130, 784, 512), (1, 24, 17), (19500, 96, 80)])
+def test_bip_tc_cta_pairs_equal_single_ctas(ctx, synth, monkeypatch, R, nv, nh):
+    """cta_group::2 (two CTAs share one M = 256 MMA, each loads half of the coupling tile) must reproduce the
+    single-CTA kernel bit for bit: same K order, same noise words; in both launch modes, for both rules, with
+    in-kernel and caller-supplied noise.  R = 130 / R = 1 leave the second CTA of a pair (almost) without replicas."""
+    L = _lib()
+    W, h, b = synth.bipartite_W(nv, nh, 111, 0.2)
+    S0, T0 = synth.spins(112, R, nv), synth.spins(113, R, nh)
+    nsteps = 4
+    T = synth.geometric_schedule(1.5, 0.4, nsteps)
+    Fv, Fh = synth.logistic(114, (nsteps, nv), 1), synth.logistic(114, (nsteps, nh), 2)
+    for prec in (L.PREC_BF16X3, L.PREC_BF16X1):
+        m = L.Model.bipartite(ctx, W, h, b, prec)
+        for rule in (0, 1):
+            for kw in (dict(seed=42, step_offset=7), dict(Fv=Fv, Fh=Fh)):
+                res = []
+                for cg, persist in (("1", "0"), ("2", "0"), ("2", "1")):
+                    monkeypatch.setenv("ISB_TC_CG", cg)
+                    monkeypatch.setenv("ISB_TC_PERSIST", persist)
+                    e = L.Ensemble(m, R)
+                    e.set_spins(S0)
+                    e.set_hidden(T0)
+                    E = e.bip_run(rule, nsteps, T=T, trace_every=2, **kw)
+                    res.append((e.get_spins(), e.get_hidden(), E))
+                for other in res[1:]:
+                    assert np.array_equal(res[0][0], other[0]) and np.array_equal(res[0][1], other[1])
+                    assert np.array_equal(res[0][2], other[2])
+
+
 # ---------------------------------------------------------------- edge cases
 def test_edge_cases(ctx, orc, synth):
     L = _lib()
