@@ -233,6 +233,16 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     else
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// true in exactly one (converged) lane of the warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 template <int CG>
@@ -381,8 +391,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
 
     if (warp == 0) {
         // ================================================================ TMA producer
-        if (lane == 0) {
-            uint32_t it = 0;
+        // (the whole warp walks the loop, one elected lane issues: see the MMA issuer below)
+        {
+            int s = 0;            // ring slot and its phase, kept incrementally
+            uint32_t ph = 0;
             while (jobs.next(p, job)) {
                 const TcLayer &L = p.L[job.layer];
                 // chain-resident mode: this half-step's A operand is what the CTA's own epilogue wrote during the
@@ -399,6 +411,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
 #else
                 const int num_kb = L.num_kb;
 #endif
+                int kq = 0, kr = 0;             // kb = kq * kb_per_blk + kr (slab of the A operand, block within it)
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (dep) {
                         const int ul = min(kb * TC_BK + TC_BK - 1, p.L[pl].nout - 1);
@@ -408,38 +421,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                             waited = idx;
                         }
                     }
-                    for (int t = 0; t < p.P; ++t, ++it) {
-                        const int s = it % NST;
-                        tc_wait1<CG>(&empty_bar[s], ((it / NST) & 1) ^ 1);
+                    for (int t = 0; t < p.P; ++t) {
+                        tc_wait1<CG>(&empty_bar[s], ph ^ 1u);
                         unsigned char *sa = smem + (size_t)s * STB;
-                        if constexpr (CG == 1) {
-                            mbar_arrive_expect_tx(&full_bar[s], tx);
-                            tma_load_3d(sa, &maps.A[job.layer], (kb % L.kb_per_blk) * TC_BK, job.m0, kb / L.kb_per_blk, &full_bar[s]);
-                            tma_load_2d(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * TC_BK, job.n_blk * L.bn, &full_bar[s]);
-                        } else {
-                            const uint32_t lbar = mapa_rank0(&full_bar[s]);
-                            if (leader)
-                                mbar_arrive_expect_tx(&full_bar[s], 2u * tx);
+                        if (elect_one()) {
+                            if constexpr (CG == 1) {
+                                mbar_arrive_expect_tx(&full_bar[s], tx);
+                                tma_load_3d(sa, &maps.A[job.layer], kr * TC_BK, job.m0, kq, &full_bar[s]);
+                                tma_load_2d(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * TC_BK, job.n_blk * L.bn, &full_bar[s]);
+                            } else {
+                                const uint32_t lbar = mapa_rank0(&full_bar[s]);
+                                if (leader)
+                                    mbar_arrive_expect_tx(&full_bar[s], 2u * tx);
 #ifndef ISB_TC_PAIR_NOARRIVE
-                            else
-                                mbar_arrive_cluster_addr(lbar);
+                                else
+                                    mbar_arrive_cluster_addr(lbar);
 #endif
-                            tma_load_3d_cg2(sa, &maps.A[job.layer], (kb % L.kb_per_blk) * TC_BK, job.m0, kb / L.kb_per_blk, lbar);
-                            tma_load_2d_cg2(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * TC_BK, job.n_blk * L.bn + crank * bnc, lbar);
+                                tma_load_3d_cg2(sa, &maps.A[job.layer], kr * TC_BK, job.m0, kq, lbar);
+                                tma_load_2d_cg2(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * TC_BK, job.n_blk * L.bn + crank * bnc, lbar);
+                            }
                         }
+                        __syncwarp();
+                        if (++s == NST) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                    if (++kr == L.kb_per_blk) {
+                        kr = 0;
+                        ++kq;
                     }
                 }
             }
             if constexpr (CG == 2) {
                 // the leader's commits also arrive on this CTA's empty barriers: do not retire (or let the peer retire)
                 // before the last of them has landed
-                for (int i = 0; i < NST; ++i, ++it) tc_wait1<CG>(&empty_bar[it % NST], ((it / NST) & 1) ^ 1);
+                for (int i = 0; i < NST; ++i) {
+                    tc_wait1<CG>(&empty_bar[s], ph ^ 1u);
+                    if (++s == NST) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer (pair: the leader CTA's only)
-        if (lane == 0 && leader) {
-            uint32_t it = 0, tl = 0;
+        // The WHOLE warp walks this loop and one elected lane issues: with warp-uniform control flow the smem
+        // descriptors, TMEM and barrier addresses stay in uniform registers.  (Under `if (lane == 0)` ptxas wrapped every
+        // tcgen05 instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: 112 instructions per K block, 890 cycles for
+        // 512 cycles of MMA — the issuing thread, not the operand feed, bounded the contraction.)
+        if (CG == 1 || leader) {
+            uint32_t tl = 0;
+            int s = 0;            // ring slot and its phase, kept incrementally
+            uint32_t ph = 0;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             while (jobs.next(p, job)) {
                 const TcLayer &L = p.L[job.layer];
                 const uint32_t idesc = umma_idesc_bf16(TC_BM * CG, L.bn);
@@ -451,20 +487,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 const int a = tl & 1;
                 tc_wait1<CG>(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(a * TC_BN_MAX);
-                for (int i = 0; i < iters; ++i, ++it) {
-                    const int s = it % NST;
-                    tc_wait1<CG>(&full_bar[s], (it / NST) & 1);
+                const uint32_t d_tmem = tmem_u + (uint32_t)(a * TC_BN_MAX);
+                for (int i = 0; i < iters; ++i) {
+                    tc_wait1<CG>(&full_bar[s], ph);
                     tc_fence_after();
                     const unsigned char *sa = smem + (size_t)s * STB;
                     const uint64_t adesc = umma_desc_sw128(sa);
                     const uint64_t bdesc = umma_desc_sw128(sa + TC_A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k)  // advance 16 bf16 = 32 B = 2 descriptor units along K
-                        umma_bf16<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
-                    umma_commit<CG>(&empty_bar[s]);  // slot free (in both CTAs of a pair) when these MMAs have read it
+                        for (int k = 0; k < TC_BK / 16; ++k)  // advance 16 bf16 = 32 B = 2 descriptor units along K
+                            umma_bf16<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+                        umma_commit<CG>(&empty_bar[s]);  // slot free (in both CTAs of a pair) when these MMAs have read it
+                    }
+                    __syncwarp();
+                    if (++s == NST) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
                 }
-                umma_commit<CG>(&tfull_bar[a]);      // accumulator complete (each CTA holds its 128 replicas x bn units)
+                if (elect_one()) umma_commit<CG>(&tfull_bar[a]);  // accumulator complete (each CTA: its 128 replicas x bn units)
+                __syncwarp();
                 ++tl;
             }
         }
@@ -938,12 +981,12 @@ static void fill_layer(TcLayer &L, int nout, int kin, int bn, __nv_bfloat16 *out
     L.npeer = 0;
 }
 
-// CTA pairs (cta_group::2) or single CTAs?  Pairs halve the coupling bytes every SM pulls from L2 (the measured wall
-// of the 1-CTA kernel: ~67 B/clk/SM against the 94 B/clk a 128 x 256 x 64 tile needs at full MMA rate).
-// ISB_TC_CG=1|2 overrides.
+// CTA pairs (cta_group::2, the default) or single CTAs (ISB_TC_CG=1)?  Pairs halve the coupling bytes every SM pulls
+// from L2 and reads from shared memory per MMA.  Measured on B200 (bf16x1 / bf16x3, TFLOP/s algorithmic): C3 1340 / 472
+// with single CTAs, 1453 / 504 with pairs; C4 651 / 325 vs 670 / 391.  Results are bit-identical.
 static int tc_cta_group() {
-    int cg = 1;
-    if (const char *env = getenv("ISB_TC_CG")) cg = atoi(env) == 2 ? 2 : 1;
+    int cg = 2;
+    if (const char *env = getenv("ISB_TC_CG")) cg = atoi(env) == 1 ? 1 : 2;
     return cg;
 }
 
