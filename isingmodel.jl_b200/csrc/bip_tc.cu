@@ -11,13 +11,16 @@
 //                W is stored as P bf16 terms W = W1 + W2 + W3 (P = 3: 24 mantissa bits, fp32-exact split;
 //                P = 1: W rounded to bf16, exact when W is bf16-representable, e.g. small integers);
 //   D          = fp32 accumulators in TMEM (2 stages x 256 columns), all P terms accumulate into the same D.
-// Warp-specialised persistent kernel, one CTA per SM:
-//   warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage smem ring, mbarrier complete_tx)
-//   warp 1 = MMA issuer (one elected thread: tcgen05.mma.cta_group::1.kind::f16, tcgen05.commit frees the slot)
+// Warp-specialised persistent kernel, one CTA per SM, by default in CTA pairs (cta_group::2: the two CTAs of a
+// cluster run one M = 256 MMA, each loading its own 128 replicas of A and half of the coupling tile):
+//   warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, smem ring of 6 (pairs) / 4 slots, mbarrier complete_tx)
+//   warp 1 = MMA issuer (tcgen05.mma.kind::f16 by one elected lane of the leader CTA, tcgen05.commit frees the slot)
 //   warp 2 = TMEM allocator
 //   warps 4-19 = epilogue: tcgen05.ld the accumulators, draw the noise (Philox4x32-10, same words as the
-//                Float64 path), apply the rule, write the new layer as bf16 (next GEMM's operand) and as
-//                int8 (the ensemble's canonical spins), overlapping the next tile's MMAs.
+//                Float64 path), apply the rule, write the new layer as bf16 (next GEMM's operand),
+//                overlapping the next tile's MMAs; the canonical int8 spins are refreshed per run / trace point.
+// The producer and issuer warps run their loops warp-uniformly and pick the issuing lane with elect.sync, so that
+// descriptors and barrier addresses stay in uniform registers (see the note at the MMA issuer).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
