@@ -258,8 +258,9 @@ def sca_main(args):
     torch.cuda.set_stream(stream)
     ctx = _lib.context(local)
     ctx.set_stream(stream.cuda_stream)
-    prec = {"bf16x3": _lib.PREC_BF16X3, "bf16x2": _lib.PREC_BF16X2, "bf16x1": _lib.PREC_BF16X1, "f64": _lib.PREC_F64}[prec_name]
-    P = {"bf16x3": 3, "bf16x2": 2, "bf16x1": 1, "f64": 1}[prec_name]
+    prec = {"bf16x3": _lib.PREC_BF16X3, "bf16x2": _lib.PREC_BF16X2, "bf16x1": _lib.PREC_BF16X1, "f64": _lib.PREC_F64,
+            "fp16x2": _lib.PREC_FP16X2, "fp16x1": _lib.PREC_FP16X1}[prec_name]
+    P = {"bf16x3": 3, "bf16x2": 2, "bf16x1": 1, "f64": 1, "fp16x2": 2, "fp16x1": 1}[prec_name]
     pv = torch.empty((R, nv), dtype=torch.int8).pin_memory().numpy()
     ph = torch.empty((R, nh), dtype=torch.int8).pin_memory().numpy()
     pv[:] = synth.spins(11 + 1000 * rank, R, nv)
@@ -336,7 +337,7 @@ def sca_main(args):
         ach = alg / kern_s / 1e12
         line = {"metric": METRIC, "value": total / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec_name != "f64" else "f64",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64" if prec_name == "f64" else prec_name[:4],
                 "data": "synthetic", "config": cfg,
                 "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                              "traffic": None, "peak_source": src, "kernel": "isb::bip_tc_kernel",
@@ -613,7 +614,8 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=8.0, help="CPU seconds per reference-arm step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU seconds of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--prec", default=None, help="c2: f64 | f32; c3/c4/c5: bf16x3 | bf16x2 | bf16x1 (c3/c4 also f64)")
+    ap.add_argument("--prec", default=None,
+                    help="c2: f64 | f32; c3/c4/c5: bf16x3 | bf16x2 | bf16x1 (c3/c4 also f64, fp16x2, fp16x1)")
     ap.add_argument("--c5-n-per-gpu", type=int, default=8192, help="c5: rows of J per GPU (N = this x GPUs; 8 GPUs -> 65536)")
     ap.add_argument("--c5-replicas", type=int, default=1024)
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],

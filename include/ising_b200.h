@@ -74,8 +74,13 @@ enum {
     ISB_PREC_AUTO = 2,/* the library's choice for the model kind (dense / sparse J: F64 throughout)   */
     ISB_PREC_BF16X3 = 3, /* bipartite tensor path: W split into 3 bf16 terms, fp32 accumulation */
     ISB_PREC_BF16X1 = 4, /* bipartite tensor path: W rounded to one bf16 term (exact when W is)  */
-    ISB_PREC_BF16X2 = 5  /* bipartite tensor path: 2 bf16 terms (16 mantissa bits: the split error, 2^-17
+    ISB_PREC_BF16X2 = 5, /* bipartite tensor path: 2 bf16 terms (16 mantissa bits: the split error, 2^-17
                             relative per coupling, is of the order of the fp32 accumulation error itself) */
+    ISB_PREC_FP16X2 = 6, /* bipartite tensor path: 2 fp16 terms of the power-of-two pre-scaled W (11 + 11 bits + the
+                            sign of the second term: 2^-24 of max|W| per coupling, i.e. W as good as rounded to
+                            float) — the accuracy of _BF16X3 up to the fp32 accumulation, in two passes instead of
+                            three.  Not for row-sharded models.                                                   */
+    ISB_PREC_FP16X1 = 7  /* one fp16 term (2^-12 of max|W|; exact when the scaled W is fp16-representable)          */
 };
 
 /* ------------------------------------------------------------------ context */

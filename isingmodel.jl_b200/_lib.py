@@ -21,7 +21,7 @@ RULE_HOPFIELD, RULE_GLAUBER, RULE_METROPOLIS = 0, 1, 2
 BIP_SCA, BIP_MA = 0, 1
 ORDER_SEQUENTIAL, ORDER_LIST, ORDER_RANDOM = 0, 1, 2
 FLUCT_PHILOX, FLUCT_SHARED, FLUCT_PER_REPLICA = 0, 1, 2
-PREC_F64, PREC_F32, PREC_AUTO, PREC_BF16X3, PREC_BF16X1, PREC_BF16X2 = 0, 1, 2, 3, 4, 5
+PREC_F64, PREC_F32, PREC_AUTO, PREC_BF16X3, PREC_BF16X1, PREC_BF16X2, PREC_FP16X2, PREC_FP16X1 = 0, 1, 2, 3, 4, 5, 6, 7
 
 _ERR_NAMES = {1: "ISB_ERR_ARG", 2: "ISB_ERR_SIZE", 3: "ISB_ERR_NONFINITE", 4: "ISB_ERR_CUDA",
               5: "ISB_ERR_UNSUPPORTED", 6: "ISB_ERR_NCCL", 7: "ISB_ERR_STATE"}

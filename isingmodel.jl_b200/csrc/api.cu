@@ -329,8 +329,9 @@ int isb_model_bipartite(isb_ctx *ctx, int nv, int nh, const double *W, int64_t l
     if (nv <= 0 || nh <= 0) return fail(ctx, ISB_ERR_SIZE, "isb_model_bipartite: nv = %d, nh = %d must be positive", nv, nh);
     if (ld < nv) return fail(ctx, ISB_ERR_SIZE, "isb_model_bipartite: leading dimension %lld < nv = %d", (long long)ld, nv);
     if (prec == ISB_PREC_AUTO) prec = ISB_PREC_F64;
-    if (prec != ISB_PREC_F64 && prec != ISB_PREC_BF16X3 && prec != ISB_PREC_BF16X2 && prec != ISB_PREC_BF16X1)
-        return fail(ctx, ISB_ERR_ARG, "isb_model_bipartite: prec must be ISB_PREC_F64, _BF16X3, _BF16X2 or _BF16X1");
+    if (prec != ISB_PREC_F64 && prec != ISB_PREC_BF16X3 && prec != ISB_PREC_BF16X2 && prec != ISB_PREC_BF16X1 &&
+        prec != ISB_PREC_FP16X2 && prec != ISB_PREC_FP16X1)
+        return fail(ctx, ISB_ERR_ARG, "isb_model_bipartite: prec must be ISB_PREC_F64, _BF16X3, _BF16X2, _BF16X1, _FP16X2 or _FP16X1");
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<double> Wr((size_t)nv * nh), Wt((size_t)nv * nh), hn((size_t)nv, 0.0), bn((size_t)nh, 0.0);
     for (int j = 0; j < nh; ++j)

@@ -23,6 +23,7 @@
 // descriptors and barrier addresses stay in uniform registers (see the note at the MMA issuer).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <stdlib.h>
 
@@ -65,6 +66,11 @@ static_assert(TC_STAGES2 * (TC_A_BYTES + TC_B_BYTES / 2) <= TC_STAGES * TC_STAGE
 
 struct TcModel {
     int P = 1;
+    // operand format: bf16 terms (8 significant bits each), or fp16 terms (11 bits each; ISB_PREC_FP16X*): the
+    // couplings are then pre-scaled by the power of two `wscale` (max |W| -> [2^13, 2^14)) so that the residual term
+    // stays in fp16's normal range, and the epilogue multiplies the accumulators by 1 / wscale (exact).
+    bool f16 = false;
+    double wscale = 1.0;
     int ldkv = 0, ldkh = 0;            // K pitch (elements) of the two operand orientations
     __nv_bfloat16 *Wt[3] = {};         // hidden update operand: [nh][ldkv]  (K = visible units)
     __nv_bfloat16 *Wn[3] = {};         // visible update operand: [nv][ldkh] (K = hidden units)
@@ -117,6 +123,8 @@ struct TcParams {
     // after every round (one proxy fence each), the earlier tiles once at their end.
     int sig_gpt[2], sig_fine;
     int r_off;               // global replica index of row 0 (a run may hold a slice of the replicas): Philox only
+    uint32_t f16;            // operands are fp16 terms (selects the F16 instantiation), else bf16
+    float acc_scale;         // accumulator -> field: 1 / (power-of-two pre-scale of the fp16 couplings), 1 for bf16
     int64_t nsteps, k0;      // steps of the whole run (fluctuation array pitch), first step of this launch
     const double *Tsched;
     const double *tscale;    // per-replica temperature factors [R] or NULL
@@ -299,9 +307,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem_tile) {
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = m (128, or 256 for a CTA pair), N = bn
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int bn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32 (bit 4), A / B format at bits 7 / 10 (0 = fp16, 1 = bf16), both K-major,
+// M = m (128, or 256 for a CTA pair), N = bn
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int bn, uint32_t f16) {
+    const uint32_t fmt = f16 ? 0u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -344,8 +354,11 @@ struct TcMaps {
     CUtensorMap B[2][3];  // coupling terms of the two orientations
 };
 
-template <bool EXTF, int CG>
+// F16: the operands are fp16 terms of the pre-scaled couplings (ISB_PREC_FP16X*) instead of bf16 terms; a template
+// parameter, so that the bf16 instantiations keep their code (and registers) exactly.
+template <bool EXTF, int CG, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+    constexpr uint32_t ONE2 = F16 ? 0x3C003C00u : 0x3F803F80u;  // two packed +1 of the operand format
     constexpr int NST = CG == 2 ? TC_STAGES2 : TC_STAGES;     // ring slots
     constexpr int STB = TC_A_BYTES + TC_B_BYTES / CG;         // bytes per slot
     extern __shared__ unsigned char smem_dyn[];
@@ -481,7 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             while (jobs.next(p, job)) {
                 const TcLayer &L = p.L[job.layer];
-                const uint32_t idesc = umma_idesc_bf16(TC_BM * CG, L.bn);
+                const uint32_t idesc = umma_idesc_bf16(TC_BM * CG, L.bn, F16 ? 1u : 0u);
 #ifdef ISB_TC_PROBE_K1
                 const int iters = p.P;
 #else
@@ -578,11 +591,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                     blk[q] = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), pc2, pc3 + (uint32_t)(c * 4 + q), keys);
                 uint32_t wb[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) wb[j] = 0x3F803F80u;
+                for (int j = 0; j < 8; ++j) wb[j] = ONE2;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float wf = (float)philox_pick(blk[j >> 2], (uint32_t)(j & 3));
-                    const float x = __uint_as_float(v[j]) + bf[j];
+                    const float x = F16 ? fmaf(__uint_as_float(v[j]), p.acc_scale, bf[j]) : __uint_as_float(v[j]) + bf[j];
                     if (fmaf(wf, ex2_approx(cE * x), wf) > 4294967296.0f) wb[j >> 1] |= 0x8000u << (16 * (j & 1));
                 }
                 if (row_ok) {
@@ -613,9 +626,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                         oldw[4 * q] = o.x; oldw[4 * q + 1] = o.y; oldw[4 * q + 2] = o.z; oldw[4 * q + 3] = o.w;
                     }
                 }
-                uint32_t wb[CW / 2];  // packed bf16 +-1 = 0x3F80 | sign
+                uint32_t wb[CW / 2];  // packed +-1 of the operand format = (0x3F80 | 0x3C00) | sign
 #pragma unroll
-                for (int j = 0; j < CW / 2; ++j) wb[j] = 0x3F803F80u;
+                for (int j = 0; j < CW / 2; ++j) wb[j] = ONE2;
                 if (EXTF) {
 #pragma unroll
                     for (int j = 0; j < CW; ++j) {
@@ -626,7 +639,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                                                                                : L.F[((int64_t)r * p.nsteps + job.k) * L.nout + u];
                             double ft = __dmul_rn(f, Td);
                             if (p.rule == ISB_BIP_MA) ft = ((oldw[j >> 1] >> (16 * (j & 1) + 15)) & 1u) ? -ft : ft;
-                            x = __dsub_rn(__dmul_rn(2.0, __dadd_rn((double)__uint_as_float(v[j]), L.bias[u])), ft);
+                            // (the accumulator times a power of two is exact)
+                            const float accf = F16 ? __uint_as_float(v[j]) * p.acc_scale : __uint_as_float(v[j]);
+                            x = __dsub_rn(__dmul_rn(2.0, __dadd_rn((double)accf, L.bias[u])), ft);
                         }
                         if (x < 0.0) wb[j >> 1] |= 0x8000u << (16 * (j & 1));
                     }
@@ -661,7 +676,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                         for (int e = 0; e < 4; ++e) {
                             const int j = q * 4 + e;
                             const uint32_t w = philox_pick(blk[q], (uint32_t)e);
-                            const float x = __uint_as_float(v[j]) + bf[j];
+                            const float x = F16 ? fmaf(__uint_as_float(v[j]), p.acc_scale, bf[j]) : __uint_as_float(v[j]) + bf[j];
                             const float u = fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (w+1/2) 2^-32
                             float t;
                             if (Tf == 0.f) {
@@ -743,7 +758,7 @@ static int make_float_bias(isb_ctx *ctx, const double *d_b, int n, float **out) 
     return ISB_OK;
 }
 
-// bf16 +-1 operand matrix -> canonical int8 spins
+// bf16 / fp16 +-1 operand matrix -> canonical int8 spins (the sign bit is bit 15 in both formats)
 __global__ void bf16_to_spins_kernel(const __nv_bfloat16 *b, int64_t ldb, int8_t *s, int64_t lds, int n, int R) {
     const int64_t total = (int64_t)R * n;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -753,14 +768,15 @@ __global__ void bf16_to_spins_kernel(const __nv_bfloat16 *b, int64_t ldb, int8_t
     }
 }
 
-// int8 +-1 -> bf16 +-1 operand matrix (pad columns zero)
-__global__ void spins_to_bf16_kernel(const int8_t *s, int64_t lds, __nv_bfloat16 *o, int64_t ldo, int n, int R) {
+// int8 +-1 -> +-1 operand matrix in bf16 (one = 0x3F80) or fp16 (one = 0x3C00), pad columns zero
+__global__ void spins_to_bf16_kernel(const int8_t *s, int64_t lds, __nv_bfloat16 *o, int64_t ldo, int n, int R,
+                                     unsigned short one) {
     const int64_t total = (int64_t)R * ldo;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = idx / ldo;
         const int u = (int)(idx % ldo);
         unsigned short v = 0;
-        if (u < n) v = s[r * lds + u] > 0 ? 0x3F80 : 0xBF80;
+        if (u < n) v = s[r * lds + u] > 0 ? one : (unsigned short)(one | 0x8000u);
         o[idx] = __ushort_as_bfloat16(v);
     }
 }
@@ -814,6 +830,15 @@ static int make_map(isb_ctx *ctx, CUtensorMap *map, const void *base, int rows, 
     return ISB_OK;
 }
 
+// fp16 term of x (round to nearest even) and its exact value
+static unsigned short fp16_rne(double x, double *back) {
+    const __half h = __double2half(x);
+    *back = (double)__half2float(h);
+    unsigned short bits;
+    memcpy(&bits, &h, 2);
+    return bits;
+}
+
 static unsigned short bf16_rne(double x, double *back) {
     float f = (float)x;
     uint32_t u;
@@ -864,8 +889,18 @@ int bip_tc_model_init(isb_model *m, const double *W /*[nv][nh] row-major*/) {
     isb_ctx *ctx = m->ctx;
     TcModel *t = new TcModel();
     m->tc = t;
-    t->P = m->prec == ISB_PREC_BF16X3 ? 3 : (m->prec == ISB_PREC_BF16X2 ? 2 : 1);
+    t->P = m->prec == ISB_PREC_BF16X3 ? 3 : ((m->prec == ISB_PREC_BF16X2 || m->prec == ISB_PREC_FP16X2) ? 2 : 1);
+    t->f16 = m->prec == ISB_PREC_FP16X2 || m->prec == ISB_PREC_FP16X1;
     const int nv = m->nv, nh = m->nh;
+    if (t->f16) {
+        double amax = 0.0;
+        for (size_t i = 0; i < (size_t)nv * nh; ++i) amax = std::max(amax, fabs(W[i]));
+        if (amax > 0.0) {
+            int e;
+            frexp(amax, &e);                 // amax = f 2^e, f in [0.5, 1)
+            t->wscale = ldexp(1.0, 14 - e);  // amax * wscale in [2^13, 2^14): far below fp16's 65504
+        }
+    }
     t->ldkv = tc_pitch(nv);
     t->ldkh = tc_pitch(nh);
     t->bn_h = pick_bn(nh);
@@ -873,14 +908,14 @@ int bip_tc_model_init(isb_model *m, const double *W /*[nv][nh] row-major*/) {
     t->rows_t = nh; t->cols_t = nv; t->rows_n = nv; t->cols_n = nh;
     std::vector<unsigned short> wt((size_t)nh * t->ldkv), wn((size_t)nv * t->ldkh);
     std::vector<double> res((size_t)nv * nh);
-    for (size_t i = 0; i < res.size(); ++i) res[i] = W[i];
+    for (size_t i = 0; i < res.size(); ++i) res[i] = W[i] * t->wscale;  // a power of two: exact
     for (int term = 0; term < t->P; ++term) {
         std::fill(wt.begin(), wt.end(), 0);
         std::fill(wn.begin(), wn.end(), 0);
         for (int i = 0; i < nv; ++i)
             for (int j = 0; j < nh; ++j) {
                 double back;
-                const unsigned short hbits = bf16_rne(res[(size_t)i * nh + j], &back);
+                const unsigned short hbits = t->f16 ? fp16_rne(res[(size_t)i * nh + j], &back) : bf16_rne(res[(size_t)i * nh + j], &back);
                 res[(size_t)i * nh + j] -= back;
                 wt[(size_t)j * t->ldkv + i] = hbits;
                 wn[(size_t)i * t->ldkh + j] = hbits;
@@ -993,9 +1028,9 @@ static int tc_cta_group() {
     return cg;
 }
 
-template <bool EXTF, int CG>
+template <bool EXTF, int CG, bool F16>
 static int launch_tc_inst(isb_ctx *ctx, const TcMaps &maps, const TcParams &p, int grid) {
-    ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<EXTF, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<EXTF, CG, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(TC_THREADS);
@@ -1008,14 +1043,18 @@ static int launch_tc_inst(isb_ctx *ctx, const TcMaps &maps, const TcParams &p, i
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CG > 1 ? 1 : 0;
-    ISB_CUDA(ctx, cudaLaunchKernelEx(&cfg, bip_tc_kernel<EXTF, CG>, maps, p));
+    ISB_CUDA(ctx, cudaLaunchKernelEx(&cfg, bip_tc_kernel<EXTF, CG, F16>, maps, p));
     return ISB_OK;
 }
 
 // grid = CTAs (a multiple of p.cg)
 static int launch_tc(isb_ctx *ctx, const TcMaps &maps, const TcParams &p, int grid, bool extf) {
-    if (p.cg == 2) return extf ? launch_tc_inst<true, 2>(ctx, maps, p, grid) : launch_tc_inst<false, 2>(ctx, maps, p, grid);
-    return extf ? launch_tc_inst<true, 1>(ctx, maps, p, grid) : launch_tc_inst<false, 1>(ctx, maps, p, grid);
+    if (p.f16) {
+        if (p.cg == 2) return extf ? launch_tc_inst<true, 2, true>(ctx, maps, p, grid) : launch_tc_inst<false, 2, true>(ctx, maps, p, grid);
+        return extf ? launch_tc_inst<true, 1, true>(ctx, maps, p, grid) : launch_tc_inst<false, 1, true>(ctx, maps, p, grid);
+    }
+    if (p.cg == 2) return extf ? launch_tc_inst<true, 2, false>(ctx, maps, p, grid) : launch_tc_inst<false, 2, false>(ctx, maps, p, grid);
+    return extf ? launch_tc_inst<true, 1, false>(ctx, maps, p, grid) : launch_tc_inst<false, 1, false>(ctx, maps, p, grid);
 }
 
 // Steps [k0, k0 + nseg) of a run: one chain-resident launch when the replicas fill the SMs, else 2 * nseg
@@ -1058,6 +1097,8 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     p.tscale = e->d_tscale;
     p.steps_per_T = steps_per_T;
     p.seed = seed;
+    p.f16 = t->f16 ? 1u : 0u;
+    p.acc_scale = (float)(1.0 / t->wscale);
     p.m_tiles = m_tiles;
     for (int l = 0; l < 2; ++l) {
         p.sig_gpt[l] = (p.L[l].bn + TC_GW - 1) / TC_GW;
@@ -1206,6 +1247,8 @@ int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, in
     p.rule = rule;
     p.fluct_mode = ISB_FLUCT_PHILOX;
     p.Tsched = nullptr;
+    p.f16 = 0u;  // row-sharded models ship bf16 terms only
+    p.acc_scale = 1.0f;
     p.T_direct = T;
     p.steps_per_T = 1;
     p.seed = seed;
@@ -1227,8 +1270,9 @@ int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, cons
     TcEns *s = (TcEns *)e->tc;
     // the canonical int8 visible layer is the input of the first half-step; the hidden bf16 matrix is
     // produced by it (MomentumAnnealing reads the hidden layer's previous value from the int8 array)
-    spins_to_bf16_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(e->spins, e->lds, s->Sv, t->ldkv, m->nv, e->R);
-    spins_to_bf16_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(e->hidden, e->ldh, s->Sh, t->ldkh, m->nh, e->R);
+    const unsigned short one = t->f16 ? 0x3C00 : 0x3F80;
+    spins_to_bf16_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(e->spins, e->lds, s->Sv, t->ldkv, m->nv, e->R, one);
+    spins_to_bf16_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(e->hidden, e->ldh, s->Sh, t->ldkh, m->nh, e->R, one);
     ISB_CUDA(ctx, cudaGetLastError());
     e->last_launches += 2;
     auto sync_canonical = [&]() -> int {  // bf16 operand matrices -> the ensemble's int8 spins

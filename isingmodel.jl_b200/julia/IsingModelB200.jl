@@ -25,6 +25,7 @@ const BIP_SCA, BIP_MA = Cint(0), Cint(1)
 const ORDER_SEQUENTIAL, ORDER_LIST, ORDER_RANDOM = Cint(0), Cint(1), Cint(2)
 const FLUCT_PHILOX, FLUCT_SHARED, FLUCT_PER_REPLICA = Cint(0), Cint(1), Cint(2)
 const PREC_F64, PREC_F32, PREC_AUTO, PREC_BF16X3, PREC_BF16X1, PREC_BF16X2 = Cint(0), Cint(1), Cint(2), Cint(3), Cint(4), Cint(5)
+const PREC_FP16X2, PREC_FP16X1 = Cint(6), Cint(7)
 
 lasterror(ctx) = unsafe_string(ccall((:isb_last_error, libisb), Cstring, (Ctx,), ctx))
 check(rc, ctx) = rc == 0 ? nothing : error(lasterror(ctx))

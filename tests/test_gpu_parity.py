@@ -419,6 +419,55 @@ def test_bip_tc_philox_matches_f64_path(ctx, synth):
     assert abs(a.mean() - c.mean()) < 4 * a.std() / np.sqrt(R)
 
 
+def test_bip_tc_fp16_terms(ctx, synth, monkeypatch):
+    """ISB_PREC_FP16X2 / _FP16X1: fp16 terms of the power-of-two pre-scaled couplings.  Integer W is exact in one fp16
+    term, so the trajectory must equal the Float64 path's bit for bit (T = 0 and caller-supplied noise, single CTAs
+    and pairs, both launch modes); for Gaussian W the two-term split represents W to 2^-24 of max|W| (as good as W
+    rounded to float), so with the same noise words almost every chain follows the Float64 trajectory, exactly as
+    with three bf16 terms."""
+    L = _lib()
+    nv, nh, R = 192, 128, 512
+    W = np.round(synth.gaussian(121, nv * nh).reshape(nv, nh) * 1.5)
+    h, b = np.round(synth.gaussian(122, nv)), np.round(synth.gaussian(123, nh))
+    S0, T0 = synth.spins(124, R, nv), synth.spins(125, R, nh)
+    Fv, Fh = synth.logistic(126, (3, nv), 1), synth.logistic(126, (3, nh), 2)
+    ref = {}
+    for kw_name, kw in (("T0", dict(seed=5, T=np.zeros(3))), ("ext", dict(Fv=Fv, Fh=Fh, T=np.array([2.0, 1.0, 0.5])))):
+        e = L.Ensemble(L.Model.bipartite(ctx, W, h, b, L.PREC_F64), R)
+        e.set_spins(S0)
+        e.set_hidden(T0)
+        e.bip_run(0, 3, **kw)
+        ref[kw_name] = (e.get_spins(), e.get_hidden())
+        for prec in (L.PREC_FP16X1, L.PREC_FP16X2):
+            for cg, persist in (("1", "0"), ("2", "0"), ("2", "1")):
+                monkeypatch.setenv("ISB_TC_CG", cg)
+                monkeypatch.setenv("ISB_TC_PERSIST", persist)
+                e = L.Ensemble(L.Model.bipartite(ctx, W, h, b, prec), R)
+                e.set_spins(S0)
+                e.set_hidden(T0)
+                e.bip_run(0, 3, **kw)
+                assert np.array_equal(e.get_spins(), ref[kw_name][0]), (kw_name, prec, cg, persist)
+                assert np.array_equal(e.get_hidden(), ref[kw_name][1]), (kw_name, prec, cg, persist)
+    monkeypatch.delenv("ISB_TC_CG")
+    monkeypatch.delenv("ISB_TC_PERSIST")
+    W, h, b = synth.bipartite_W(nv, nh, 127, 0.1)
+    En = {}
+    for prec in (L.PREC_F64, L.PREC_FP16X2, L.PREC_BF16X3):
+        e = L.Ensemble(L.Model.bipartite(ctx, W, h, b, prec), R)
+        e.set_spins(S0)
+        e.set_hidden(T0)
+        e.bip_run(0, 30, seed=6, T=np.full(30, 1.0))
+        En[prec] = e.energy()
+    a = En[L.PREC_F64]
+    for prec in (L.PREC_FP16X2, L.PREC_BF16X3):
+        c = En[prec]
+        assert np.mean(np.abs(a - c) < 1e-9 * np.maximum(1, np.abs(a))) > 0.9, prec
+        assert abs(a.mean() - c.mean()) < 4 * a.std() / np.sqrt(R)
+    # a row-sharded model ships bf16 terms only
+    with pytest.raises(L.IsbError):
+        L.Model.shard_sk(ctx, 256, 2, 0, 1, 1.0, prec=L.PREC_FP16X2)
+
+
 @pytest.mark.parametrize("R,nv,nh", [(300, 160, 96), (19500, 96, 80), (1000, 784, 512)])
 def test_bip_tc_chain_resident_equals_per_half_step_launches(ctx, synth, monkeypatch, R, nv, nh):
     """The chain-resident persistent kernel (one launch for all steps, each CTA keeps its replicas) must give
