@@ -157,3 +157,27 @@ def test_ctypes_signatures_match_the_header(pkg):
                 assert ck.startswith("ptr:"), f"{name}: argument {pos + 1} is a pointer in _lib.py but {ck} in the header"
         want = {"int": C.c_int, "int64_t": C.c_int64, "void": None, "const char *": C.c_char_p}[c_ret]
         assert res is want, f"{name}: return type"
+
+
+def test_enum_values_agree_across_the_layers():
+    """The enums of include/ising_b200.h against the constants of the Python mirror and of the Julia shim."""
+    from isingmodel_jl_b200 import _lib
+    txt = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    enums = {k: int(v) for k, v in re.findall(r"\b(ISB_[A-Z0-9_]+)\s*=\s*(\d+)", txt)}
+    assert len(enums) >= 25
+    for name, val in enums.items():
+        py = name[len("ISB_"):]
+        if hasattr(_lib, py):
+            assert getattr(_lib, py) == val, name
+    for group in ("PREC_", "RULE_", "BIP_", "ORDER_", "FLUCT_"):
+        names = [n for n in enums if n.startswith("ISB_" + group)]
+        assert names, group
+        for n in names:
+            assert hasattr(_lib, n[4:]), f"{n} has no constant in _lib.py"
+    jl = open(SHIM).read()
+    for m in re.finditer(r"const ([A-Z0-9_, ]+?) = ((?:Cint\(\d+\)(?:, )?)+)", jl):
+        names = [n.strip() for n in m.group(1).split(",")]
+        vals = [int(v) for v in re.findall(r"Cint\((\d+)\)", m.group(2))]
+        assert len(names) == len(vals)
+        for n, v in zip(names, vals):
+            assert enums.get("ISB_" + n) == v, f"IsingModelB200.jl: {n} = {v}, the header says {enums.get('ISB_' + n)}"
