@@ -47,7 +47,7 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KiB
 constexpr int TC_B_BYTES = TC_BN_MAX * TC_BK * 2;      // 32 KiB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 #ifndef ISB_TC_EPI_WARPS
-#define ISB_TC_EPI_WARPS 16
+#define ISB_TC_EPI_WARPS 12
 #endif
 #ifndef ISB_TC_CW
 #define ISB_TC_CW 16

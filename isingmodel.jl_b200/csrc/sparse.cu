@@ -53,17 +53,10 @@ struct SpParams {
     unsigned long long *flips, *near_ties;
     double tie_eps;
     int chains_per_cta;
-    PhiloxKeys keys;  // round keys of `seed` (prefetch variant)
 };
 
-// PF > 0 (sequential order, every row has at most PF stored neighbours; opt-in with ISB_SPARSE_PREFETCH=1 until it has
-// been measured): each lane fetches the CSR row of ITS site of the 32-site window into registers before the
-// speculation loop, and an accepted flip broadcasts the flipping lane's row with shuffles — the loop then holds no
-// dependent global loads (rowptr -> col / val -> shared memory was an L2 round trip chain per accepted flip); the
-// window's temperature comes from a running (entry, offset) pair instead of a 64-bit division per lane.
-template <bool LIST, int PF = 0>
+template <bool LIST>
 __global__ void ssf_sparse_kernel(const SpParams p) {
-    static_assert(PF == 0 || !LIST, "the prefetch variant walks the sites in order");
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * p.chains_per_cta + warp;
@@ -118,96 +111,7 @@ __global__ void ssf_sparse_kernel(const SpParams p) {
     };
     int64_t next_trace = p.trace_every > 0 ? p.trace_every : INT64_MAX, trace_idx = 0;
 
-    if constexpr (!LIST && PF > 0) {
-        int64_t t = 0;
-        int site = p.start;
-        const uint64_t spT = (uint64_t)p.steps_per_T;
-        uint64_t ti = 0, tr = 0;  // t = ti * spT + tr
-        while (t < p.nsteps) {
-            int len = 32;
-            if (p.n - site < len) len = p.n - site;
-            if (p.nsteps - t < len) len = (int)(p.nsteps - t);
-            if (next_trace - t < len) len = (int)(next_trace - t);
-            const bool mine = lane < len;
-            const int64_t tl = t + lane;
-            const int i = site + (mine ? lane : 0);
-            // my site's stored neighbours (at most PF of them), fetched before anything depends on them
-            const int ra = __ldg(&p.rowptr[i]);
-            const int deg = __ldg(&p.rowptr[i + 1]) - ra;
-            int pc[PF];
-            double pv[PF];
-#pragma unroll
-            for (int e = 0; e < PF; ++e) {
-                const bool ok = e < deg;
-                pc[e] = ok ? __ldg(&p.col[ra + e]) : 0;
-                pv[e] = ok ? __ldg(&p.val[ra + e]) : 0.0;
-            }
-            double Tl = 0.0;
-            if (tr + (uint64_t)(len - 1) < spT) {
-                Tl = __dmul_rn(__ldg(&p.Tsched[ti]), tsc);
-            } else if (mine) {
-                Tl = __dmul_rn(__ldg(&p.Tsched[ti + (tr + (uint64_t)lane) / spT]), tsc);
-            }
-            double f = 0.0;
-            if (mine && rule != 0) {
-                if (p.fluct_mode == ISB_FLUCT_PHILOX)
-                    f = ssf_fluct_from_word(rule, philox_step_word_k(p.keys, DOM_SSF_FLUCT, (uint32_t)r, p.step_offset + (uint64_t)tl));
-                else
-                    f = p.fluct_mode == ISB_FLUCT_SHARED ? __ldg(&p.fluct[tl]) : __ldg(&p.fluct[(int64_t)r * p.nsteps + tl]);
-            }
-            const double ftl = __dmul_rn(f, mine ? Tl : 0.0);
-            bool mybit = sp[i] > 0;
-            uint32_t rem = __ballot_sync(FULL, mine);
-            while (true) {
-                const double h2 = 2.0 * fld[i];
-                const double fts = metro ? (mybit ? ftl : -ftl) : ftl;
-                const double x = __dsub_rn(h2, fts);
-                const bool nb = !(x < 0.0);
-                const uint32_t fm = __ballot_sync(FULL, nb != mybit) & rem;
-                if (audit) {
-                    const uint32_t tm = __ballot_sync(FULL, fabs(x) < p.tie_eps) & rem;
-                    nties += __popc(fm ? (tm & ((2u << (__ffs(fm) - 1)) - 1u)) : tm);
-                }
-                if (fm == 0) break;
-                const int l0 = __ffs(fm) - 1;
-                const bool up = (__ballot_sync(FULL, nb) >> l0) & 1u;
-                {   // fld[j] += d * J[i0][j] over the neighbours of the flipping lane's site: lane e takes neighbour e
-                    const double d = up ? 2.0 : -2.0;
-                    const int dg = __shfl_sync(FULL, deg, l0);
-                    int c = 0;
-                    double v = 0.0;
-#pragma unroll
-                    for (int e = 0; e < PF; ++e) {
-                        const int ce = __shfl_sync(FULL, pc[e], l0);
-                        const double ve = __shfl_sync(FULL, pv[e], l0);
-                        if (lane == e) {
-                            c = ce;
-                            v = ve;
-                        }
-                    }
-                    if (lane < dg) fld[c] += d * v;
-                    if (lane == 0) sp[site + l0] = up ? (int8_t)1 : (int8_t)-1;
-                    __syncwarp();
-                }
-                if (lane == l0) mybit = up;
-                ++nflips;
-                rem &= ~((2u << l0) - 1u);
-                if (rem == 0) break;
-            }
-            t += len;
-            site += len;
-            if (site >= p.n) site = 0;
-            tr += (uint64_t)len;
-            if (tr >= spT) {
-                ti += tr / spT;
-                tr %= spT;
-            }
-            if (t == next_trace) {
-                write_trace(trace_idx++);
-                next_trace += p.trace_every;
-            }
-        }
-    } else if constexpr (!LIST) {
+    if constexpr (!LIST) {
         int64_t t = 0;
         int site = p.start;
         while (t < p.nsteps) {
@@ -438,17 +342,10 @@ int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const
     p.out_E = d_E; p.out_M = d_M; p.out_S = d_S; p.ldS = m->n; p.flips = e->d_flips; p.near_ties = e->d_counters; p.tie_eps = e->tie_eps;
     p.chains_per_cta = chains;
     const size_t smem = per_chain * chains;
-    p.keys = philox_keys(seed);
-    constexpr int SP_PF = 8;  // neighbours per site the prefetch variant keeps in registers
-    const char *env_pf = getenv("ISB_SPARSE_PREFETCH");
-    const bool prefetch = env_pf && atoi(env_pf) != 0 && sm->maxdeg <= SP_PF;
     cudaError_t ce;
     if (order != ISB_ORDER_SEQUENTIAL) {
         ce = cudaFuncSetAttribute(ssf_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce == cudaSuccess) ssf_sparse_kernel<true><<<grid, 32 * chains, smem, ctx->stream>>>(p);
-    } else if (prefetch) {
-        ce = cudaFuncSetAttribute(ssf_sparse_kernel<false, SP_PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (ce == cudaSuccess) ssf_sparse_kernel<false, SP_PF><<<grid, 32 * chains, smem, ctx->stream>>>(p);
     } else {
         ce = cudaFuncSetAttribute(ssf_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce == cudaSuccess) ssf_sparse_kernel<false><<<grid, 32 * chains, smem, ctx->stream>>>(p);

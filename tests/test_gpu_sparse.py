@@ -253,41 +253,3 @@ def test_configuration_histogram(pkg, ctx, synth):
     tv = 0.5 * np.abs(hist / hist.sum() - p).sum()
     assert tv < 0.05, tv
     assert 0.5 * np.abs(1 / 512 - p).sum() > 0.2       # the target is far from uniform, so the bound above is a real check
-
-
-@pytest.mark.skipif(__import__("os").environ.get("ISB_TEST_UNVERIFIED") != "1",
-                    reason="ISB_SPARSE_PREFETCH=1 (register-prefetched CSR rows) is opt-in and has not run on hardware yet: "
-                           "set ISB_TEST_UNVERIFIED=1 to check it against the default kernel")
-@pytest.mark.parametrize("kind,rule,seeded", [("lattice", 2, True), ("lattice", 1, False), ("random8", 1, True),
-                                              ("random8", 2, False), ("random8", 0, False)])
-def test_sparse_prefetch_variant_equals_default(ctx, synth, monkeypatch, kind, rule, seeded):
-    """The opt-in prefetch variant of the sparse sweep kernel (each lane keeps its site's CSR row in registers, an
-    accepted flip broadcasts it with shuffles) must reproduce the default kernel bit for bit: spins, flip counts,
-    traces; in-kernel Philox noise and caller-supplied fluctuations; a window that straddles a schedule entry."""
-    import scipy.sparse as sp
-    L = _lib()
-    if kind == "lattice":
-        n = 32 * 32
-        A = sp.csc_matrix(synth.lattice_J(32))
-    else:
-        n = 600
-        A = _random_sparse(synth, n, 2, 77, False)      # largest degree 7: within the 8 neighbours the variant keeps
-        assert np.diff(A.tocsr().indptr).max() <= 8
-    R, nsteps = 37, 3 * n + 19
-    h = synth.gaussian(5, n) * 0.2
-    S0 = synth.spins(6, R, n)
-    T = synth.geometric_schedule(2.5, 0.5, 7)
-    spT = (nsteps + 6) // 7          # not a multiple of 32: some windows straddle two schedule entries
-    fl = None
-    if not seeded and rule != 0:
-        fl = synth.logistic(8, (R, nsteps)) if rule == 1 else synth.exponential(8, (R, nsteps))
-    res = []
-    for pf in ("0", "1"):
-        monkeypatch.setenv("ISB_SPARSE_PREFETCH", pf)
-        e = L.Ensemble(L.Model.sparse(ctx, A, h), R)
-        e.set_spins(S0)
-        out = e.ssf_run(rule, nsteps, start=n // 3, fluct=fl, fluct_per_replica=fl is not None, seed=11, step_offset=5,
-                        T=T, steps_per_T=spT, trace_every=n)
-        res.append((e.get_spins(), out["flips"], out["E"], out["M"]))
-    for a, b in zip(res[0], res[1]):
-        assert np.array_equal(a, b)
