@@ -80,7 +80,16 @@ enum {
                             sign of the second term: 2^-24 of max|W| per coupling, i.e. W as good as rounded to
                             float) — the accuracy of _BF16X3 up to the fp32 accumulation, in two passes instead of
                             three.  Not for row-sharded models.                                                   */
-    ISB_PREC_FP16X1 = 7  /* one fp16 term (2^-12 of max|W|; exact when the scaled W is fp16-representable)          */
+    ISB_PREC_FP16X1 = 7, /* one fp16 term (2^-12 of max|W|; exact when the scaled W is fp16-representable)          */
+    ISB_PREC_I8X3 = 8,   /* bipartite tensor path, INT8 DIGIT PLANES: W is rounded once to a 24-bit fixed-point grid
+                            (quantum = a power of two, 2^-23 of the largest coupling; a square model's dominant diagonal —
+                            the pinning term of the MultiSpinFlip embedding — is kept apart, exactly, on the same grid)
+                            and contracted with tcgen05.mma.kind::i8 into int32 accumulators: the contraction itself is
+                            EXACT at any depth K, so with caller-supplied fluctuations the trajectories are bit-identical
+                            to the Float64 reference run on the grid couplings (isb_model_effective_couplings).  Three
+                            int8 passes cost 1.5 bf16 passes.  Also valid for row-sharded models.                        */
+    ISB_PREC_I8X2 = 9,   /* the same with a 16-bit grid (two planes: one bf16 pass equivalent)                             */
+    ISB_PREC_I8X4 = 10   /* the same with a 32-bit grid (four planes: two bf16 pass equivalents)                           */
 };
 
 /* ------------------------------------------------------------------ context */
@@ -110,6 +119,14 @@ int isb_model_sparse(isb_ctx *ctx, int n, const int64_t *colptr, const int32_t *
 int isb_model_bipartite(isb_ctx *ctx, int nv, int nh, const double *W, int64_t ld,
                         const double *h, const double *b, int prec, isb_model **out);
 void isb_model_destroy(isb_model *m);
+/* One more owner of the model (each owner calls isb_model_destroy once): lets a host object that is copied
+ * (`deepcopy(ss)`, test/runtests.jl:22-24,30-31) share the immutable device couplings with its copy. */
+int isb_model_retain(isb_model *m);
+/* The couplings exactly as the kernels of this model use them: W itself for ISB_PREC_F64, the sum of the stored
+ * bf16 / fp16 terms or int8 digit planes (plus the split diagonal) for the tensor path.  W is nv x nh column-major with
+ * leading dimension ld, like the constructor's argument.  What parity tests hand to the Float64 reference
+ * (src/OnBipartiteGraph.jl:30-43) when they compare trajectories of a reduced-storage model. */
+int isb_model_effective_couplings(isb_model *m, double *W, int64_t ld);
 int isb_model_num_visible(const isb_model *m);
 int isb_model_num_hidden(const isb_model *m); /* 0 for a general-graph model */
 
@@ -117,6 +134,9 @@ int isb_model_num_hidden(const isb_model *m); /* 0 for a general-graph model */
 int isb_ens_create(isb_model *m, int R, isb_ens **out);
 void isb_ens_destroy(isb_ens *e);
 int isb_ens_replicas(const isb_ens *e);
+/* An independent copy of the ensemble on the same model (spins, hidden layer, per-replica temperature factors; all
+ * copied device to device): what `deepcopy(ss)` of the host object maps to (test/runtests.jl:22-24,30-31). */
+int isb_ens_clone(isb_ens *src, isb_ens **out);
 /* spinConfiguration get/set: src/SpinSystems.jl:61-62,128-129 */
 int isb_ens_set_spins(isb_ens *e, const int8_t *s, int64_t ld);
 int isb_ens_get_spins(isb_ens *e, int8_t *s, int64_t ld);
@@ -220,12 +240,17 @@ int isb_philox_bip_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64
  *   full layer  : bf16 [n_blocks][R][nb]   (block-major, +1/-1)        — the K operand of a half-step
  *   own block   : bf16 [R][nb], one buffer per layer                    — what this rank samples (on entry it
  *                 holds the block's previous values, which MomentumAnnealing multiplies into the noise)
+ * (ISB_PREC_I8X* models: the same buffers hold int8 +1/-1 instead of bf16 — half the bytes to all-gather.)
  * Noise is the library's Philox stream indexed by GLOBAL (replica, step, unit), so the trajectory does not
  * depend on the number of blocks.
  */
 /* W rows given by the caller: Wrows is [nb][n] row-major (rows block*nb .. of the symmetric W). */
 int isb_shard_model_rows(isb_ctx *ctx, int n, int n_blocks, int block, const double *Wrows, const double *h_blk,
                          const double *b_blk, int prec, isb_model **out);
+/* The same for the int8 digit-plane formats, whose fixed-point grid must be identical on every rank: wmax = the
+ * largest off-diagonal |W| of the WHOLE matrix (<= 0: use this block's own maximum). */
+int isb_shard_model_rows_q(isb_ctx *ctx, int n, int n_blocks, int block, const double *Wrows, const double *h_blk,
+                           const double *b_blk, int prec, double wmax, isb_model **out);
 /* Synthetic SK instance generated on the device, never materialised in full: J_ij = J_ji ~ N(0, 1/n) from the
  * counter RNG (seed), W = (J + qI)/2, zero fields. */
 int isb_shard_model_sk(isb_ctx *ctx, int n, int n_blocks, int block, uint64_t seed, double q, int prec,

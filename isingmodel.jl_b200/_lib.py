@@ -22,6 +22,8 @@ BIP_SCA, BIP_MA = 0, 1
 ORDER_SEQUENTIAL, ORDER_LIST, ORDER_RANDOM = 0, 1, 2
 FLUCT_PHILOX, FLUCT_SHARED, FLUCT_PER_REPLICA = 0, 1, 2
 PREC_F64, PREC_F32, PREC_AUTO, PREC_BF16X3, PREC_BF16X1, PREC_BF16X2, PREC_FP16X2, PREC_FP16X1 = 0, 1, 2, 3, 4, 5, 6, 7
+PREC_I8X3, PREC_I8X2, PREC_I8X4 = 8, 9, 10
+I8_PRECS = (PREC_I8X3, PREC_I8X2, PREC_I8X4)
 
 _ERR_NAMES = {1: "ISB_ERR_ARG", 2: "ISB_ERR_SIZE", 3: "ISB_ERR_NONFINITE", 4: "ISB_ERR_CUDA",
               5: "ISB_ERR_UNSUPPORTED", 6: "ISB_ERR_NCCL", 7: "ISB_ERR_STATE"}
@@ -61,9 +63,12 @@ SIGNATURES = {
     "isb_model_sparse": (_i, [_vp, _i, _vp, _vp, _vp, _vp, C.POINTER(_i), C.POINTER(_vp)]),
     "isb_model_bipartite": (_i, [_vp, _i, _i, _vp, _i64, _vp, _vp, _i, C.POINTER(_vp)]),
     "isb_model_destroy": (None, [_vp]),
+    "isb_model_retain": (_i, [_vp]),
+    "isb_model_effective_couplings": (_i, [_vp, _vp, _i64]),
     "isb_model_num_visible": (_i, [_vp]),
     "isb_model_num_hidden": (_i, [_vp]),
     "isb_ens_create": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "isb_ens_clone": (_i, [_vp, C.POINTER(_vp)]),
     "isb_ens_destroy": (None, [_vp]),
     "isb_ens_replicas": (_i, [_vp]),
     "isb_ens_set_spins": (_i, [_vp, _vp, _i64]),
@@ -85,6 +90,7 @@ SIGNATURES = {
     "isb_bip_run_snap": (_i, [_vp, _i, _i64, _i, _vp, _vp, _u64, _u64, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _i64]),
     "isb_philox_bip_fluct": (_i, [_vp, _i, _i, _u64, _u64, _i, _i, _i, _i, _i64, _vp]),
     "isb_shard_model_rows": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
+    "isb_shard_model_rows_q": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _d, C.POINTER(_vp)]),
     "isb_shard_model_sk": (_i, [_vp, _i, _i, _i, _u64, _d, _i, C.POINTER(_vp)]),
     "isb_sk_rows": (_i, [_vp, _i, _u64, _i, _i, _vp]),
     "isb_model_shard_block": (_i, [_vp]),
@@ -249,15 +255,18 @@ class Model:
         return cls(ctx, m, "bipartite")
 
     @classmethod
-    def shard_rows(cls, ctx: Context, n, n_blocks, block, Wrows, h_blk=None, b_blk=None, prec=PREC_BF16X3):
-        """Row block `block` of a symmetric W (Wrows: [n // n_blocks][n]) — isb_shard_model_rows."""
+    def shard_rows(cls, ctx: Context, n, n_blocks, block, Wrows, h_blk=None, b_blk=None, prec=PREC_BF16X3, wmax=0.0):
+        """Row block `block` of a symmetric W (Wrows: [n // n_blocks][n]) — isb_shard_model_rows(_q).  wmax: the largest
+        off-diagonal |W| of the whole matrix (int8 digit planes: every rank must use the same fixed-point grid)."""
         A = np.ascontiguousarray(Wrows, dtype=np.float64)
         h_blk = None if h_blk is None else np.ascontiguousarray(h_blk, dtype=np.float64)
         b_blk = None if b_blk is None else np.ascontiguousarray(b_blk, dtype=np.float64)
         m = _vp()
-        check(load().isb_shard_model_rows(ctx.handle, int(n), int(n_blocks), int(block), ptr(A), ptr(h_blk),
-                                          ptr(b_blk), prec, C.byref(m)), ctx.handle)
-        return cls(ctx, m, "shard")
+        check(load().isb_shard_model_rows_q(ctx.handle, int(n), int(n_blocks), int(block), ptr(A), ptr(h_blk),
+                                            ptr(b_blk), prec, float(wmax), C.byref(m)), ctx.handle)
+        obj = cls(ctx, m, "shard")
+        obj.prec = prec
+        return obj
 
     @classmethod
     def shard_sk(cls, ctx: Context, n, n_blocks, block, seed, q, prec=PREC_BF16X3):
@@ -265,7 +274,9 @@ class Model:
         m = _vp()
         check(load().isb_shard_model_sk(ctx.handle, int(n), int(n_blocks), int(block), int(seed), float(q), prec,
                                         C.byref(m)), ctx.handle)
-        return cls(ctx, m, "shard")
+        obj = cls(ctx, m, "shard")
+        obj.prec = prec
+        return obj
 
     def shard_halfstep(self, R, layer, rule, in_full_ptr, out_block_ptr, seed, step_abs, T, replica_offset=0):
         """isb_shard_halfstep_dev with raw device pointers (ints)."""
@@ -279,6 +290,13 @@ class Model:
         check(load().isb_shard_halfstep_fused_dev(self.handle, int(R), int(replica_offset), int(layer), int(rule), _vp(in_full_ptr),
                                                   _vp(out_block_ptr), len(peer_ptrs), C.cast(arr, _vp), int(seed),
                                                   int(step_abs), float(T)), self.ctx.handle)
+
+    def effective_couplings(self):
+        """The couplings exactly as the kernels use them (isb_model_effective_couplings): [nv][nh]."""
+        nv, nh = self.num_visible, self.num_hidden
+        W = np.zeros((nv, nh), dtype=np.float64, order="F")
+        check(load().isb_model_effective_couplings(self.handle, ptr(W), max(1, nv)), self.ctx.handle)
+        return np.ascontiguousarray(W)
 
     @property
     def num_visible(self):
@@ -308,6 +326,14 @@ class Ensemble:
         check(load().isb_ens_create(model.handle, int(R), C.byref(e)), model.ctx.handle)
         self.model, self.handle, self.R = model, e, int(R)
         self.nv, self.nh = model.num_visible, model.num_hidden
+
+    def clone(self):
+        """isb_ens_clone: an independent device-side copy (deepcopy of the host object)."""
+        e = _vp()
+        check(load().isb_ens_clone(self.handle, C.byref(e)), self.model.ctx.handle)
+        new = object.__new__(Ensemble)
+        new.model, new.handle, new.R, new.nv, new.nh = self.model, e, self.R, self.nv, self.nh
+        return new
 
     def close(self):
         if self.handle:

@@ -12,7 +12,11 @@
 
 #include "handles.hpp"
 
+// Error texts are per THREAD (and remember which context they belong to): two threads that share a context, or use
+// two contexts, each read the message of their own last failed call.
 static thread_local std::string g_create_err = "";
+static thread_local std::string g_ctx_err = "";
+static thread_local const isb_ctx *g_ctx_err_owner = nullptr;
 
 namespace isb {
 
@@ -22,10 +26,12 @@ int fail(isb_ctx *ctx, int code, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (ctx)
-        ctx->err = buf;
-    else
+    if (ctx) {
+        g_ctx_err = buf;
+        g_ctx_err_owner = ctx;
+    } else {
         g_create_err = buf;
+    }
     return code;
 }
 
@@ -139,10 +145,14 @@ static void ctx_release(isb_ctx *ctx) {
 
 void isb_destroy(isb_ctx *ctx) { ctx_release(ctx); }
 
-const char *isb_last_error(const isb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+const char *isb_last_error(const isb_ctx *ctx) {
+    if (!ctx) return g_create_err.c_str();
+    return g_ctx_err_owner == ctx ? g_ctx_err.c_str() : "";
+}
 
 int isb_set_stream(isb_ctx *ctx, void *cuda_stream) {
     if (!ctx) return ISB_ERR_ARG;
+    ISB_LOCK(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -153,6 +163,7 @@ int isb_set_stream(isb_ctx *ctx, void *cuda_stream) {
 
 int isb_synchronize(isb_ctx *ctx) {
     if (!ctx) return ISB_ERR_ARG;
+    ISB_LOCK(ctx);
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ISB_OK;
@@ -168,6 +179,7 @@ static int next_pow2(int v) {
 int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const double *h, int prec, int *warn,
                     isb_model **out) {
     if (!ctx) return ISB_ERR_ARG;
+    ISB_LOCK(ctx);
     if (!out || !J) return fail(ctx, ISB_ERR_ARG, "isb_model_dense: NULL argument");
     *out = nullptr;
     if (warn) *warn = 0;
@@ -287,6 +299,7 @@ int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const doub
 int isb_model_sparse(isb_ctx *ctx, int n, const int64_t *colptr, const int32_t *rowval, const double *nzval,
                      const double *h, int *warn, isb_model **out) {
     if (!ctx) return ISB_ERR_ARG;
+    ISB_LOCK(ctx);
     if (!out || !colptr) return fail(ctx, ISB_ERR_ARG, "isb_model_sparse: NULL argument");
     *out = nullptr;
     if (warn) *warn = 0;
@@ -324,14 +337,15 @@ int isb_model_sparse(isb_ctx *ctx, int n, const int64_t *colptr, const int32_t *
 int isb_model_bipartite(isb_ctx *ctx, int nv, int nh, const double *W, int64_t ld, const double *h, const double *b,
                         int prec, isb_model **out) {
     if (!ctx) return ISB_ERR_ARG;
+    ISB_LOCK(ctx);
     if (!out || !W) return fail(ctx, ISB_ERR_ARG, "isb_model_bipartite: NULL argument");
     *out = nullptr;
     if (nv <= 0 || nh <= 0) return fail(ctx, ISB_ERR_SIZE, "isb_model_bipartite: nv = %d, nh = %d must be positive", nv, nh);
     if (ld < nv) return fail(ctx, ISB_ERR_SIZE, "isb_model_bipartite: leading dimension %lld < nv = %d", (long long)ld, nv);
     if (prec == ISB_PREC_AUTO) prec = ISB_PREC_F64;
     if (prec != ISB_PREC_F64 && prec != ISB_PREC_BF16X3 && prec != ISB_PREC_BF16X2 && prec != ISB_PREC_BF16X1 &&
-        prec != ISB_PREC_FP16X2 && prec != ISB_PREC_FP16X1)
-        return fail(ctx, ISB_ERR_ARG, "isb_model_bipartite: prec must be ISB_PREC_F64, _BF16X3, _BF16X2, _BF16X1, _FP16X2 or _FP16X1");
+        prec != ISB_PREC_FP16X2 && prec != ISB_PREC_FP16X1 && prec != ISB_PREC_I8X3 && prec != ISB_PREC_I8X2 && prec != ISB_PREC_I8X4)
+        return fail(ctx, ISB_ERR_ARG, "isb_model_bipartite: prec must be ISB_PREC_F64, _BF16X3, _BF16X2, _BF16X1, _FP16X2, _FP16X1, _I8X3, _I8X2 or _I8X4");
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<double> Wr((size_t)nv * nh), Wt((size_t)nv * nh), hn((size_t)nv, 0.0), bn((size_t)nh, 0.0);
     for (int j = 0; j < nh; ++j)
@@ -385,23 +399,44 @@ int isb_model_bipartite(isb_ctx *ctx, int nv, int nh, const double *W, int64_t l
 
 static void model_release(isb_model *m) {
     if (!m || m->refs.fetch_sub(1) != 1) return;
-    cudaSetDevice(m->ctx->device);
-    cudaStreamSynchronize(m->ctx->stream);
-    if (m->tc) isb::bip_tc_model_free(m);
-    if (m->sp) isb::sparse_model_free(m);
-    cudaFree(m->J64);
-    cudaFree(m->Jperm);
-    cudaFree(m->h64);
-    cudaFree(m->W64);
-    cudaFree(m->Wt64);
-    cudaFree(m->hb64);
-    cudaFree(m->bb64);
     isb_ctx *ctx = m->ctx;
-    delete m;
+    {
+        ISB_LOCK(ctx);
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (m->tc) isb::bip_tc_model_free(m);
+        if (m->sp) isb::sparse_model_free(m);
+        cudaFree(m->J64);
+        cudaFree(m->Jperm);
+        cudaFree(m->h64);
+        cudaFree(m->W64);
+        cudaFree(m->Wt64);
+        cudaFree(m->hb64);
+        cudaFree(m->bb64);
+        delete m;
+    }
     ctx_release(ctx);
 }
 
 void isb_model_destroy(isb_model *m) { model_release(m); }
+
+int isb_model_effective_couplings(isb_model *m, double *W, int64_t ld) {
+    if (!m) return ISB_ERR_ARG;
+    isb_ctx *ctx = m->ctx;
+    ISB_LOCK(ctx);
+    if (m->kind != ISB_KIND_BIPARTITE) return fail(ctx, ISB_ERR_STATE, "isb_model_effective_couplings: not a bipartite model");
+    if (!W) return fail(ctx, ISB_ERR_ARG, "isb_model_effective_couplings: W is NULL");
+    if (ld < m->nv) return fail(ctx, ISB_ERR_SIZE, "isb_model_effective_couplings: leading dimension %lld < nv = %d", (long long)ld, m->nv);
+    ISB_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<double> Wr((size_t)m->nv * m->nh);
+    if (m->tc)
+        ISB_TRY(isb::bip_tc_effective_couplings(m, Wr.data()));
+    else
+        ISB_CUDA(ctx, cudaMemcpy(Wr.data(), m->W64, Wr.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < m->nh; ++j)
+        for (int i = 0; i < m->nv; ++i) W[i + (int64_t)j * ld] = Wr[(size_t)i * m->nh + j];
+    return ISB_OK;
+}
 
 static bool general_graph(const isb_model *m) { return m->kind == ISB_KIND_DENSE || m->kind == ISB_KIND_SPARSE; }
 int isb_model_num_visible(const isb_model *m) { return !m ? 0 : (general_graph(m) ? m->n : m->nv); }
@@ -412,6 +447,7 @@ int isb_model_shard_block(const isb_model *m) { return !m ? 0 : m->shard_nb; }
 int isb_ens_create(isb_model *m, int R, isb_ens **out) {
     if (!m) return ISB_ERR_ARG;
     isb_ctx *ctx = m->ctx;
+    ISB_LOCK(ctx);
     if (!out) return fail(ctx, ISB_ERR_ARG, "isb_ens_create: out is NULL");
     *out = nullptr;
     if (R <= 0) return fail(ctx, ISB_ERR_SIZE, "isb_ens_create: R = %d must be positive", R);
@@ -459,24 +495,66 @@ int isb_ens_create(isb_model *m, int R, isb_ens **out) {
 
 void isb_ens_destroy(isb_ens *e) {
     if (!e) return;
-    cudaSetDevice(e->model->ctx->device);
-    cudaStreamSynchronize(e->model->ctx->stream);
-    if (e->tc) isb::bip_tc_ens_free(e);
-    cudaFree(e->spins);
-    cudaFree(e->hidden);
-    cudaFree(e->fields);
-    cudaFree(e->d_flips);
-    cudaFree(e->d_counters);
-    cudaFree(e->d_tscale);
     isb_model *m = e->model;
-    delete e;
+    {
+        ISB_LOCK(m->ctx);
+        cudaSetDevice(m->ctx->device);
+        cudaStreamSynchronize(m->ctx->stream);
+        if (e->tc) isb::bip_tc_ens_free(e);
+        cudaFree(e->spins);
+        cudaFree(e->hidden);
+        cudaFree(e->fields);
+        cudaFree(e->d_flips);
+        cudaFree(e->d_counters);
+        cudaFree(e->d_tscale);
+        delete e;
+    }
     model_release(m);
 }
 
 int isb_ens_replicas(const isb_ens *e) { return e ? e->R : 0; }
 
+int isb_model_retain(isb_model *m) {
+    if (!m) return ISB_ERR_ARG;
+    m->refs.fetch_add(1);
+    return ISB_OK;
+}
+
+int isb_ens_clone(isb_ens *src, isb_ens **out) {
+    if (!src) return ISB_ERR_ARG;
+    isb_ctx *ctx = src->model->ctx;
+    ISB_LOCK(ctx);
+    if (!out) return fail(ctx, ISB_ERR_ARG, "isb_ens_clone: out is NULL");
+    *out = nullptr;
+    isb_ens *e = nullptr;
+    ISB_TRY(isb_ens_create(src->model, src->R, &e));
+    cudaError_t ce = cudaSuccess;
+    if (e->lds != src->lds || e->ldh != src->ldh) {
+        isb_ens_destroy(e);
+        return fail(ctx, ISB_ERR_STATE, "isb_ens_clone: layout mismatch");
+    }
+    ce = cudaMemcpyAsync(e->spins, src->spins, (size_t)src->R * src->lds, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (ce == cudaSuccess && src->hidden)
+        ce = cudaMemcpyAsync(e->hidden, src->hidden, (size_t)src->R * src->ldh, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (ce == cudaSuccess && src->d_tscale) {
+        ce = cudaMalloc(&e->d_tscale, (size_t)src->R * sizeof(double));
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(e->d_tscale, src->d_tscale, (size_t)src->R * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) {
+        isb_ens_destroy(e);
+        return fail(ctx, ISB_ERR_CUDA, "isb_ens_clone: copy failed: %s", cudaGetErrorString(ce));
+    }
+    e->tie_eps = src->tie_eps;
+    e->fields_rule_sign = 0;  // the cached local fields are rebuilt from the copied spins by the next run
+    *out = e;
+    return ISB_OK;
+}
+
 static int copy_spins_in(isb_ens *e, int8_t *dst, int64_t ldd, int n, const int8_t *s, int64_t ld, const char *who) {
     isb_ctx *ctx = e->model->ctx;
+    ISB_LOCK(ctx);
     if (!s) return fail(ctx, ISB_ERR_ARG, "%s: NULL spin array", who);
     if (ld < n) return fail(ctx, ISB_ERR_SIZE, "%s: leading dimension %lld < %d units", who, (long long)ld, n);
     for (int r = 0; r < e->R; ++r) {
@@ -497,6 +575,7 @@ static int copy_spins_in(isb_ens *e, int8_t *dst, int64_t ldd, int n, const int8
 }
 static int copy_spins_out(isb_ens *e, const int8_t *src, int64_t lds, int n, int8_t *s, int64_t ld, const char *who) {
     isb_ctx *ctx = e->model->ctx;
+    ISB_LOCK(ctx);
     if (!s) return fail(ctx, ISB_ERR_ARG, "%s: NULL spin array", who);
     if (ld < n) return fail(ctx, ISB_ERR_SIZE, "%s: leading dimension %lld < %d units", who, (long long)ld, n);
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -530,6 +609,7 @@ int isb_ens_get_hidden(isb_ens *e, int8_t *t, int64_t ld) {
 int isb_ens_energy(isb_ens *e, double *E) {
     if (!e) return ISB_ERR_ARG;
     isb_ctx *ctx = e->model->ctx;
+    ISB_LOCK(ctx);
     if (!E) return fail(ctx, ISB_ERR_ARG, "isb_ens_energy: E is NULL");
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     double *dE;
@@ -545,6 +625,7 @@ int isb_ens_energy(isb_ens *e, double *E) {
 int isb_ens_magnetization(isb_ens *e, double *M) {
     if (!e) return ISB_ERR_ARG;
     isb_ctx *ctx = e->model->ctx;
+    ISB_LOCK(ctx);
     if (!M) return fail(ctx, ISB_ERR_ARG, "isb_ens_magnetization: M is NULL");
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     double *dM;
@@ -558,6 +639,7 @@ int isb_ens_magnetization(isb_ens *e, double *M) {
 static int field_common(isb_ens *e, int layer, double *F, int64_t ld, const char *who) {
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
+    ISB_LOCK(ctx);
     const int nout = general_graph(m) ? m->n : (layer == 0 ? m->nv : m->nh);
     if (!F) return fail(ctx, ISB_ERR_ARG, "%s: output is NULL", who);
     if (ld < nout) return fail(ctx, ISB_ERR_SIZE, "%s: leading dimension %lld < %d", who, (long long)ld, nout);
@@ -629,6 +711,7 @@ int isb_ssf_run_hist(isb_ens *e, int rule, int64_t nsteps, int order, const int3
                      int64_t steps_per_T, int64_t trace_every, int64_t *hist) {
     if (!e) return ISB_ERR_ARG;
     isb_ctx *ctx = e->model->ctx;
+    ISB_LOCK(ctx);
     if (!hist) return fail(ctx, ISB_ERR_ARG, "isb_ssf_run_hist: hist is NULL");
     if (general_graph(e->model) && e->model->n > 24)
         return fail(ctx, ISB_ERR_SIZE, "isb_ssf_run_hist: N = %d > 24 (the histogram has 2^N bins)", e->model->n);
@@ -644,6 +727,7 @@ static int ssf_run_impl(isb_ens *e, int rule, int64_t nsteps, int order, const i
     if (!e) return ISB_ERR_ARG;
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
+    ISB_LOCK(ctx);
     const char *who = "isb_ssf_run";
     if (!general_graph(m)) return fail(ctx, ISB_ERR_STATE, "%s: not a general-graph ensemble", who);
     if (rule < ISB_RULE_HOPFIELD || rule > ISB_RULE_METROPOLIS) return fail(ctx, ISB_ERR_ARG, "%s: unknown rule %d", who, rule);
@@ -760,6 +844,7 @@ int isb_philox_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64_t s
                      int64_t nsteps, double *out) {
     (void)prec;
     if (!ctx) return ISB_ERR_ARG;
+    ISB_LOCK(ctx);
     if (!out || nr < 0 || nsteps < 0 || r0 < 0) return fail(ctx, ISB_ERR_ARG, "isb_philox_fluct: bad argument");
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     double *d;
@@ -773,6 +858,7 @@ int isb_philox_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64_t s
 
 int isb_philox_nodes(isb_ctx *ctx, int n, uint64_t seed, uint64_t step_offset, int64_t nsteps, int32_t *out) {
     if (!ctx) return ISB_ERR_ARG;
+    ISB_LOCK(ctx);
     if (!out || n <= 0 || nsteps < 0) return fail(ctx, ISB_ERR_ARG, "isb_philox_nodes: bad argument");
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     int32_t *d;
@@ -785,6 +871,7 @@ int isb_philox_nodes(isb_ctx *ctx, int n, uint64_t seed, uint64_t step_offset, i
 
 int isb_philox_raw(isb_ctx *ctx, const uint32_t *ctr, const uint32_t key[2], int nblocks, uint32_t *out) {
     if (!ctx) return ISB_ERR_ARG;
+    ISB_LOCK(ctx);
     if (!ctr || !key || !out || nblocks < 0) return fail(ctx, ISB_ERR_ARG, "isb_philox_raw: bad argument");
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     uint32_t *dc, *dout;
@@ -811,6 +898,7 @@ int isb_bip_run_snap(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const
     if (!e) return ISB_ERR_ARG;
     isb_model *m = e->model;
     isb_ctx *ctx = m->ctx;
+    ISB_LOCK(ctx);
     const char *who = "isb_bip_run";
     if (m->kind != ISB_KIND_BIPARTITE) return fail(ctx, ISB_ERR_STATE, "%s: not a bipartite ensemble", who);
     if (rule != ISB_BIP_SCA && rule != ISB_BIP_MA) return fail(ctx, ISB_ERR_ARG, "%s: unknown rule %d", who, rule);
@@ -875,6 +963,7 @@ int isb_philox_bip_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64
                          int r0, int nr, int64_t nsteps, double *out) {
     (void)prec;
     if (!ctx) return ISB_ERR_ARG;
+    ISB_LOCK(ctx);
     if (!out || nr < 0 || nsteps < 0 || r0 < 0 || nunits <= 0 || (layer != 0 && layer != 1))
         return fail(ctx, ISB_ERR_ARG, "isb_philox_bip_fluct: bad argument");
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -890,16 +979,19 @@ int isb_philox_bip_fluct(isb_ctx *ctx, int rule, int prec, uint64_t seed, uint64
 
 // ------------------------------------------------------------------ row-sharded symmetric SCA (config 5)
 static int shard_model_common(isb_ctx *ctx, int n, int n_blocks, int block, const double *Wrows, const double *h_blk,
-                              const double *b_blk, uint64_t seed, double q, int prec, isb_model **out, const char *who) {
+                              const double *b_blk, uint64_t seed, double q, int prec, double wmax, isb_model **out, const char *who) {
     if (!ctx) return ISB_ERR_ARG;
+    ISB_LOCK(ctx);
     if (!out) return fail(ctx, ISB_ERR_ARG, "%s: out is NULL", who);
     *out = nullptr;
     if (n <= 0 || n_blocks <= 0 || block < 0 || block >= n_blocks || n % n_blocks != 0)
         return fail(ctx, ISB_ERR_SIZE, "%s: n = %d must split evenly into %d blocks (block %d)", who, n, n_blocks, block);
     const int nb = n / n_blocks;
-    if (nb % 64 != 0) return fail(ctx, ISB_ERR_UNSUPPORTED, "%s: block size %d must be a multiple of 64", who, nb);
-    if (prec != ISB_PREC_BF16X3 && prec != ISB_PREC_BF16X2 && prec != ISB_PREC_BF16X1)
-        return fail(ctx, ISB_ERR_ARG, "%s: prec must be ISB_PREC_BF16X3, _BF16X2 or _BF16X1", who);
+    const bool i8 = prec == ISB_PREC_I8X3 || prec == ISB_PREC_I8X2 || prec == ISB_PREC_I8X4;
+    if (nb % (i8 ? 128 : 64) != 0)
+        return fail(ctx, ISB_ERR_UNSUPPORTED, "%s: block size %d must be a multiple of %d", who, nb, i8 ? 128 : 64);
+    if (prec != ISB_PREC_BF16X3 && prec != ISB_PREC_BF16X2 && prec != ISB_PREC_BF16X1 && !i8)
+        return fail(ctx, ISB_ERR_ARG, "%s: prec must be ISB_PREC_BF16X3, _BF16X2, _BF16X1, _I8X3, _I8X2 or _I8X4", who);
     if (!std::isfinite(q)) return fail(ctx, ISB_ERR_NONFINITE, "%s: q is not finite", who);
     if (Wrows && !all_finite(Wrows, (size_t)nb * n)) return fail(ctx, ISB_ERR_NONFINITE, "%s: W is not finite", who);
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -921,7 +1013,7 @@ static int shard_model_common(isb_ctx *ctx, int n, int n_blocks, int block, cons
     if (!rc) {
         cudaMemcpy(m->hb64, hn.data(), nb * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(m->bb64, bn.data(), nb * sizeof(double), cudaMemcpyHostToDevice);
-        rc = isb::shard_model_init(m, Wrows, seed, q);
+        rc = isb::shard_model_init(m, Wrows, seed, q, wmax);
     }
     if (rc) {
         isb_model_destroy(m);
@@ -934,15 +1026,22 @@ static int shard_model_common(isb_ctx *ctx, int n, int n_blocks, int block, cons
 int isb_shard_model_rows(isb_ctx *ctx, int n, int n_blocks, int block, const double *Wrows, const double *h_blk,
                          const double *b_blk, int prec, isb_model **out) {
     if (ctx && !Wrows) return fail(ctx, ISB_ERR_ARG, "isb_shard_model_rows: W rows are NULL");
-    return shard_model_common(ctx, n, n_blocks, block, Wrows, h_blk, b_blk, 0, 0.0, prec, out, "isb_shard_model_rows");
+    return shard_model_common(ctx, n, n_blocks, block, Wrows, h_blk, b_blk, 0, 0.0, prec, 0.0, out, "isb_shard_model_rows");
+}
+
+int isb_shard_model_rows_q(isb_ctx *ctx, int n, int n_blocks, int block, const double *Wrows, const double *h_blk,
+                           const double *b_blk, int prec, double wmax, isb_model **out) {
+    if (ctx && !Wrows) return fail(ctx, ISB_ERR_ARG, "isb_shard_model_rows_q: W rows are NULL");
+    return shard_model_common(ctx, n, n_blocks, block, Wrows, h_blk, b_blk, 0, 0.0, prec, wmax, out, "isb_shard_model_rows_q");
 }
 
 int isb_shard_model_sk(isb_ctx *ctx, int n, int n_blocks, int block, uint64_t seed, double q, int prec, isb_model **out) {
-    return shard_model_common(ctx, n, n_blocks, block, nullptr, nullptr, nullptr, seed, q, prec, out, "isb_shard_model_sk");
+    return shard_model_common(ctx, n, n_blocks, block, nullptr, nullptr, nullptr, seed, q, prec, 0.0, out, "isb_shard_model_sk");
 }
 
 int isb_sk_rows(isb_ctx *ctx, int n, uint64_t seed, int row0, int nrows, double *out) {
     if (!ctx) return ISB_ERR_ARG;
+    ISB_LOCK(ctx);
     if (!out || n <= 0 || row0 < 0 || nrows < 0 || row0 + nrows > n) return fail(ctx, ISB_ERR_ARG, "isb_sk_rows: bad argument");
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     double *d;
@@ -965,6 +1064,7 @@ int isb_shard_halfstep_fused_dev(isb_model *m, int R, int replica_offset, int la
                                  uint64_t step_abs, double T) {
     if (!m) return ISB_ERR_ARG;
     isb_ctx *ctx = m->ctx;
+    ISB_LOCK(ctx);
     const char *who = "isb_shard_halfstep_dev";
     if (m->kind != ISB_KIND_SHARD) return fail(ctx, ISB_ERR_STATE, "%s: not a row-sharded model", who);
     if (!in_full_bf16 || !out_block_bf16 || R <= 0 || replica_offset < 0 || (layer != 0 && layer != 1) || n_peers < 0 ||
@@ -991,6 +1091,7 @@ int64_t isb_ens_last_near_ties(const isb_ens *e) { return e ? e->last_near_ties 
 int isb_ens_set_temperature_scale(isb_ens *e, const double *scale) {
     if (!e) return ISB_ERR_ARG;
     isb_ctx *ctx = e->model->ctx;
+    ISB_LOCK(ctx);
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!scale) {
         ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

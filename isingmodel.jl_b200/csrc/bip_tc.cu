@@ -21,6 +21,17 @@
 //                overlapping the next tile's MMAs; the canonical int8 spins are refreshed per run / trace point.
 // The producer and issuer warps run their loops warp-uniformly and pick the issuing lane with elect.sync, so that
 // descriptors and barrier addresses stay in uniform registers (see the note at the MMA issuer).
+//
+// Operand formats (template parameter FMT): 0 = bf16 terms, 1 = fp16 terms of the pre-scaled couplings, 2 = INT8 DIGIT
+// PLANES (ISB_PREC_I8X*): W is rounded once to a P x 8-bit fixed-point grid (quantum q0 = 2^e, a power of two) and
+// stored as P planes of balanced base-256 digits; spins are int8 +-1 (the ensemble's canonical arrays ARE the A
+// operand); tcgen05.mma.kind::i8 accumulates every plane EXACTLY in its own int32 TMEM accumulator (4 slots of 128
+// columns, rotating, so the next tile's first plane runs under this tile's epilogue) and the epilogue recombines
+// field = q0 * sum_t 256^(P-1-t) acc_t — no rounding anywhere in the contraction, at any K.  One int8 pass costs half a
+// bf16 pass (2x tensor rate, half the operand bytes), so 24-bit couplings cost 1.5 bf16-pass equivalents (bf16x3: 3,
+// fp16x2: 2).  A square model's diagonal (the pinning term q/2 of the MultiSpinFlip embedding, demo.jl:82-90, 64x
+// larger than the couplings) is split off and added in the epilogue from the unit's own input spin, so that the
+// fixed-point grid is scaled to the off-diagonal couplings.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -36,7 +47,10 @@
 namespace isb {
 
 constexpr int TC_BM = 128;      // replicas per tile (UMMA M)
-constexpr int TC_BK = 64;       // K elements per stage (128 bytes of bf16 = one swizzle span)
+constexpr int TC_BK = 64;       // K elements per stage, 16-bit operands (128 bytes = one swizzle span)
+constexpr int TC_BK8 = 128;     // K elements per stage, int8 digit planes (the same 128 bytes)
+constexpr int TC_I8_SLOT = 128; // int8 mode: TMEM columns per accumulator slot (4 slots), = the widest tile
+constexpr int TC_PMAX = 4;      // coupling terms / digit planes
 constexpr int TC_BN_MAX = 256;  // units per tile (UMMA N), runtime BN <= 256, multiple of 16
 constexpr int TC_STAGES = 4;     // smem ring slots, single CTAs (16 KiB of A + 32 KiB of B each)
 #ifndef ISB_TC_STAGES2
@@ -60,8 +74,8 @@ constexpr int TC_HALVES = TC_EPI_WARPS / 4;     // epilogue warps per TMEM lane 
 constexpr int TC_GW = TC_CW * TC_HALVES;        // accumulator columns the epilogue warps cover per round
 constexpr int TC_SIG_MAX = 32;                  // chain-resident mode: progress barriers per layer
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers*/;
-static_assert((2 * TC_STAGES + 6 + 2 * TC_SIG_MAX) * 8 <= 1024, "barrier block");
-static_assert((2 * TC_STAGES2 + 6 + 2 * TC_SIG_MAX) * 8 <= 1024, "barrier block");
+static_assert((2 * TC_STAGES + 8 + 2 * TC_SIG_MAX) * 8 <= 1024, "barrier block");
+static_assert((2 * TC_STAGES2 + 8 + 2 * TC_SIG_MAX) * 8 <= 1024, "barrier block");
 static_assert(TC_STAGES2 * (TC_A_BYTES + TC_B_BYTES / 2) <= TC_STAGES * TC_STAGE_BYTES, "pair ring fits the same smem");
 
 struct TcModel {
@@ -71,21 +85,29 @@ struct TcModel {
     // stays in fp16's normal range, and the epilogue multiplies the accumulators by 1 / wscale (exact).
     bool f16 = false;
     double wscale = 1.0;
+    // int8 digit planes (ISB_PREC_I8X*): W_offdiag = q0 * sum_t 256^(P-1-t) digit_t, q0 a power of two; the diagonal of
+    // a square model is kept apart (diag_d / diag_f, multiples of q0) and added by the epilogue
+    bool i8 = false;
+    double q0 = 1.0;
+    double *diag_d = nullptr;
+    float *diag_f = nullptr;
     int ldkv = 0, ldkh = 0;            // K pitch (elements) of the two operand orientations
-    __nv_bfloat16 *Wt[3] = {};         // hidden update operand: [nh][ldkv]  (K = visible units)
-    __nv_bfloat16 *Wn[3] = {};         // visible update operand: [nv][ldkh] (K = hidden units)
-    CUtensorMap mapWt[3], mapWn[3];
+    __nv_bfloat16 *Wt[TC_PMAX] = {};   // hidden update operand: [nh][ldkv]  (K = visible units); int8 planes when i8
+    __nv_bfloat16 *Wn[TC_PMAX] = {};   // visible update operand: [nv][ldkh] (K = hidden units)
+    CUtensorMap mapWt[TC_PMAX], mapWn[TC_PMAX];
     int bn_h = 0, bn_v = 0;            // default tile widths for the hidden / visible update (least padding)
     int rows_t = 0, cols_t = 0, rows_n = 0, cols_n = 0;  // shapes of the two operand orientations
     struct BnMaps {
         int orient, bn;
-        CUtensorMap m[3];
+        CUtensorMap m[TC_PMAX];
     };
     std::vector<BnMaps> bn_cache;      // tensor maps for other tile widths (the box height is part of the map)
     float *bias_hf = nullptr, *bias_vf = nullptr;  // hidden / visible biases in float, zero padded to 16
 };
 struct TcEns {
-    __nv_bfloat16 *Sv = nullptr, *Sh = nullptr;  // [R][ldkv], [R][ldkh]
+    // [R][ldkv], [R][ldkh] +-1 in the operand format; int8 mode: aliases of the ensemble's canonical int8 arrays
+    __nv_bfloat16 *Sv = nullptr, *Sh = nullptr;
+    bool alias = false;
     CUtensorMap mapSv, mapSh;
 };
 
@@ -94,8 +116,15 @@ struct TcLayer {
     int nout, kin, bn, n_tiles, num_kb;
     int u_off;        // global index of output unit 0 (row-sharded models: this rank's block offset), else 0
     int kb_per_blk;   // K blocks per slab of the A operand (block-major [G][R][nb] spin matrices), else num_kb
-    __nv_bfloat16 *out_bf;   // [R][ldo] the sampled layer (on entry: its previous values, read by MomentumAnnealing)
+    void *out_bf;            // [R][ldo] the sampled layer in the operand format (bf16 / fp16 / int8 +-1; on entry: its
+                             // previous values, read by MomentumAnnealing)
     int64_t ldo;
+    // int8 mode, square models: diagonal couplings of this layer's units (NULL: none) and where unit u's own INPUT
+    // spin of replica r lives: in_diag[r * ld_in + u] (int8)
+    const float *diag_f;
+    const double *diag_d;
+    const int8_t *in_diag;
+    int64_t ld_in;
     const double *bias;      // [nout]
     const float *bias_f;     // [nout rounded up to 16] the same in float (Philox mode)
     const double *F;         // external fluctuations (f64) or NULL
@@ -103,7 +132,7 @@ struct TcLayer {
     // fused all-gather (row-sharded SCA): the sampled block is also stored straight into every peer GPU's
     // gathered matrix through NVLink-mapped pointers (same [R][ldo] addressing as out_bf), tile by tile
     int npeer;
-    __nv_bfloat16 *peer[7];
+    void *peer[7];
 };
 struct TcParams {
     TcLayer L[2];     // [1] = hidden from visible, [0] = visible from hidden (persistent mode uses both)
@@ -123,8 +152,10 @@ struct TcParams {
     // after every round (one proxy fence each), the earlier tiles once at their end.
     int sig_gpt[2], sig_fine;
     int r_off;               // global replica index of row 0 (a run may hold a slice of the replicas): Philox only
-    uint32_t f16;            // operands are fp16 terms (selects the F16 instantiation), else bf16
+    uint32_t fmt;            // operand format: 0 bf16 terms, 1 fp16 terms, 2 int8 digit planes (selects the instantiation)
     float acc_scale;         // accumulator -> field: 1 / (power-of-two pre-scale of the fp16 couplings), 1 for bf16
+    float i8_sf[TC_PMAX];    // int8: weight of plane t, q0 * 256^(P-1-t) (powers of two), as float and as double
+    double i8_sd[TC_PMAX];
     int64_t nsteps, k0;      // steps of the whole run (fluctuation array pitch), first step of this launch
     const double *Tsched;
     const double *tscale;    // per-replica temperature factors [R] or NULL
@@ -273,6 +304,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
             : "memory");
 }
+// kind::i8: A, B signed 8-bit, D = int32 accumulators, K = 32 per instruction (the same 32 operand bytes per row)
+template <int CG>
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if constexpr (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+}
 // CG = 2: the arrive is multicast to the barrier at the same offset in both CTAs of the pair
 template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -313,6 +362,10 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int bn, uint32_t f16)
     const uint32_t fmt = f16 ? 0u : 1u;
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// kind::i8 instruction descriptor: D = s32 (c_format 2 at bit 4), A / B = signed 8-bit (1 at bits 7 / 10), K-major
+__device__ __forceinline__ uint32_t umma_idesc_i8(int m, int bn) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 // ------------------------------------------------------------------ the kernel
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -351,13 +404,16 @@ __device__ __forceinline__ void tc_wait1(uint64_t *bar, uint32_t parity) {
 
 struct TcMaps {
     CUtensorMap A[2];     // input spin matrix of layer update [1] (visible layer) and [0] (hidden layer)
-    CUtensorMap B[2][3];  // coupling terms of the two orientations
+    CUtensorMap B[2][TC_PMAX];  // coupling terms / digit planes of the two orientations
 };
 
-// F16: the operands are fp16 terms of the pre-scaled couplings (ISB_PREC_FP16X*) instead of bf16 terms; a template
+// FMT: operand format (0 bf16 terms, 1 fp16 terms of the pre-scaled couplings, 2 int8 digit planes); a template
 // parameter, so that the bf16 instantiations keep their code (and registers) exactly.
-template <bool EXTF, int CG, bool F16>
+template <bool EXTF, int CG, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+    constexpr bool F16 = FMT == 1;
+    constexpr bool I8 = FMT == 2;
+    constexpr int BK = I8 ? TC_BK8 : TC_BK;                   // K elements per ring slot (128 bytes either way)
     constexpr uint32_t ONE2 = F16 ? 0x3C003C00u : 0x3F803F80u;  // two packed +1 of the operand format
     constexpr int NST = CG == 2 ? TC_STAGES2 : TC_STAGES;     // ring slots
     constexpr int STB = TC_A_BYTES + TC_B_BYTES / CG;         // bytes per slot
@@ -367,9 +423,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
     uint64_t *full_bar = bars;                     // [NST]
     uint64_t *empty_bar = bars + NST;        // [NST]
     uint64_t *tfull_bar = bars + 2 * NST;    // [2]
-    uint64_t *tempty_bar = bars + 2 * NST + 2;  // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 5);
-    uint64_t *sig_bar = bars + 2 * NST + 6;  // [2][TC_SIG_MAX] chain-resident mode: epilogue -> producer progress
+    uint64_t *tempty_bar = bars + 2 * NST + 2;  // [4] (two accumulator stages; int8 mode: four rotating slots)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 7);
+    uint64_t *sig_bar = bars + 2 * NST + 8;  // [2][TC_SIG_MAX] chain-resident mode: epilogue -> producer progress
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int crank = CG == 2 ? (int)cluster_ctarank() : 0;  // rank in the CTA pair; 0 = leader (issues the MMAs)
@@ -384,10 +440,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
 #endif
             mbar_init(&empty_bar[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tfull_bar[a], 1);
+        for (int a = 0; a < 2; ++a) mbar_init(&tfull_bar[a], 1);
+        for (int a = 0; a < 4; ++a)
             mbar_init(&tempty_bar[a], CG * TC_EPI_WARPS);  // pair: the epilogue warps of both CTAs release the leader's
-        }
         if (p.persist)
             for (int i = 0; i < 2 * TC_SIG_MAX; ++i) mbar_init(&sig_bar[i], TC_EPI_WARPS);
         mbar_fence_init();
@@ -421,30 +476,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 const uint32_t dep_par = (uint32_t)((job.hs >> 1) - (job.layer == 1 ? 1 : 0)) & 1u;
                 int waited = -1;
                 const int bnc = L.bn / CG;      // rows of the coupling tile this CTA loads
-                const uint32_t tx = (uint32_t)(TC_A_BYTES + bnc * TC_BK * 2);
+                const uint32_t tx = (uint32_t)(TC_A_BYTES + bnc * 128);
 #ifdef ISB_TC_PROBE_K1  // timing probe only: one K block per tile = the epilogue's cost without the contraction
                 const int num_kb = 1;
 #else
                 const int num_kb = L.num_kb;
 #endif
+                // 16-bit terms: K block outer, term inner (all terms accumulate into one accumulator).  int8 digit
+                // planes: plane outer, K block inner (each plane has its own accumulator slot, and the next tile's
+                // first plane may start while this tile's epilogue still reads the other slots).
+                const int n_outer = I8 ? p.P : 1, n_inner = I8 ? 1 : p.P;
+                for (int to = 0; to < n_outer; ++to) {
                 int kq = 0, kr = 0;             // kb = kq * kb_per_blk + kr (slab of the A operand, block within it)
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (dep) {
-                        const int ul = min(kb * TC_BK + TC_BK - 1, p.L[pl].nout - 1);
+                        const int ul = min(kb * BK + BK - 1, p.L[pl].nout - 1);
                         const int idx = (ul / p.L[pl].bn) * p.sig_gpt[pl] + (ul % p.L[pl].bn) / TC_GW;
                         if (idx > waited) {
                             tc_wait1<CG>(&sig_bar[pl * TC_SIG_MAX + idx], dep_par);
                             waited = idx;
                         }
                     }
-                    for (int t = 0; t < p.P; ++t) {
+                    for (int ti = 0; ti < n_inner; ++ti) {
+                        const int t = I8 ? to : ti;
                         tc_wait1<CG>(&empty_bar[s], ph ^ 1u);
                         unsigned char *sa = smem + (size_t)s * STB;
                         if (elect_one()) {
                             if constexpr (CG == 1) {
                                 mbar_arrive_expect_tx(&full_bar[s], tx);
-                                tma_load_3d(sa, &maps.A[job.layer], kr * TC_BK, job.m0, kq, &full_bar[s]);
-                                tma_load_2d(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * TC_BK, job.n_blk * L.bn, &full_bar[s]);
+                                tma_load_3d(sa, &maps.A[job.layer], kr * BK, job.m0, kq, &full_bar[s]);
+                                tma_load_2d(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * BK, job.n_blk * L.bn, &full_bar[s]);
                             } else {
                                 const uint32_t lbar = mapa_rank0(&full_bar[s]);
                                 if (leader)
@@ -453,8 +514,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                                 else
                                     mbar_arrive_cluster_addr(lbar);
 #endif
-                                tma_load_3d_cg2(sa, &maps.A[job.layer], kr * TC_BK, job.m0, kq, lbar);
-                                tma_load_2d_cg2(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * TC_BK, job.n_blk * L.bn + crank * bnc, lbar);
+                                tma_load_3d_cg2(sa, &maps.A[job.layer], kr * BK, job.m0, kq, lbar);
+                                tma_load_2d_cg2(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * BK, job.n_blk * L.bn + crank * bnc, lbar);
                             }
                         }
                         __syncwarp();
@@ -467,6 +528,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                         kr = 0;
                         ++kq;
                     }
+                }
                 }
             }
             if constexpr (CG == 2) {
@@ -494,32 +556,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             while (jobs.next(p, job)) {
                 const TcLayer &L = p.L[job.layer];
-                const uint32_t idesc = umma_idesc_bf16(TC_BM * CG, L.bn, F16 ? 1u : 0u);
+                const uint32_t idesc = I8 ? umma_idesc_i8(TC_BM * CG, L.bn) : umma_idesc_bf16(TC_BM * CG, L.bn, F16 ? 1u : 0u);
 #ifdef ISB_TC_PROBE_K1
-                const int iters = p.P;
+                const int num_kb = 1;
 #else
-                const int iters = L.num_kb * p.P;
+                const int num_kb = L.num_kb;
 #endif
                 const int a = tl & 1;
-                tc_wait1<CG>(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_u + (uint32_t)(a * TC_BN_MAX);
-                for (int i = 0; i < iters; ++i) {
-                    tc_wait1<CG>(&full_bar[s], ph);
-                    tc_fence_after();
-                    const unsigned char *sa = smem + (size_t)s * STB;
-                    const uint64_t adesc = umma_desc_sw128(sa);
-                    const uint64_t bdesc = umma_desc_sw128(sa + TC_A_BYTES);
-                    if (elect_one()) {
-#pragma unroll
-                        for (int k = 0; k < TC_BK / 16; ++k)  // advance 16 bf16 = 32 B = 2 descriptor units along K
-                            umma_bf16<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
-                        umma_commit<CG>(&empty_bar[s]);  // slot free (in both CTAs of a pair) when these MMAs have read it
+                // 16-bit terms: one accumulator stage per tile, all K blocks x terms into it.  int8: one slot per plane.
+                const int n_outer = I8 ? p.P : 1, iters = I8 ? num_kb : num_kb * p.P;
+                for (int to = 0; to < n_outer; ++to) {
+                    uint32_t d_tmem;
+                    if constexpr (I8) {
+                        const uint32_t use = tl * (uint32_t)p.P + (uint32_t)to;   // slot use counter: slot = use mod 4
+                        tc_wait1<CG>(&tempty_bar[use & 3u], ((use >> 2) & 1u) ^ 1u);  // epilogue has drained this slot
+                        d_tmem = tmem_u + (use & 3u) * (uint32_t)TC_I8_SLOT;
+                    } else {
+                        tc_wait1<CG>(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                        d_tmem = tmem_u + (uint32_t)(a * TC_BN_MAX);
                     }
-                    __syncwarp();
-                    if (++s == NST) {
-                        s = 0;
-                        ph ^= 1u;
+                    tc_fence_after();
+                    for (int i = 0; i < iters; ++i) {
+                        tc_wait1<CG>(&full_bar[s], ph);
+                        tc_fence_after();
+                        const unsigned char *sa = smem + (size_t)s * STB;
+                        const uint64_t adesc = umma_desc_sw128(sa);
+                        const uint64_t bdesc = umma_desc_sw128(sa + TC_A_BYTES);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {  // 4 x 32 operand bytes per slot row: advance 2 descriptor units along K
+                                if constexpr (I8)
+                                    umma_i8<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+                                else
+                                    umma_bf16<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+                            }
+                            umma_commit<CG>(&empty_bar[s]);  // slot free (in both CTAs of a pair) when these MMAs have read it
+                        }
+                        __syncwarp();
+                        if (++s == NST) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
                     }
                 }
                 if (elect_one()) umma_commit<CG>(&tfull_bar[a]);  // accumulator complete (each CTA: its 128 replicas x bn units)
@@ -567,9 +644,122 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             const int tile_u0 = job.n_blk * L.bn;
             const int nfull = fastp ? min(L.bn, L.nout - tile_u0) / CW : 0;   // chunks the fast path takes
             const float *bias_t = L.bias_f + tile_u0;
-            __nv_bfloat16 *out_t = L.out_bf + (int64_t)(row_ok ? r : job.m0) * L.ldo + tile_u0;
+            __nv_bfloat16 *out_t = reinterpret_cast<__nv_bfloat16 *>(L.out_bf) + (int64_t)(row_ok ? r : job.m0) * L.ldo + tile_u0;
             const uint32_t taddr_t = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TC_BN_MAX);
             const uint32_t pc2 = (uint32_t)(r + p.r_off), pc3 = (L.domain << 28) | (uint32_t)((L.u_off + tile_u0) >> 2);
+            if constexpr (I8) {
+              // ---- int8 digit planes: P exact int32 accumulators per unit, recombined here
+              const int rr = row_ok ? r : job.m0;   // rows without a replica read / compute on a valid row, store nothing
+              int8_t *out8 = reinterpret_cast<int8_t *>(L.out_bf) + (int64_t)rr * L.ldo + tile_u0;
+              const int8_t *in8 = L.in_diag ? L.in_diag + (int64_t)rr * L.ld_in + tile_u0 : nullptr;
+              const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
+              const uint32_t use0 = tl * (uint32_t)p.P;
+              for (int g = 0; g * TC_HALVES < nchunks; ++g) {
+                const int c = g * TC_HALVES + half;
+                if (c < nfull) {
+                  // fast path (SCA, in-kernel noise, T > 0, 16 real units): field in float — every plane sum is an exact
+                  // integer and every plane weight a power of two, so the only roundings are the P + 1 additions
+                  float xf[16];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                      const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias_t + c * 16) + q);
+                      xf[4 * q] = b4.x; xf[4 * q + 1] = b4.y; xf[4 * q + 2] = b4.z; xf[4 * q + 3] = b4.w;
+                  }
+                  for (int t = 0; t < p.P; ++t) {
+                      uint32_t v[16];
+                      tmem_ld16(tq + ((use0 + (uint32_t)t) & 3u) * (uint32_t)TC_I8_SLOT + (uint32_t)(c * 16), v);
+                      const float sf = p.i8_sf[t];
+#pragma unroll
+                      for (int j = 0; j < 16; ++j) xf[j] = fmaf((float)(int)v[j], sf, xf[j]);
+                  }
+                  if (in8) {  // the unit's own coupling (square models): diag * own input spin
+                      const uint4 sv = __ldcg(reinterpret_cast<const uint4 *>(in8 + c * 16));
+                      const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                      for (int q = 0; q < 4; ++q) {
+                          const float4 d4 = __ldg(reinterpret_cast<const float4 *>(L.diag_f + tile_u0 + c * 16) + q);
+                          const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                          for (int e = 0; e < 4; ++e)
+                              xf[4 * q + e] += ((sw[q] >> (8 * e + 7)) & 1u) ? -dd[e] : dd[e];
+                      }
+                  }
+                  Philox4 blk[4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q)
+                      blk[q] = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), pc2, pc3 + (uint32_t)(c * 4 + q), keys);
+                  uint32_t wb[4] = {0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u};
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                      const float wf = (float)philox_pick(blk[j >> 2], (uint32_t)(j & 3));
+                      if (fmaf(wf, ex2_approx(cE * xf[j]), wf) > 4294967296.0f) wb[j >> 2] |= 0xFEu << (8 * (j & 3));
+                  }
+                  if (row_ok) *reinterpret_cast<uint4 *>(out8 + c * 16) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+                } else if (c < nchunks) do {
+                  // general path: the field in double, EXACT (every term is a multiple of the quantum q0)
+                  double xd[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) xd[j] = 0.0;
+                  for (int t = 0; t < p.P; ++t) {
+                      uint32_t v[16];
+                      tmem_ld16(tq + ((use0 + (uint32_t)t) & 3u) * (uint32_t)TC_I8_SLOT + (uint32_t)(c * 16), v);
+                      const double sd = p.i8_sd[t];
+#pragma unroll
+                      for (int j = 0; j < 16; ++j) xd[j] = fma((double)(int)v[j], sd, xd[j]);
+                  }
+                  const int u0 = tile_u0 + c * 16;
+                  if (!row_ok || u0 >= L.nout) break;
+                  int8_t *ob = out8 + c * 16;
+                  const bool full = u0 + 16 <= L.nout;
+                  uint32_t wb[4] = {0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u};
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                      const int u = u0 + j;
+                      if (u >= L.nout) continue;
+                      if (in8) xd[j] += (__ldcg(in8 + c * 16 + j) < 0) ? -L.diag_d[u] : L.diag_d[u];
+                      const bool old_neg = p.rule == ISB_BIP_MA && ob[j] < 0;  // MomentumAnnealing: own previous value
+                      bool neg;
+                      if (EXTF) {
+                          const double f = p.fluct_mode == ISB_FLUCT_SHARED ? L.F[job.k * L.nout + u]
+                                                                             : L.F[((int64_t)r * p.nsteps + job.k) * L.nout + u];
+                          double ft = __dmul_rn(f, Td);
+                          if (p.rule == ISB_BIP_MA && old_neg) ft = -ft;
+                          neg = __dsub_rn(__dmul_rn(2.0, __dadd_rn(xd[j], L.bias[u])), ft) < 0.0;
+                      } else {
+                          const Philox4 b4 = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), (uint32_t)(r + p.r_off),
+                                                            (L.domain << 28) | (uint32_t)((L.u_off + u) >> 2), keys);
+                          const uint32_t w = philox_pick(b4, (uint32_t)((L.u_off + u) & 3));
+                          const float x = (float)xd[j] + L.bias_f[u];
+                          const float uu = fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (w+1/2) 2^-32
+                          float tt;
+                          if (Tf == 0.f) {
+                              tt = x + 0.0f;
+                          } else if (p.rule == ISB_BIP_SCA) {
+                              tt = 1.0f - fmaf(uu, ex2_approx(cE * x), uu);
+                          } else {
+                              const float l = cS * __log2f(uu);
+                              tt = x + (old_neg ? -l : l);
+                          }
+                          neg = (__float_as_uint(tt) & 0x80000000u) != 0u;
+                      }
+                      if (neg) wb[j >> 2] |= 0xFEu << (8 * (j & 3));
+                  }
+                  if (full) {
+                      *reinterpret_cast<uint4 *>(ob) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+                      for (int pq = 0; pq < L.npeer; ++pq)  // peer stores over NVLink overlap the next tile's MMAs
+                          *reinterpret_cast<uint4 *>(reinterpret_cast<int8_t *>(L.peer[pq]) + (int64_t)r * L.ldo + u0) =
+                              make_uint4(wb[0], wb[1], wb[2], wb[3]);
+                  } else {
+                      for (int j = 0; j < 16 && u0 + j < L.nout; ++j) ob[j] = (int8_t)((wb[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+                  }
+                } while (0);
+                if (fine) {
+                  fence_proxy_async_global();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&sig[g]);
+                }
+              }
+            } else {
 #ifdef ISB_TC_PROBE_NO_EPI  // timing probe only: the contraction without the sampling epilogue
             for (int g = 0; false;) {
 #else
@@ -612,7 +802,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                     tmem_ld8(taddr, reinterpret_cast<uint32_t(&)[8]>(v));
                 const int u0 = job.n_blk * L.bn + c * CW;
                 if (!row_ok || u0 >= L.nout) break;
-                __nv_bfloat16 *ob = L.out_bf + (int64_t)r * L.ldo + u0;
+                __nv_bfloat16 *ob = reinterpret_cast<__nv_bfloat16 *>(L.out_bf) + (int64_t)r * L.ldo + u0;
                 const bool full = u0 + CW <= L.nout;
                 // MomentumAnnealing multiplies the noise by the unit's own previous value: it is still in the
                 // output matrix (bf16 +-1; pad columns read as 0 and are never stored)
@@ -699,7 +889,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                     for (int q = 0; q < CW / 8; ++q)
                         *reinterpret_cast<uint4 *>(ob + 8 * q) = make_uint4(wb[4 * q], wb[4 * q + 1], wb[4 * q + 2], wb[4 * q + 3]);
                     for (int pq = 0; pq < L.npeer; ++pq) {  // peer stores over NVLink overlap the next tile's MMAs
-                        __nv_bfloat16 *pb = L.peer[pq] + (int64_t)r * L.ldo + u0;
+                        __nv_bfloat16 *pb = reinterpret_cast<__nv_bfloat16 *>(L.peer[pq]) + (int64_t)r * L.ldo + u0;
 #pragma unroll
                         for (int q = 0; q < CW / 8; ++q)
                             *reinterpret_cast<uint4 *>(pb + 8 * q) = make_uint4(wb[4 * q], wb[4 * q + 1], wb[4 * q + 2], wb[4 * q + 3]);
@@ -717,13 +907,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 if (lane == 0) mbar_arrive(&sig[g]);
               }
             }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (CG == 2 && !leader)
-                    mbar_arrive_cluster_addr(mapa_rank0(&tempty_bar[a]));
-                else
-                    mbar_arrive(&tempty_bar[a]);
+                const int nrel = I8 ? p.P : 1;      // int8: one slot per digit plane
+                for (int t = 0; t < nrel; ++t) {
+                    uint64_t *tb = &tempty_bar[I8 ? (int)((tl * (uint32_t)p.P + (uint32_t)t) & 3u) : a];
+                    if (CG == 2 && !leader)
+                        mbar_arrive_cluster_addr(mapa_rank0(tb));
+                    else
+                        mbar_arrive(tb);
+                }
             }
             if (p.persist && !fine) {
                 fence_proxy_async_global();
@@ -800,14 +995,15 @@ static EncodeTiledFn encode_fn() {
 
 // 3-D bf16 operand [slabs][rows][ld] (cols valid per slab), box = {64 cols, 128 rows, 1 slab}: the A operand.
 // An ordinary [R][K] spin matrix is the 1-slab case; row-sharded models keep the spins block-major [G][R][nb].
-static int make_map_a(isb_ctx *ctx, CUtensorMap *map, const void *base, int slabs, int rows, int cols, int64_t ld) {
+// esz = bytes per element: 2 (bf16 / fp16 terms) or 1 (int8 digit planes: box of 128 elements = the same 128 bytes)
+static int make_map_a(isb_ctx *ctx, CUtensorMap *map, const void *base, int slabs, int rows, int cols, int64_t ld, int esz = 2) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(ctx, ISB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slabs};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)rows};
-    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)ld * esz * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)(128 / esz), (cuuint32_t)TC_BM, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = fn(map, esz == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -816,14 +1012,14 @@ static int make_map_a(isb_ctx *ctx, CUtensorMap *map, const void *base, int slab
 }
 
 // 2-D bf16 matrix [rows][ld] (cols valid), box = {64 cols, box_rows}, 128B swizzle, OOB -> 0
-static int make_map(isb_ctx *ctx, CUtensorMap *map, const void *base, int rows, int cols, int64_t ld, int box_rows) {
+static int make_map(isb_ctx *ctx, CUtensorMap *map, const void *base, int rows, int cols, int64_t ld, int box_rows, int esz = 2) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(ctx, ISB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = fn(map, esz == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, ISB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %d x %d, ld %lld", (int)r, rows, cols, (long long)ld);
@@ -854,10 +1050,10 @@ static unsigned short bf16_rne(double x, double *back) {
 
 // Tile width for a one-launch-per-half-step GEMM: the launch takes waves x bn "column units" of MMA time, so
 // minimise ceil(m_tiles * ceil(nout / bn) / SMs) * bn over the legal widths (multiples of 16 up to 256).
-static int pick_bn_waves(int nout, int m_tiles, int num_sms /* CTAs, or CTA pairs, that run tiles concurrently */) {
+static int pick_bn_waves(int nout, int m_tiles, int num_sms /* CTAs, or CTA pairs, that run tiles concurrently */, int bn_max = TC_BN_MAX) {
     int best = 0;
     long best_cost = 0;
-    for (int bn = 256; bn >= 64; bn -= 16) {
+    for (int bn = bn_max; bn >= 64; bn -= 16) {
         const long tiles = (long)m_tiles * ((nout + bn - 1) / bn);
         const long cost = ((tiles + num_sms - 1) / num_sms) * bn;
         if (best == 0 || cost < best_cost) {
@@ -868,8 +1064,8 @@ static int pick_bn_waves(int nout, int m_tiles, int num_sms /* CTAs, or CTA pair
     return best;
 }
 
-static int pick_bn(int nout) {
-    const int nt = (nout + TC_BN_MAX - 1) / TC_BN_MAX;
+static int pick_bn(int nout, int bn_max = TC_BN_MAX) {
+    const int nt = (nout + bn_max - 1) / bn_max;
     int bn = ((nout + nt - 1) / nt + 15) / 16 * 16;
     return bn < 16 ? 16 : bn;
 }
@@ -877,21 +1073,123 @@ static int pick_bn(int nout) {
 // Row pitch (elements) of a K-major bf16 operand with k valid columns.  A TMA box reads 128-256 rows at this pitch at
 // once: a pitch that is a multiple of 1 KiB would put all of them on a few L2 slices, so such pitches get one more
 // 128-byte line (ISB_TC_PAD=0 disables the padding, for A/B measurements).
-static int tc_pitch(int k) {
+static int tc_pitch(int k, int esz = 2) {
     int ld = (k + 15) / 16 * 16;
     bool pad = true;
     if (const char *env = getenv("ISB_TC_PAD")) pad = atoi(env) != 0;
-    if (pad && (ld * 2) % 1024 == 0) ld += 64;
+    if (pad && (ld * esz) % 1024 == 0) ld += 128 / esz;
     return ld;
+}
+
+// ---- int8 digit planes (ISB_PREC_I8X*)
+// Fixed-point grid of P x 8 bits for couplings of magnitude <= amax: quantum q0 = 2^e (a power of two) such that every
+// |W| / q0 rounds to an integer that P balanced base-256 digits (each in [-128, 127]; the top one in [-127, 127]) hold.
+static long long i8_max_int(int P) {
+    long long m = 0;
+    for (int t = 0; t < P; ++t) m = m * 256 + 127;
+    return m;
+}
+double i8_quantum(double amax, int P) {
+    if (!(amax > 0.0)) return ldexp(1.0, -8 * P);
+    int e;
+    frexp(amax, &e);                       // amax = f 2^e, f in [0.5, 1)
+    double q0 = ldexp(1.0, e - (8 * P - 1));  // amax / q0 < 2^(8P-1)
+    if (rint(amax / q0) > (double)i8_max_int(P)) q0 *= 2.0;
+    return q0;
+}
+// w (an integer, |w| <= i8_max_int(P)) -> P balanced digits, most significant first
+__host__ __device__ inline void i8_digits(long long w, int P, int8_t *d) {
+    for (int t = P - 1; t >= 0; --t) {
+        long long r = ((w % 256) + 256) % 256;   // w mod 256 in [0, 255]
+        if (r > 127) r -= 256;                    // balanced: [-128, 127]
+        d[t] = (int8_t)r;
+        w = (w - r) / 256;
+    }
+}
+__host__ __device__ inline long long i8_quantize(double w, double q0, long long maxint) {
+    double x = rint(w / q0);                      // q0 is a power of two: the division is exact
+    if (x > (double)maxint) x = (double)maxint;
+    if (x < -(double)maxint) x = -(double)maxint;
+    return (long long)x;
+}
+
+static int prec_terms(int prec) {
+    switch (prec) {
+        case ISB_PREC_BF16X3: case ISB_PREC_I8X3: return 3;
+        case ISB_PREC_BF16X2: case ISB_PREC_FP16X2: case ISB_PREC_I8X2: return 2;
+        case ISB_PREC_I8X4: return 4;
+        default: return 1;
+    }
+}
+static bool prec_is_i8(int prec) { return prec == ISB_PREC_I8X2 || prec == ISB_PREC_I8X3 || prec == ISB_PREC_I8X4; }
+
+// int8 digit planes of a bipartite model (host side): both orientations, the diagonal of a square model split off when
+// it dominates the couplings (the pinning term of the MultiSpinFlip embedding)
+static int bip_tc_model_init_i8(isb_model *m, TcModel *t, const double *W) {
+    isb_ctx *ctx = m->ctx;
+    const int nv = m->nv, nh = m->nh, P = t->P;
+    double amax_off = 0.0, amax_diag = 0.0, amax_all = 0.0;
+    for (int i = 0; i < nv; ++i)
+        for (int j = 0; j < nh; ++j) {
+            const double a = fabs(W[(size_t)i * nh + j]);
+            amax_all = std::max(amax_all, a);
+            if (nv == nh && i == j) amax_diag = std::max(amax_diag, a); else amax_off = std::max(amax_off, a);
+        }
+    const bool split = nv == nh && amax_diag > 2.0 * amax_off;
+    t->q0 = i8_quantum(split ? amax_off : amax_all, P);
+    const long long maxint = i8_max_int(P);
+    t->ldkv = tc_pitch(nv, 1);
+    t->ldkh = tc_pitch(nh, 1);
+    t->bn_h = pick_bn(nh, TC_I8_SLOT);
+    t->bn_v = pick_bn(nv, TC_I8_SLOT);
+    t->rows_t = nh; t->cols_t = nv; t->rows_n = nv; t->cols_n = nh;
+    std::vector<std::vector<int8_t>> wt(P, std::vector<int8_t>((size_t)nh * t->ldkv, 0)), wn(P, std::vector<int8_t>((size_t)nv * t->ldkh, 0));
+    std::vector<double> dg;
+    if (split) dg.assign((size_t)nv, 0.0);
+    for (int i = 0; i < nv; ++i)
+        for (int j = 0; j < nh; ++j) {
+            const double w = W[(size_t)i * nh + j];
+            if (split && i == j) {
+                dg[i] = rint(w / t->q0) * t->q0;   // on the grid, not clamped: the epilogue adds it in float / double
+                continue;
+            }
+            int8_t d[TC_PMAX];
+            i8_digits(i8_quantize(w, t->q0, maxint), P, d);
+            for (int term = 0; term < P; ++term) {
+                wt[term][(size_t)j * t->ldkv + i] = d[term];
+                wn[term][(size_t)i * t->ldkh + j] = d[term];
+            }
+        }
+    for (int term = 0; term < P; ++term) {
+        ISB_CUDA(ctx, cudaMalloc(&t->Wt[term], wt[term].size()));
+        ISB_CUDA(ctx, cudaMalloc(&t->Wn[term], wn[term].size()));
+        ISB_CUDA(ctx, cudaMemcpy(t->Wt[term], wt[term].data(), wt[term].size(), cudaMemcpyHostToDevice));
+        ISB_CUDA(ctx, cudaMemcpy(t->Wn[term], wn[term].data(), wn[term].size(), cudaMemcpyHostToDevice));
+    }
+    if (split) {
+        std::vector<float> dgf(((size_t)nv + 15) / 16 * 16, 0.f);
+        for (int i = 0; i < nv; ++i) dgf[i] = (float)dg[i];
+        ISB_CUDA(ctx, cudaMalloc(&t->diag_d, dg.size() * sizeof(double)));
+        ISB_CUDA(ctx, cudaMalloc(&t->diag_f, dgf.size() * sizeof(float)));
+        ISB_CUDA(ctx, cudaMemcpy(t->diag_d, dg.data(), dg.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ISB_CUDA(ctx, cudaMemcpy(t->diag_f, dgf.data(), dgf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return ISB_OK;
 }
 
 int bip_tc_model_init(isb_model *m, const double *W /*[nv][nh] row-major*/) {
     isb_ctx *ctx = m->ctx;
     TcModel *t = new TcModel();
     m->tc = t;
-    t->P = m->prec == ISB_PREC_BF16X3 ? 3 : ((m->prec == ISB_PREC_BF16X2 || m->prec == ISB_PREC_FP16X2) ? 2 : 1);
+    t->P = prec_terms(m->prec);
     t->f16 = m->prec == ISB_PREC_FP16X2 || m->prec == ISB_PREC_FP16X1;
+    t->i8 = prec_is_i8(m->prec);
     const int nv = m->nv, nh = m->nh;
+    const int esz = t->i8 ? 1 : 2;
+    if (t->i8) {
+        int rc = bip_tc_model_init_i8(m, t, W);
+        if (rc) return rc;
+    } else {
     if (t->f16) {
         double amax = 0.0;
         for (size_t i = 0; i < (size_t)nv * nh; ++i) amax = std::max(amax, fabs(W[i]));
@@ -924,29 +1222,70 @@ int bip_tc_model_init(isb_model *m, const double *W /*[nv][nh] row-major*/) {
         ISB_CUDA(ctx, cudaMalloc(&t->Wn[term], wn.size() * 2));
         ISB_CUDA(ctx, cudaMemcpy(t->Wt[term], wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
         ISB_CUDA(ctx, cudaMemcpy(t->Wn[term], wn.data(), wn.size() * 2, cudaMemcpyHostToDevice));
-        int rc = make_map(ctx, &t->mapWt[term], t->Wt[term], nh, nv, t->ldkv, t->bn_h);
-        if (rc) return rc;
-        rc = make_map(ctx, &t->mapWn[term], t->Wn[term], nv, nh, t->ldkh, t->bn_v);
-        if (rc) return rc;
     }
-    for (int term = t->P; term < 3; ++term) {
-        t->mapWt[term] = t->mapWt[0];
-        t->mapWn[term] = t->mapWn[0];
+    }
+    for (int term = 0; term < TC_PMAX; ++term) {
+        const int src = term < t->P ? term : 0;
+        int rc = make_map(ctx, &t->mapWt[term], t->Wt[src], nh, nv, t->ldkv, t->bn_h, esz);
+        if (rc) return rc;
+        rc = make_map(ctx, &t->mapWn[term], t->Wn[src], nv, nh, t->ldkh, t->bn_v, esz);
+        if (rc) return rc;
     }
     int rc = make_float_bias(ctx, m->bb64, nh, &t->bias_hf);
     if (rc) return rc;
     return make_float_bias(ctx, m->hb64, nv, &t->bias_vf);
 }
 
+// The couplings exactly as the tensor path uses them (sum of the stored terms / digit planes, plus the split diagonal):
+// Wout is [nv][nh] row-major (host).  Parity tests feed the oracle this matrix.
+int bip_tc_effective_couplings(isb_model *m, double *Wout) {
+    isb_ctx *ctx = m->ctx;
+    TcModel *t = (TcModel *)m->tc;
+    const int nv = m->nv, nh = m->nh;
+    const size_t esz = t->i8 ? 1 : 2;
+    std::vector<unsigned char> buf((size_t)nv * t->ldkh * esz);
+    std::fill(Wout, Wout + (size_t)nv * nh, 0.0);
+    for (int term = 0; term < t->P; ++term) {
+        ISB_CUDA(ctx, cudaMemcpy(buf.data(), t->Wn[term], buf.size(), cudaMemcpyDeviceToHost));
+        const double wgt = t->i8 ? t->q0 * pow(256.0, t->P - 1 - term) : 1.0 / t->wscale;
+        for (int i = 0; i < nv; ++i)
+            for (int j = 0; j < nh; ++j) {
+                const size_t k = (size_t)i * t->ldkh + j;
+                double v;
+                if (t->i8) {
+                    v = (double)reinterpret_cast<const int8_t *>(buf.data())[k];
+                } else if (t->f16) {
+                    __half hv;
+                    memcpy(&hv, buf.data() + 2 * k, 2);
+                    v = (double)__half2float(hv);
+                } else {
+                    const uint32_t ub = (uint32_t)reinterpret_cast<const unsigned short *>(buf.data())[k] << 16;
+                    float fb;
+                    memcpy(&fb, &ub, 4);
+                    v = (double)fb;
+                }
+                Wout[(size_t)i * nh + j] += v * wgt;   // exact: every term is a multiple of the smallest term's ulp
+            }
+    }
+    if (t->diag_d) {
+        std::vector<double> dg((size_t)nv);
+        ISB_CUDA(ctx, cudaMemcpy(dg.data(), t->diag_d, dg.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nv; ++i) Wout[(size_t)i * nh + i] += dg[i];
+    }
+    return ISB_OK;
+}
+
 void bip_tc_model_free(isb_model *m) {
     TcModel *t = (TcModel *)m->tc;
     if (!t) return;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < TC_PMAX; ++i) {
         cudaFree(t->Wt[i]);
         cudaFree(t->Wn[i]);
     }
     cudaFree(t->bias_hf);
     cudaFree(t->bias_vf);
+    cudaFree(t->diag_d);
+    cudaFree(t->diag_f);
     delete t;
     m->tc = nullptr;
 }
@@ -957,6 +1296,16 @@ int bip_tc_ens_init(isb_ens *e) {
     TcModel *t = (TcModel *)m->tc;
     TcEns *s = new TcEns();
     e->tc = s;
+    if (t->i8) {
+        // int8 digit planes: the ensemble's canonical int8 spin arrays ARE the A operands (TMA zero-fills the columns
+        // beyond nv / nh, whatever the pad bytes hold), and the epilogue writes +-1 bytes straight into them
+        s->alias = true;
+        s->Sv = reinterpret_cast<__nv_bfloat16 *>(e->spins);
+        s->Sh = reinterpret_cast<__nv_bfloat16 *>(e->hidden);
+        int rc = make_map_a(ctx, &s->mapSv, e->spins, 1, e->R, m->nv, e->lds, 1);
+        if (rc) return rc;
+        return make_map_a(ctx, &s->mapSh, e->hidden, 1, e->R, m->nh, e->ldh, 1);
+    }
     ISB_CUDA(ctx, cudaMalloc(&s->Sv, (size_t)e->R * t->ldkv * 2));
     ISB_CUDA(ctx, cudaMalloc(&s->Sh, (size_t)e->R * t->ldkh * 2));
     int rc = make_map_a(ctx, &s->mapSv, s->Sv, 1, e->R, m->nv, t->ldkv);
@@ -967,33 +1316,35 @@ int bip_tc_ens_init(isb_ens *e) {
 void bip_tc_ens_free(isb_ens *e) {
     TcEns *s = (TcEns *)e->tc;
     if (!s) return;
-    cudaFree(s->Sv);
-    cudaFree(s->Sh);
+    if (!s->alias) {
+        cudaFree(s->Sv);
+        cudaFree(s->Sh);
+    }
     delete s;
     e->tc = nullptr;
 }
 
-static int make_map(isb_ctx *ctx, CUtensorMap *map, const void *base, int rows, int cols, int64_t ld, int box_rows);
 // Coupling tensor maps of orientation `orient` (1: Wt, hidden update; 0: Wn, visible update) whose box holds `bn`
 // rows of W (the tile width, or half of it when a CTA pair shares the tile)
-static int get_maps_b(isb_ctx *ctx, TcModel *t, int orient, int bn, CUtensorMap out[3]) {
+static int get_maps_b(isb_ctx *ctx, TcModel *t, int orient, int bn, CUtensorMap out[TC_PMAX]) {
     const int dflt = orient == 1 ? t->bn_h : t->bn_v;
+    const int esz = t->i8 ? 1 : 2;
     if (bn == dflt) {
-        for (int i = 0; i < 3; ++i) out[i] = orient == 1 ? t->mapWt[i] : t->mapWn[i];
+        for (int i = 0; i < TC_PMAX; ++i) out[i] = orient == 1 ? t->mapWt[i] : t->mapWn[i];
         return ISB_OK;
     }
     for (auto &c : t->bn_cache)
         if (c.orient == orient && c.bn == bn) {
-            for (int i = 0; i < 3; ++i) out[i] = c.m[i];
+            for (int i = 0; i < TC_PMAX; ++i) out[i] = c.m[i];
             return ISB_OK;
         }
     TcModel::BnMaps c;
     c.orient = orient;
     c.bn = bn;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < TC_PMAX; ++i) {
         const int src = i < t->P ? i : 0;
-        int rc = orient == 1 ? make_map(ctx, &c.m[i], t->Wt[src], t->rows_t, t->cols_t, t->ldkv, bn)
-                             : make_map(ctx, &c.m[i], t->Wn[src], t->rows_n, t->cols_n, t->ldkh, bn);
+        int rc = orient == 1 ? make_map(ctx, &c.m[i], t->Wt[src], t->rows_t, t->cols_t, t->ldkv, bn, esz)
+                             : make_map(ctx, &c.m[i], t->Wn[src], t->rows_n, t->cols_n, t->ldkh, bn, esz);
         if (rc) return rc;
         out[i] = c.m[i];
     }
@@ -1001,13 +1352,17 @@ static int get_maps_b(isb_ctx *ctx, TcModel *t, int orient, int bn, CUtensorMap 
     return ISB_OK;
 }
 
-static void fill_layer(TcLayer &L, int nout, int kin, int bn, __nv_bfloat16 *out_bf, int64_t ldo, const double *bias,
-                       const float *bias_f, const double *F, uint32_t domain) {
+static void fill_layer(TcLayer &L, int nout, int kin, int bn, void *out_bf, int64_t ldo, const double *bias,
+                       const float *bias_f, const double *F, uint32_t domain, int bk = TC_BK) {
     L.nout = nout;
     L.kin = kin;
     L.bn = bn;
     L.n_tiles = (nout + bn - 1) / bn;
-    L.num_kb = (kin + TC_BK - 1) / TC_BK;
+    L.num_kb = (kin + bk - 1) / bk;
+    L.diag_f = nullptr;
+    L.diag_d = nullptr;
+    L.in_diag = nullptr;
+    L.ld_in = 0;
     L.u_off = 0;
     L.kb_per_blk = L.num_kb;
     L.out_bf = out_bf;
@@ -1028,9 +1383,9 @@ static int tc_cta_group() {
     return cg;
 }
 
-template <bool EXTF, int CG, bool F16>
+template <bool EXTF, int CG, int FMT>
 static int launch_tc_inst(isb_ctx *ctx, const TcMaps &maps, const TcParams &p, int grid) {
-    ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<EXTF, CG, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    ISB_CUDA(ctx, cudaFuncSetAttribute(bip_tc_kernel<EXTF, CG, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(TC_THREADS);
@@ -1043,18 +1398,22 @@ static int launch_tc_inst(isb_ctx *ctx, const TcMaps &maps, const TcParams &p, i
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CG > 1 ? 1 : 0;
-    ISB_CUDA(ctx, cudaLaunchKernelEx(&cfg, bip_tc_kernel<EXTF, CG, F16>, maps, p));
+    ISB_CUDA(ctx, cudaLaunchKernelEx(&cfg, bip_tc_kernel<EXTF, CG, FMT>, maps, p));
     return ISB_OK;
 }
 
 // grid = CTAs (a multiple of p.cg)
 static int launch_tc(isb_ctx *ctx, const TcMaps &maps, const TcParams &p, int grid, bool extf) {
-    if (p.f16) {
-        if (p.cg == 2) return extf ? launch_tc_inst<true, 2, true>(ctx, maps, p, grid) : launch_tc_inst<false, 2, true>(ctx, maps, p, grid);
-        return extf ? launch_tc_inst<true, 1, true>(ctx, maps, p, grid) : launch_tc_inst<false, 1, true>(ctx, maps, p, grid);
+    if (p.fmt == 2) {
+        if (p.cg == 2) return extf ? launch_tc_inst<true, 2, 2>(ctx, maps, p, grid) : launch_tc_inst<false, 2, 2>(ctx, maps, p, grid);
+        return extf ? launch_tc_inst<true, 1, 2>(ctx, maps, p, grid) : launch_tc_inst<false, 1, 2>(ctx, maps, p, grid);
     }
-    if (p.cg == 2) return extf ? launch_tc_inst<true, 2, false>(ctx, maps, p, grid) : launch_tc_inst<false, 2, false>(ctx, maps, p, grid);
-    return extf ? launch_tc_inst<true, 1, false>(ctx, maps, p, grid) : launch_tc_inst<false, 1, false>(ctx, maps, p, grid);
+    if (p.fmt == 1) {
+        if (p.cg == 2) return extf ? launch_tc_inst<true, 2, 1>(ctx, maps, p, grid) : launch_tc_inst<false, 2, 1>(ctx, maps, p, grid);
+        return extf ? launch_tc_inst<true, 1, 1>(ctx, maps, p, grid) : launch_tc_inst<false, 1, 1>(ctx, maps, p, grid);
+    }
+    if (p.cg == 2) return extf ? launch_tc_inst<true, 2, 0>(ctx, maps, p, grid) : launch_tc_inst<false, 2, 0>(ctx, maps, p, grid);
+    return extf ? launch_tc_inst<true, 1, 0>(ctx, maps, p, grid) : launch_tc_inst<false, 1, 0>(ctx, maps, p, grid);
 }
 
 // Steps [k0, k0 + nseg) of a run: one chain-resident launch when the replicas fill the SMs, else 2 * nseg
@@ -1075,8 +1434,9 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     bool persist = rows >= 96;
     if (const char *env = getenv("ISB_TC_PERSIST")) persist = atoi(env) != 0 && e->R >= 1;
     // tile widths: least padding per CTA in chain-resident mode, fewest (waves x width) otherwise
-    const int bn_h = persist ? t->bn_h : pick_bn_waves(m->nh, m_tiles, ctx->num_sms / cg);
-    const int bn_v = persist ? t->bn_v : pick_bn_waves(m->nv, m_tiles, ctx->num_sms / cg);
+    const int bn_max = t->i8 ? TC_I8_SLOT : TC_BN_MAX;
+    const int bn_h = persist ? t->bn_h : pick_bn_waves(m->nh, m_tiles, ctx->num_sms / cg, bn_max);
+    const int bn_v = persist ? t->bn_v : pick_bn_waves(m->nv, m_tiles, ctx->num_sms / cg, bn_max);
     TcMaps maps;
     maps.A[1] = s->mapSv;
     maps.A[0] = s->mapSh;
@@ -1086,8 +1446,19 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     if (rcm) return rcm;
     TcParams p{};
     p.cg = cg;
-    fill_layer(p.L[1], m->nh, m->nv, bn_h, s->Sh, t->ldkh, m->bb64, t->bias_hf, d_Fh, DOM_BIP_HIDDEN);
-    fill_layer(p.L[0], m->nv, m->nh, bn_v, s->Sv, t->ldkv, m->hb64, t->bias_vf, d_Fv, DOM_BIP_VISIBLE);
+    const int bk = t->i8 ? TC_BK8 : TC_BK;
+    fill_layer(p.L[1], m->nh, m->nv, bn_h, s->Sh, t->i8 ? e->ldh : t->ldkh, m->bb64, t->bias_hf, d_Fh, DOM_BIP_HIDDEN, bk);
+    fill_layer(p.L[0], m->nv, m->nh, bn_v, s->Sv, t->i8 ? e->lds : t->ldkv, m->hb64, t->bias_vf, d_Fv, DOM_BIP_VISIBLE, bk);
+    if (t->diag_d) {  // square model with the diagonal split off: unit u's own input spin is column u of the input layer
+        p.L[1].diag_f = p.L[0].diag_f = t->diag_f;
+        p.L[1].diag_d = p.L[0].diag_d = t->diag_d;
+        p.L[1].in_diag = e->spins;  p.L[1].ld_in = e->lds;
+        p.L[0].in_diag = e->hidden; p.L[0].ld_in = e->ldh;
+    }
+    for (int term = 0; term < TC_PMAX; ++term) {
+        p.i8_sd[term] = term < t->P ? t->q0 * pow(256.0, t->P - 1 - term) : 0.0;
+        p.i8_sf[term] = (float)p.i8_sd[term];
+    }
     p.R = e->R;
     p.P = t->P;
     p.rule = rule;
@@ -1097,7 +1468,7 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     p.tscale = e->d_tscale;
     p.steps_per_T = steps_per_T;
     p.seed = seed;
-    p.f16 = t->f16 ? 1u : 0u;
+    p.fmt = t->i8 ? 2u : (t->f16 ? 1u : 0u);
     p.acc_scale = (float)(1.0 / t->wscale);
     p.m_tiles = m_tiles;
     for (int l = 0; l < 2; ++l) {
@@ -1174,6 +1545,26 @@ __global__ void shard_fill_kernel(int n, int row0, int nrows, uint64_t seed, dou
         }
     }
 }
+// int8 digit planes of the same rows: off-diagonal couplings on the grid q0, the diagonal kept apart (on the grid too)
+__global__ void shard_fill_i8_kernel(int n, int row0, int nrows, uint64_t seed, double q, const double *Wrows, int P,
+                                     double q0, long long maxint, int8_t *p0, int8_t *p1, int8_t *p2, int8_t *p3,
+                                     double *diag_d, float *diag_f) {
+    const int64_t total = (int64_t)nrows * n;
+    int8_t *pl[TC_PMAX] = {p0, p1, p2, p3};
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / n), c = (int)(idx % n);
+        const double w = Wrows ? Wrows[idx] : 0.5 * (sk_coupling(seed, n, row0 + r, c) + (row0 + r == c ? q : 0.0));
+        int8_t d[TC_PMAX] = {0, 0, 0, 0};
+        if (row0 + r == c) {
+            const double dg = rint(w / q0) * q0;
+            diag_d[r] = dg;
+            diag_f[r] = (float)dg;
+        } else {
+            i8_digits(i8_quantize(w, q0, maxint), P, d);
+        }
+        for (int t = 0; t < P; ++t) pl[t][idx] = d[t];
+    }
+}
 __global__ void sk_rows_kernel(int n, uint64_t seed, int row0, int nrows, double *out) {
     const int64_t total = (int64_t)nrows * n;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x)
@@ -1186,14 +1577,16 @@ int sk_rows_device(isb_ctx *ctx, int n, uint64_t seed, int row0, int nrows, doub
     return ISB_OK;
 }
 
-int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q) {
+int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q, double wmax) {
     isb_ctx *ctx = m->ctx;
     TcModel *t = new TcModel();
     m->tc = t;
-    t->P = m->prec == ISB_PREC_BF16X3 ? 3 : (m->prec == ISB_PREC_BF16X2 ? 2 : 1);
+    t->P = prec_terms(m->prec);
+    t->i8 = prec_is_i8(m->prec);
+    const int esz = t->i8 ? 1 : 2;
     const int n = m->nv, nb = m->shard_nb;
     t->ldkv = t->ldkh = n;
-    t->bn_h = t->bn_v = pick_bn(nb);
+    t->bn_h = t->bn_v = pick_bn(nb, t->i8 ? TC_I8_SLOT : TC_BN_MAX);
     t->rows_t = t->rows_n = nb; t->cols_t = t->cols_n = n;
     const size_t elems = (size_t)nb * n;
     double *dW = nullptr;
@@ -1201,15 +1594,33 @@ int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q)
         ISB_CUDA(ctx, cudaMalloc(&dW, elems * sizeof(double)));
         ISB_CUDA(ctx, cudaMemcpyAsync(dW, Wrows, elems * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
-    for (int term = 0; term < t->P; ++term) ISB_CUDA(ctx, cudaMalloc(&t->Wt[term], elems * 2));
-    shard_fill_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, m->shard_g * nb, nb, seed, q, dW, t->P, t->Wt[0],
-                                                                 t->Wt[1], t->Wt[2]);
+    for (int term = 0; term < t->P; ++term) ISB_CUDA(ctx, cudaMalloc(&t->Wt[term], elems * esz));
+    if (t->i8) {
+        // The grid must be the same on every rank (the trajectory may not depend on the sharding): the caller passes
+        // the largest off-diagonal |W| of the WHOLE matrix (wmax); for the synthetic instance it is bounded a priori:
+        // |J_ij| = |g| / sqrt(n) with |g| <= sqrt(-2 ln 2^-33) < 6.77 (Box-Muller on a 32-bit uniform), W = J / 2.
+        if (!Wrows) wmax = 0.5 * 6.77 / sqrt((double)n);
+        if (!(wmax > 0.0) && Wrows) {   // not given: this block's own maximum (single-block models)
+            for (int r = 0; r < nb; ++r)
+                for (int c = 0; c < n; ++c)
+                    if (m->shard_g * nb + r != c) wmax = std::max(wmax, fabs(Wrows[(size_t)r * n + c]));
+        }
+        t->q0 = i8_quantum(wmax, t->P);
+        ISB_CUDA(ctx, cudaMalloc(&t->diag_d, (size_t)nb * sizeof(double)));
+        ISB_CUDA(ctx, cudaMalloc(&t->diag_f, (size_t)nb * sizeof(float)));
+        shard_fill_i8_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(
+            n, m->shard_g * nb, nb, seed, q, dW, t->P, t->q0, i8_max_int(t->P), (int8_t *)t->Wt[0], (int8_t *)t->Wt[1],
+            (int8_t *)t->Wt[2], (int8_t *)t->Wt[3], t->diag_d, t->diag_f);
+    } else {
+        shard_fill_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, m->shard_g * nb, nb, seed, q, dW, t->P, t->Wt[0],
+                                                                     t->Wt[1], t->Wt[2]);
+    }
     ISB_CUDA(ctx, cudaGetLastError());
     ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (dW) cudaFree(dW);
-    for (int term = 0; term < 3; ++term) {
+    for (int term = 0; term < TC_PMAX; ++term) {
         const int src = term < t->P ? term : 0;
-        int rc = make_map(ctx, &t->mapWt[term], t->Wt[src], nb, n, n, t->bn_h);
+        int rc = make_map(ctx, &t->mapWt[term], t->Wt[src], nb, n, n, t->bn_h, esz);
         if (rc) return rc;
     }
     int rc = make_float_bias(ctx, m->bb64, nb, &t->bias_hf);
@@ -1222,24 +1633,35 @@ int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, in
     isb_ctx *ctx = m->ctx;
     TcModel *t = (TcModel *)m->tc;
     TcMaps maps;
-    int rc = make_map_a(ctx, &maps.A[layer], in_full, m->shard_G, R, m->shard_nb, m->shard_nb);
+    const int esz = t->i8 ? 1 : 2, bk = t->i8 ? TC_BK8 : TC_BK;
+    int rc = make_map_a(ctx, &maps.A[layer], in_full, m->shard_G, R, m->shard_nb, m->shard_nb, esz);
     if (rc) return rc;
     maps.A[1 - layer] = maps.A[layer];
     const int cg = tc_cta_group();
     const int m_tiles = (R + TC_BM * cg - 1) / (TC_BM * cg);
-    const int bn = pick_bn_waves(m->shard_nb, m_tiles, ctx->num_sms / cg);
+    const int bn = pick_bn_waves(m->shard_nb, m_tiles, ctx->num_sms / cg, t->i8 ? TC_I8_SLOT : TC_BN_MAX);
     rc = get_maps_b(ctx, t, 1, bn / cg, maps.B[1]);  // W is symmetric: one orientation serves both half-steps
     if (rc) return rc;
-    for (int i = 0; i < 3; ++i) maps.B[0][i] = maps.B[1][i];
+    for (int i = 0; i < TC_PMAX; ++i) maps.B[0][i] = maps.B[1][i];
     TcParams p{};
-    fill_layer(p.L[layer], m->shard_nb, m->nv, bn, (__nv_bfloat16 *)out_block, m->shard_nb,
+    fill_layer(p.L[layer], m->shard_nb, m->nv, bn, out_block, m->shard_nb,
                layer == 1 ? m->bb64 : m->hb64, layer == 1 ? t->bias_hf : t->bias_vf, nullptr,
-               layer == 1 ? DOM_BIP_HIDDEN : DOM_BIP_VISIBLE);
+               layer == 1 ? DOM_BIP_HIDDEN : DOM_BIP_VISIBLE, bk);
     p.L[layer].u_off = m->shard_g * m->shard_nb;
-    p.L[layer].num_kb = m->nv / TC_BK;
-    p.L[layer].kb_per_blk = m->shard_nb / TC_BK;
+    p.L[layer].num_kb = m->nv / bk;
+    p.L[layer].kb_per_blk = m->shard_nb / bk;
     p.L[layer].npeer = n_peers;
-    for (int q = 0; q < n_peers; ++q) p.L[layer].peer[q] = (__nv_bfloat16 *)peer_blocks[q];
+    for (int q = 0; q < n_peers; ++q) p.L[layer].peer[q] = peer_blocks[q];
+    if (t->i8) {  // the diagonal of W: unit u's own input spin sits in this rank's slab of the gathered input layer
+        p.L[layer].diag_f = t->diag_f;
+        p.L[layer].diag_d = t->diag_d;
+        p.L[layer].in_diag = reinterpret_cast<const int8_t *>(in_full) + (size_t)m->shard_g * R * m->shard_nb;
+        p.L[layer].ld_in = m->shard_nb;
+    }
+    for (int term = 0; term < TC_PMAX; ++term) {
+        p.i8_sd[term] = term < t->P ? t->q0 * pow(256.0, t->P - 1 - term) : 0.0;
+        p.i8_sf[term] = (float)p.i8_sd[term];
+    }
     p.L[1 - layer] = p.L[layer];
     p.R = R;
     p.r_off = replica_offset;
@@ -1247,7 +1669,7 @@ int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, in
     p.rule = rule;
     p.fluct_mode = ISB_FLUCT_PHILOX;
     p.Tsched = nullptr;
-    p.f16 = 0u;  // row-sharded models ship bf16 terms only
+    p.fmt = t->i8 ? 2u : 0u;  // row-sharded models: bf16 terms or int8 digit planes
     p.acc_scale = 1.0f;
     p.T_direct = T;
     p.steps_per_T = 1;
@@ -1270,12 +1692,16 @@ int bip_run_tc_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, cons
     TcEns *s = (TcEns *)e->tc;
     // the canonical int8 visible layer is the input of the first half-step; the hidden bf16 matrix is
     // produced by it (MomentumAnnealing reads the hidden layer's previous value from the int8 array)
+    // (int8 digit planes: the canonical int8 arrays are the operands themselves — nothing to convert)
     const unsigned short one = t->f16 ? 0x3C00 : 0x3F80;
-    spins_to_bf16_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(e->spins, e->lds, s->Sv, t->ldkv, m->nv, e->R, one);
-    spins_to_bf16_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(e->hidden, e->ldh, s->Sh, t->ldkh, m->nh, e->R, one);
-    ISB_CUDA(ctx, cudaGetLastError());
-    e->last_launches += 2;
+    if (!t->i8) {
+        spins_to_bf16_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(e->spins, e->lds, s->Sv, t->ldkv, m->nv, e->R, one);
+        spins_to_bf16_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(e->hidden, e->ldh, s->Sh, t->ldkh, m->nh, e->R, one);
+        ISB_CUDA(ctx, cudaGetLastError());
+        e->last_launches += 2;
+    }
     auto sync_canonical = [&]() -> int {  // bf16 operand matrices -> the ensemble's int8 spins
+        if (t->i8) return ISB_OK;
         bf16_to_spins_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(s->Sv, t->ldkv, e->spins, e->lds, m->nv, e->R);
         bf16_to_spins_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(s->Sh, t->ldkh, e->hidden, e->ldh, m->nh, e->R);
         ISB_CUDA(ctx, cudaGetLastError());

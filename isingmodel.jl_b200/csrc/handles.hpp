@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 #include "../../include/ising_b200.h"
@@ -21,8 +22,10 @@ struct isb_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::string err;
     isb_devbuf scratch[13];      // grow-only device staging buffers (see isb::dev_reserve)
+    // Every entry point that uses the stream, the events or the scratch buffers holds this lock for its whole
+    // (synchronous) duration: calls on one context are serialised, different contexts run concurrently.
+    std::recursive_mutex mtx;
 };
 
 enum { ISB_KIND_DENSE = 0, ISB_KIND_BIPARTITE = 1, ISB_KIND_SHARD = 2, ISB_KIND_SPARSE = 3 };
@@ -79,6 +82,8 @@ int dev_reserve(isb_ctx *ctx, int slot, size_t bytes, void **out);
 enum { SCR_NODES = 0, SCR_FLUCT = 1, SCR_T = 2, SCR_E = 3, SCR_M = 4, SCR_FLUCT2 = 5, SCR_OUT = 6, SCR_TMP = 7,
        SCR_TC0 = 8, SCR_TC1 = 9, SCR_S = 10, SCR_S2 = 11, SCR_HIST = 12 };
 
+#define ISB_LOCK(ctx) std::lock_guard<std::recursive_mutex> isb_lock_guard_((ctx)->mtx)
+
 #define ISB_CUDA(ctx, call)                                                                      \
     do {                                                                                         \
         cudaError_t _e = (call);                                                                 \
@@ -129,7 +134,8 @@ int bip_tc_model_init(isb_model *m, const double *W_host_rowmajor_vh);
 void bip_tc_model_free(isb_model *m);
 int bip_tc_ens_init(isb_ens *e);
 void bip_tc_ens_free(isb_ens *e);
-int shard_model_init(isb_model *m, const double *Wrows /*[nb][n] or NULL*/, uint64_t seed, double q);
+int shard_model_init(isb_model *m, const double *Wrows /*[nb][n] or NULL*/, uint64_t seed, double q, double wmax);
+int bip_tc_effective_couplings(isb_model *m, double *W_host_rowmajor_vh);
 int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, int rule, const void *in_full, void *out_block,
                           int n_peers, void *const *peer_blocks, uint64_t seed, uint64_t step_abs, double T);
 int sk_rows_device(isb_ctx *ctx, int n, uint64_t seed, int row0, int nrows, double *d_out);

@@ -32,8 +32,8 @@ from . import _lib
 class _Group:
     """One slice of the replicas with its own gathered matrices and in-flight collective."""
 
-    def __init__(self, r0, R, G, nb, nblocks_local, dev, torch, symm=None, dist_group=None):
-        bf = torch.bfloat16
+    def __init__(self, r0, R, G, nb, nblocks_local, dev, torch, symm=None, dist_group=None, dtype=None):
+        bf = dtype if dtype is not None else torch.bfloat16   # +-1 in the operand format of the model (bf16 or int8)
         self.r0, self.R = r0, R
         self.hv = self.hh = None
         if symm is not None:
@@ -85,12 +85,20 @@ class RowShardedSCA:
         self.dev = torch.device("cuda", self.ctx.device)
         torch.cuda.set_device(self.dev)
         self.ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        # operand format of the spin matrices: int8 +-1 for the int8 digit-plane models (half the bytes to exchange)
+        self.dtype = torch.int8 if prec in _lib.I8_PRECS else torch.bfloat16
+        self.esz = 1 if prec in _lib.I8_PRECS else 2
         self.models = []
+        wmax = 0.0
+        if W is not None and prec in _lib.I8_PRECS:
+            # the fixed-point grid must be the same on every rank: the largest off-diagonal |W| of the whole matrix
+            Wa = np.abs(np.asarray(W, dtype=np.float64))
+            wmax = float((Wa - np.diag(np.diag(Wa))).max())
         for g in self.blocks:
             if W is not None:
                 Wg = np.asarray(W, dtype=np.float64)[g * self.nb:(g + 1) * self.nb, :]
                 hb = None if h is None else 0.5 * np.asarray(h, dtype=np.float64)[g * self.nb:(g + 1) * self.nb]
-                self.models.append(_lib.Model.shard_rows(self.ctx, self.n, self.G, g, Wg, hb, hb, prec))
+                self.models.append(_lib.Model.shard_rows(self.ctx, self.n, self.G, g, Wg, hb, hb, prec, wmax=wmax))
             else:
                 self.models.append(_lib.Model.shard_sk(self.ctx, self.n, self.G, g, int(seed), q, prec))
         symm = None
@@ -119,14 +127,14 @@ class RowShardedSCA:
         else:
             slices = [(0, self.R)]
         try:
-            self.groups = [_Group(r0, Rg, self.G, self.nb, len(self.blocks), self.dev, torch, symm, grp)
+            self.groups = [_Group(r0, Rg, self.G, self.nb, len(self.blocks), self.dev, torch, symm, grp, self.dtype)
                            for r0, Rg in slices if Rg > 0]
         except Exception as exc:  # pragma: no cover - symmetric memory unavailable on this driver
             if not self.fused and self.cstream is None:
                 raise
             self.cstream = None
             self.fused, self.fused_error, self.exchange = False, repr(exc), "nccl"
-            self.groups = [_Group(0, self.R, self.G, self.nb, len(self.blocks), self.dev, torch)]
+            self.groups = [_Group(0, self.R, self.G, self.nb, len(self.blocks), self.dev, torch, dtype=self.dtype)]
         self.launches = 0
         self.gather_bytes = 0
 
@@ -137,7 +145,7 @@ class RowShardedSCA:
         self._drain()
         S = torch.as_tensor(np.ascontiguousarray(S, dtype=np.int8), device=self.dev)
         for gr in self.groups:
-            full = S[gr.r0:gr.r0 + gr.R].view(gr.R, self.G, self.nb).permute(1, 0, 2).contiguous().to(torch.bfloat16)
+            full = S[gr.r0:gr.r0 + gr.R].view(gr.R, self.G, self.nb).permute(1, 0, 2).contiguous().to(self.dtype)
             gr.full_v.copy_(full)
             gr.full_h.copy_(full)
             for i, g in enumerate(self.blocks):
@@ -188,12 +196,12 @@ class RowShardedSCA:
             gr.pending[src_layer] = None
         if self.fused:
             g, hdl = self.blocks[0], (gr.hh if layer == 1 else gr.hv)
-            slab = g * gr.R * self.nb * 2  # byte offset of this rank's block in every gathered matrix
+            slab = g * gr.R * self.nb * self.esz  # byte offset of this rank's block in every gathered matrix
             peers = [int(ptr) + slab for q, ptr in enumerate(hdl.buffer_ptrs) if q != hdl.rank]
             self.models[0].shard_halfstep_fused(gr.R, layer, self.rule, src.data_ptr(), dst.data_ptr() + slab, peers,
                                                 seed, step_abs, T, replica_offset=gr.r0)
             self.launches += 1
-            self.gather_bytes += (self.G - 1) * gr.R * self.nb * 2
+            self.gather_bytes += (self.G - 1) * gr.R * self.nb * self.esz
             hdl.barrier(channel=0)  # all peers' stores have landed before anyone reads the layer
             return
         blk = gr.blk_h if layer == 1 else gr.blk_v
@@ -211,20 +219,20 @@ class RowShardedSCA:
             with torch.cuda.stream(self.cstream):
                 self.cstream.wait_event(ready)
                 for q in range(self.G):
-                    peer = hdl.get_buffer(q, (self.G, gr.R, self.nb), torch.bfloat16)
+                    peer = hdl.get_buffer(q, (self.G, gr.R, self.nb), self.dtype)
                     peer[g].copy_(blk[0], non_blocking=True)
                 hdl.barrier(channel=0)
                 done = torch.cuda.Event()
                 done.record(self.cstream)
             gr.pending[layer] = done
-            self.gather_bytes += (self.G - 1) * blk[0].numel() * 2
+            self.gather_bytes += (self.G - 1) * blk[0].numel() * self.esz
         elif self.distributed:
             # the one real exchange step of this path: [R][nb] per rank -> [G][R][nb] everywhere.  async_op: the
             # collective runs on NCCL's stream after this kernel; the next kernel of the OTHER group is enqueued
             # right behind this one and overlaps it ("pipelined"); "nccl" waits for it at the next half-step.
             gr.pending[layer] = self.dist.all_gather_into_tensor(dst.view(-1), blk[0].view(-1), group=self.group,
                                                                  async_op=True)
-            self.gather_bytes += (self.G - 1) * blk[0].numel() * 2
+            self.gather_bytes += (self.G - 1) * blk[0].numel() * self.esz
         else:
             for i, g in enumerate(self.blocks):
                 dst[g].copy_(blk[i])

@@ -116,3 +116,57 @@ def test_c3_full_size_dense4096_8192_replicas(ctx, synth):
     for r in same:
         Hs = -0.5 * S[r].astype(float) @ J @ S[r].astype(float)
         assert abs(Hs - (E[0][r] + 0.5 * q * N)) < 1e-6 * N
+
+
+@pytest.mark.parametrize("prec", ["i8x3", "bf16x3", "fp16x2"])
+def test_c3_depth_half_steps_against_the_oracle(ctx, orc, synth, prec):
+    """One full SCA step (both half-steps, contraction depth K = 4096: the C3 shape) for 12 replicas against the
+    Float64 oracle (src/OnBipartiteGraph.jl:35-42) with caller-supplied fluctuations.
+
+    int8 digit planes: the contraction is exact, so the result must equal the oracle run on the grid couplings BIT FOR
+    BIT; against the ORIGINAL couplings a decision may differ only where |2(W's + b) - F T| is below the deterministic
+    quantisation bound K x quantum (every coupling is off by at most quantum / 2, each term enters with weight 2).
+    bf16x3 / fp16x2: exact products, fp32 accumulation over K = 4096 terms: a decision may differ only in the band
+    |x| <= 2 K 2^-24 max|partial sum| (each of the K additions rounds to fp32) plus the split error; the band is
+    asserted and the number of differing decisions printed."""
+    L = _lib()
+    N, R = 4096, 12
+    J = synth.sk_J(N, 3)
+    q = 0.5 * 2.0                                  # ~ eigmax(J) / 2 (demo.jl:82) for J ~ N(0, 1/N)
+    W = 0.5 * (J + q * np.eye(N))
+    hb = synth.gaussian(31, N) * 0.05
+    P = {"i8x3": L.PREC_I8X3, "bf16x3": L.PREC_BF16X3, "fp16x2": L.PREC_FP16X2}[prec]
+    m = L.Model.bipartite(ctx, W, hb, hb, P)
+    Weff = m.effective_couplings()
+    S0 = synth.spins(32, R, N)
+    Fv, Fh = synth.logistic(33, (R, 1, N), 1), synth.logistic(33, (R, 1, N), 2)
+    T = 0.6
+    e = L.Ensemble(m, R)
+    e.set_spins(S0)
+    e.set_hidden(S0)
+    e.bip_run(L.BIP_SCA, 1, Fv=Fv, Fh=Fh, fluct_per_replica=True, T=np.array([T]))
+    S, H = e.get_spins(), e.get_hidden()
+    absW = np.abs(W).sum(1).max()
+    if prec == "i8x3":
+        quantum = 2.0 * np.abs(W - Weff)[~np.eye(N, dtype=bool)].max()
+        assert quantum <= 2.0 ** -23 * np.abs(J).max()
+        band = N * quantum                          # 2 x sum_k |dW_k| <= 2 K quantum / 2
+    else:
+        band = 2.0 * N * 2.0 ** -24 * absW + 2.0 * N * np.abs(W - Weff).max()
+    ndiff = 0
+    for r in range(R):
+        if prec == "i8x3":   # exact on the grid couplings
+            xh = 2.0 * orc.bip_aux_bias(Weff, hb, S0[r]) - Fh[r, 0] * T
+            assert np.array_equal(H[r], np.where(xh < 0, -1, 1)), f"replica {r}: hidden layer"
+            xv = 2.0 * orc.bip_local_field(Weff, hb, H[r]) - Fv[r, 0] * T
+            assert np.array_equal(S[r], np.where(xv < 0, -1, 1)), f"replica {r}: visible layer"
+        xh = 2.0 * orc.bip_aux_bias(W, hb, S0[r]) - Fh[r, 0] * T
+        dh = H[r] != np.where(xh < 0, -1, 1)
+        assert np.all(np.abs(xh[dh]) <= band), (r, np.abs(xh[dh]).max(), band)
+        xv = 2.0 * orc.bip_local_field(W, hb, H[r]) - Fv[r, 0] * T
+        dv = S[r] != np.where(xv < 0, -1, 1)
+        assert np.all(np.abs(xv[dv]) <= band), (r, np.abs(xv[dv]).max(), band)
+        ndiff += int(dh.sum() + dv.sum())
+    print(f"\n[{prec}] K = {N}: {ndiff} of {2 * R * N} decisions differ from the Float64 oracle on the original "
+          f"couplings (band {band:.3g})")
+    assert ndiff <= 4

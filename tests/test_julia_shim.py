@@ -181,3 +181,89 @@ def test_enum_values_agree_across_the_layers():
         assert len(names) == len(vals)
         for n, v in zip(names, vals):
             assert enums.get("ISB_" + n) == v, f"IsingModelB200.jl: {n} = {v}, the header says {enums.get('ISB_' + n)}"
+
+
+def _strip_julia(txt):
+    """Source without comments and string contents (enough for the structural checks below)."""
+    out = []
+    for line in txt.split("\n"):
+        s, q, i = "", False, 0
+        while i < len(line):
+            ch = line[i]
+            if q:
+                if ch == "\\":
+                    i += 2
+                    continue
+                if ch == '"':
+                    q = False
+                    s += '"'
+            elif ch == '"':
+                q = True
+                s += '"'
+            elif ch == "#":
+                break
+            else:
+                s += ch
+            i += 1
+        out.append(s.rstrip())
+    return "\n".join(out)
+
+
+def test_shim_blocks_and_brackets_balance():
+    """No julia binary here: at least every block opener has its `end` and every bracket closes."""
+    src = _strip_julia(open(SHIM).read())
+    depth = {"(": 0, "[": 0, "{": 0}
+    pair = {")": "(", "]": "[", "}": "{"}
+    for ch in src:
+        if ch in depth:
+            depth[ch] += 1
+        elif ch in pair:
+            depth[pair[ch]] -= 1
+            assert depth[pair[ch]] >= 0
+    assert depth == {"(": 0, "[": 0, "{": 0}, depth
+    opens = ends = 0
+    stack = []
+    for n, line in enumerate(src.split("\n"), 1):
+        t = line.strip()
+        if not t or t.startswith("abstract type") or t.startswith("@enum"):
+            continue
+        if re.match(r"(module|function|mutable struct|struct|if|for|while|try|let|begin)\b", t) and not re.search(r"\bend$", t):
+            opens += 1
+            stack.append((n, t[:40]))
+        elif re.search(r"\bdo( \w+)?$", t):
+            opens += 1
+            stack.append((n, t[:40]))
+        if re.match(r"end\b", t):
+            ends += 1
+            assert stack, f"line {n}: `end` without an opener"
+            stack.pop()
+    assert opens == ends and not stack, (opens, ends, stack[-3:])
+
+
+def test_shim_keeps_reference_object_semantics():
+    """What the reference's own test needs from the host objects (test/runtests.jl:6-31, src/SpinSystems.jl:61-66,
+    128-137, src/SamplingHelper.jl:64-91): independent deep copies, released handles, setters and assignments that reach
+    the device, streaming samplers on the snapshot entry points, and the MultiSpinFlip sampling methods."""
+    txt = open(SHIM).read()
+    bound = {c[0] for c in julia_ccalls()}
+    for need in ("isb_model_retain", "isb_model_destroy", "isb_ens_clone", "isb_ens_destroy", "isb_ssf_run_snap",
+                 "isb_bip_run_snap"):
+        assert need in bound, need
+    assert len(re.findall(r"Base\.deepcopy_internal\((?:ss)::(SpinSystem|SpinSystemOnBipartiteGraph), dict::IdDict\)", txt)) == 2
+    assert txt.count("finalizer(_release!, ss)") == 4            # both constructors of both system types
+    assert len(re.findall(r"function Base\.setproperty!\(ss::(SpinSystem|SpinSystemOnBipartiteGraph), name::Symbol, v\)", txt)) == 2
+    for setter in ("setSpinConfiguration(ua::UpdatingAlgorithm,", "setCouplingCoefficients(ua::UpdatingAlgorithm,",
+                   "setExternalMagneticField(ua::UpdatingAlgorithm,", "setSpinConfiguration(ua::UpdatingAlgorithmOnBipartiteGraph,",
+                   "setHiddenLayer(ua::UpdatingAlgorithmOnBipartiteGraph,", "setCouplingCoefficients(ua::UpdatingAlgorithmOnBipartiteGraph,",
+                   "setExternalMagneticField(ua::UpdatingAlgorithmOnBipartiteGraph,", "setAuxiliaryBias(ua::UpdatingAlgorithmOnBipartiteGraph,"):
+        assert setter in txt, setter
+    # every device operation of the host objects is preceded by the host -> device check
+    for fn in ("calcEnergy(ss::SpinSystem)", "calcEnergy(ss::SpinSystemOnBipartiteGraph)"):
+        line = next(ln for ln in txt.split("\n") if ln.startswith(fn))
+        assert "_sync!(ss)" in line, fn
+    # the three samplers of src/SamplingHelper.jl (keyword schedule, POSITIONAL schedule for MultiSpinFlip, keyword)
+    assert re.search(r"function makeSampler!\(updatingAlgorithm::SingleSpinFlip\.SingleSpinUpdatingAlgorithm, maxMCSteps::Integer;", txt)
+    assert re.search(r"function makeSampler!\(updatingAlgorithm::MultiSpinFlip\.MultiSpinUpdatingAlgorithm, maxMCSteps::Integer,\s*annealingSchedule::Function", txt)
+    assert re.search(r"function makeSampler!\(updatingAlgorithm::UpdatingAlgorithmOnBipartiteGraph, maxMCSteps::Integer;", txt)
+    assert re.search(r"function update!\(ua::MultiSpinFlip\.MultiSpinUpdatingAlgorithm; rng", txt)
+    assert txt.count("trace_every = 1") >= 3 and txt.count("put!(channel, ua)") == 6     # n + 1 items from each sampler
