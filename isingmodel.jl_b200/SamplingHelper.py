@@ -124,10 +124,18 @@ def makeSampler_(updatingAlgorithm, maxMCSteps, annealingSchedule=None, rng=None
 
     A generator standing in for the Julia ``Channel``: yields ``updatingAlgorithm`` (the same mutable
     object every time) once before the first step and then after every ``stride`` steps (reference:
-    stride = 1, n + 1 items).  All randomness is drawn up front in the reference's order.  For single-spin
-    algorithms the device runs `chunk` steps per library call and records the state after every `stride` steps
-    (isb_ssf_run_snap); the generator replays those snapshots, so `map(calcEnergy, sampler)` (demo.jl:108-115)
-    costs no device round trip per spin.
+    stride = 1, n + 1 items).  All randomness is drawn up front in the reference's order.
+
+    Read-ahead: the device runs up to ``chunk`` steps per library call and records the state after every ``stride``
+    steps (isb_ssf_run_snap / isb_bip_run_snap); the generator replays those snapshots, so
+    ``map(calcEnergy, sampler)`` (demo.jl:108-115) costs no device round trip per spin.  The reference's Channel is
+    unbuffered and steps lazily; the replay keeps what a consumer can observe of that:
+      * every yielded state (spins, energy, fields, temperature) is the state after exactly that step;
+      * if the consumer assigns spins between two items (or, with the default schedule, the temperature), the rest of
+        the chunk is discarded and the run resumes from the consumer's state at the next step;
+      * if the consumer stops early (``break``, ``islice``, ``close()``), the device is put back to the last yielded
+        state, so later ``update_`` / ``run_`` calls continue from what the consumer saw (``chunk=stride`` gives the
+        reference's strict laziness: nothing is computed ahead).
     """
     ua = updatingAlgorithm
     if maxMCSteps < 0:
@@ -136,67 +144,83 @@ def makeSampler_(updatingAlgorithm, maxMCSteps, annealingSchedule=None, rng=None
     rng = _rng(rng)
     T = _schedule(ua, maxMCSteps, annealingSchedule)
     single = isinstance(ua, SingleSpinUpdatingAlgorithm)
+    multi = isinstance(ua, MultiSpinFlip.MultiSpinUpdatingAlgorithm)
+    b = _bip(ua)
     if single:
         n = ua.spinSystem._host_spins.shape[1]
         updatedNodes = rng.integers(0, n, maxMCSteps)              # :39
         fluctuations = ua.distribution.rand(rng, maxMCSteps)       # :40
     else:
-        b = _bip(ua)
+        if multi:
+            ua._sync_in()
         ens = b.spinSystem._ensemble()
         Fv = b.distribution.rand(rng, (maxMCSteps, ens.nv))        # :121
         Fh = b.distribution.rand(rng, (maxMCSteps, ens.nh))        # :122
+    per_yield = max(1, int(stride))
+
+    def run_chunk(k, full, py):
+        """Steps [k, k + full) on the device; returns the list of per-yield snapshots (tuples for ss._set_snapshot)."""
+        if single:
+            ss = ua.spinSystem
+            out = ss._ensemble().ssf_run(ua._rule, full, nodes=updatedNodes[k:k + full],
+                                         fluct=None if ua._rule == _lib.RULE_HOPFIELD else fluctuations[k:k + full],
+                                         T=None if T is None else T[k + 1:k + 1 + full], trace_every=py,
+                                         want_M=False, want_S=True)
+            ss._dev_newer = True
+            return [(out["S"][j], out["E"][j]) for j in range(full // py)]
+        if multi:
+            ua._sync_in()
+        ss = b.spinSystem
+        E, Sv, Sh = ss._ensemble().bip_run(b._rule, full, Fv=Fv[k:k + full], Fh=Fh[k:k + full], T=T[k + 1:k + 1 + full],
+                                           trace_every=py, want_S=True)
+        ss._dev_newer = True
+        return [(Sv[j], Sh[j], E[j]) for j in range(full // py)]
 
     def gen():
         if T is not None:
             ua.temperature = float(T[0])                           # :43
         yield ua                                                   # :44
+        ss = b.spinSystem if not single else ua.spinSystem
         k = 0
         while k < maxMCSteps:
-            if single:
-                # one library call per chunk; the kernel records the spins (and energies) after every `stride`
-                # steps and the Channel contract is replayed from those snapshots
-                ss = ua.spinSystem
-                per_yield = max(1, stride)
-                m = min(maxMCSteps - k, max(per_yield, (chunk // per_yield) * per_yield))
-                full = (m // per_yield) * per_yield
-                if full == 0:
-                    full = m                                       # the last, shorter piece: one yield at its end
-                    per_yield = m
-                out = ss._ensemble().ssf_run(ua._rule, full, nodes=updatedNodes[k:k + full],
-                                             fluct=None if ua._rule == _lib.RULE_HOPFIELD else fluctuations[k:k + full],
-                                             T=None if T is None else T[k + 1:k + 1 + full], trace_every=per_yield,
-                                             want_M=False, want_S=True)
-                ss._dev_newer = True
-                for j in range(full // per_yield):
-                    ss._set_snapshot(out["S"][j], out["E"][j])
-                    if T is not None:
-                        ua.temperature = float(T[k + (j + 1) * per_yield])   # :46
-                    yield ua                                       # :48
-                ss._set_snapshot(None)
-                k += full
-                continue
-            # bipartite / multi-spin: the same replay from kernel-recorded snapshots of both layers
-            b = _bip(ua)
-            ss = b.spinSystem
-            per_yield = max(1, stride)
-            m = min(maxMCSteps - k, max(per_yield, (chunk // per_yield) * per_yield))
-            full = (m // per_yield) * per_yield
+            py = per_yield
+            m = min(maxMCSteps - k, max(py, (chunk // py) * py))
+            full = (m // py) * py
             if full == 0:
-                full = m
-                per_yield = m
-            E, Sv, Sh = ss._ensemble().bip_run(b._rule, full, Fv=Fv[k:k + full], Fh=Fh[k:k + full], T=T[k + 1:k + 1 + full],
-                                               trace_every=per_yield, want_S=True)
-            ss._dev_newer = True
-            for j in range(full // per_yield):
-                ss._set_snapshot(Sv[j], Sh[j], E[j])
-                if b is not ua:
-                    ua.spinSystem._set_snapshot(Sv[j])
-                ua.temperature = float(T[k + (j + 1) * per_yield])     # :128
-                yield ua                                               # :130
-            ss._set_snapshot(None)
-            if b is not ua:
-                ua.spinSystem._set_snapshot(None)
-                ua._sync_back()
-            k += full
+                full = py = m                                      # the last, shorter piece: one yield at its end
+            snaps = run_chunk(k, full, py)
+            done = 0
+            try:
+                for j, snap in enumerate(snaps):
+                    ss._set_snapshot(*snap)
+                    if multi:
+                        ua.spinSystem._set_snapshot(snap[0])
+                    kk = k + (j + 1) * py
+                    if T is not None:
+                        ua.temperature = float(T[kk])              # :46 / :128
+                    yield ua                                       # :48 / :130
+                    done = j + 1
+                    touched = ss._snap is None or ss._snap[0] is not snap[0] or \
+                        (multi and (ua.spinSystem._snap is None or ua.spinSystem._snap[0] is not snap[0]))
+                    if T is not None and annealingSchedule is None and float(ua.temperature) != float(T[kk]):
+                        T[kk:] = float(ua.temperature)             # default schedule n -> ua.temperature, read lazily
+                        touched = True
+                    if touched and done < len(snaps):
+                        break
+            finally:
+                # the device holds the END of the chunk; the consumer saw snapshot `done` (1-based; at a close() or an
+                # exception inside `yield` the one being shown).  Anything but a completed chunk: put the device back.
+                shown = ss._snap
+                complete = done == len(snaps) and shown is not None and shown[0] is snaps[-1][0]
+                if shown is not None and not complete:
+                    ss._restore_snapshot()
+                else:
+                    ss._set_snapshot(None)
+                if multi:
+                    assigned = ua.spinSystem._snap is None         # the consumer assigned the general-graph spins:
+                    ua.spinSystem._set_snapshot(None)              # they reach the embedding at the next step
+                    if not assigned:
+                        ua._sync_back()
+            k += done * py
 
     return gen()

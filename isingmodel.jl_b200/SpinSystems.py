@@ -30,6 +30,15 @@ def _as_spins(x, name):
     return a
 
 
+def _checked_spins(value, shape, name):
+    a = np.atleast_2d(np.asarray(value))
+    if a.shape != shape:
+        raise ValueError(f"{name} has the wrong shape")
+    if not np.all(np.abs(np.asarray(a, dtype=np.float64)) == 1.0):
+        raise ValueError("spins must be +1 / -1")
+    return np.ascontiguousarray(a, dtype=np.int8)
+
+
 def _squeeze(self, arr):
     """Reference objects hold one chain: return the vector / scalar when R == 1 and the input was 1-D."""
     return arr[0] if self._single else arr
@@ -111,6 +120,17 @@ class SpinSystem:
     def _set_snapshot(self, spins2d, energies=None):
         self._snap = None if spins2d is None else (spins2d, energies)
 
+    def _restore_snapshot(self):
+        """End a replay early: the state the consumer last saw becomes the state of the host and of the device."""
+        if self._snap is None:
+            return
+        v = np.ascontiguousarray(self._snap[0], dtype=np.int8).copy()
+        self._snap = None
+        self._host_spins = v
+        self._dev_newer = False
+        if self._ens is not None:
+            self._ens.set_spins(v)
+
     def _query_ensemble(self):
         """The ensemble that holds the state a caller currently sees (the snapshot during a replay)."""
         ens = self._ensemble()
@@ -155,9 +175,8 @@ class SpinSystem:
 
     @spinConfiguration.setter
     def spinConfiguration(self, value):
-        v = np.ascontiguousarray(np.atleast_2d(np.asarray(value)), dtype=np.int8)
-        if v.shape != self._host_spins.shape:
-            raise ValueError("spin configuration has the wrong shape")
+        v = _checked_spins(value, self._host_spins.shape, "spin configuration")   # validated BEFORE anything changes
+        self._snap = None       # during a replay (makeSampler_) the consumer's state wins: the sampler resumes from it
         self._host_spins = v
         self._dev_newer = False
         if self._ens is not None:
@@ -189,8 +208,22 @@ class SpinSystem:
         self._h = h
 
     def __deepcopy__(self, memo):
-        return SpinSystem(self.spinConfiguration.copy(), self._J.copy(), self._h.copy(), device=self._device,
-                          prec=self._prec)
+        """deepcopy(ss) (test/runtests.jl:22-24): an independent system; when this one is already on the device the
+        copy shares the immutable model and gets a device-side clone of the ensemble (isb_ens_clone)."""
+        new = object.__new__(SpinSystem)
+        new.__dict__.update(self.__dict__)
+        new._J, new._h = self._J.copy(), self._h.copy()
+        new._host_spins = np.array(self._spins2d(), dtype=np.int8, copy=True)
+        new._snap = new._query_ens = new._query_loaded = None
+        new._dev_newer = False
+        if self._ens is not None:
+            self._restore_or_keep()
+            new._ens = self._ens.clone()
+        return new
+
+    def _restore_or_keep(self):
+        if self._snap is not None:      # copied in the middle of a replay: the copy starts from what is shown
+            self._restore_snapshot()
 
 
 class UpdatingAlgorithm:
@@ -247,6 +280,19 @@ class SpinSystemOnBipartiteGraph:
     def _set_snapshot(self, visible2d, hidden2d=None, energies=None):
         self._snap = None if visible2d is None else (visible2d, hidden2d, energies)
 
+    def _restore_snapshot(self):
+        """End a replay early: the layers the consumer last saw become the state of the host and of the device."""
+        if self._snap is None:
+            return
+        s = np.ascontiguousarray(self._snap[0], dtype=np.int8).copy()
+        t = np.ascontiguousarray(self._snap[1], dtype=np.int8).copy()
+        self._snap = None
+        self._host_s, self._host_t = s, t
+        self._dev_newer = False
+        if self._ens is not None:
+            self._ens.set_spins(s)
+            self._ens.set_hidden(t)
+
     def _query_ensemble(self):
         ens = self._ensemble()
         if self._snap is None:
@@ -287,10 +333,9 @@ class SpinSystemOnBipartiteGraph:
 
     @spinConfiguration.setter
     def spinConfiguration(self, value):
+        v = _checked_spins(value, self._host_s.shape, "spin configuration")
+        self._restore_snapshot()    # during a replay the other layer keeps the shown state, the sampler resumes from here
         self._pull()
-        v = np.ascontiguousarray(np.atleast_2d(np.asarray(value)), dtype=np.int8)
-        if v.shape != self._host_s.shape:
-            raise ValueError("spin configuration has the wrong shape")
         self._host_s = v
         if self._ens is not None:
             self._ens.set_spins(v)
@@ -304,10 +349,9 @@ class SpinSystemOnBipartiteGraph:
 
     @hiddenLayer.setter
     def hiddenLayer(self, value):
+        v = _checked_spins(value, self._host_t.shape, "hidden layer")
+        self._restore_snapshot()
         self._pull()
-        v = np.ascontiguousarray(np.atleast_2d(np.asarray(value)), dtype=np.int8)
-        if v.shape != self._host_t.shape:
-            raise ValueError("hidden layer has the wrong shape")
         self._host_t = v
         if self._ens is not None:
             self._ens.set_hidden(v)
@@ -330,8 +374,11 @@ class SpinSystemOnBipartiteGraph:
 
     @externalMagneticField.setter
     def externalMagneticField(self, h):
+        h = np.asarray(h, dtype=np.float64)
+        if h.shape != self._h.shape:
+            raise ValueError("external-magnetic-field vector has the wrong shape")
         self._invalidate_model()
-        self._h = np.asarray(h, dtype=np.float64)
+        self._h = h
 
     @property
     def auxiliaryBias(self):
@@ -339,12 +386,24 @@ class SpinSystemOnBipartiteGraph:
 
     @auxiliaryBias.setter
     def auxiliaryBias(self, b):
+        b = np.asarray(b, dtype=np.float64)
+        if b.shape != self._b.shape:
+            raise ValueError("auxiliary-bias vector has the wrong shape")
         self._invalidate_model()
-        self._b = np.asarray(b, dtype=np.float64)
+        self._b = b
 
     def __deepcopy__(self, memo):
-        return SpinSystemOnBipartiteGraph(self.spinConfiguration.copy(), self.hiddenLayer.copy(), self._W.copy(),
-                                          self._h.copy(), self._b.copy(), device=self._device, prec=self._prec)
+        """deepcopy(ss) (test/runtests.jl:30-31): shares the immutable device model, clones the ensemble."""
+        self._restore_snapshot()
+        self._pull()
+        new = object.__new__(SpinSystemOnBipartiteGraph)
+        new.__dict__.update(self.__dict__)
+        new._W, new._h, new._b = self._W.copy(), self._h.copy(), self._b.copy()
+        new._host_s, new._host_t = self._host_s.copy(), self._host_t.copy()
+        new._snap = new._query_ens = new._query_loaded = None
+        if self._ens is not None:
+            new._ens = self._ens.clone()
+        return new
 
 
 class UpdatingAlgorithmOnBipartiteGraph:

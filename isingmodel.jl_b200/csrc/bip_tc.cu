@@ -25,11 +25,13 @@
 // Operand formats (template parameter FMT): 0 = bf16 terms, 1 = fp16 terms of the pre-scaled couplings, 2 = INT8 DIGIT
 // PLANES (ISB_PREC_I8X*): W is rounded once to a P x 8-bit fixed-point grid (quantum q0 = 2^e, a power of two) and
 // stored as P planes of balanced base-256 digits; spins are int8 +-1 (the ensemble's canonical arrays ARE the A
-// operand); tcgen05.mma.kind::i8 accumulates every plane EXACTLY in its own int32 TMEM accumulator (4 slots of 128
-// columns, rotating, so the next tile's first plane runs under this tile's epilogue) and the epilogue recombines
-// field = q0 * sum_t 256^(P-1-t) acc_t — no rounding anywhere in the contraction, at any K.  One int8 pass costs half a
-// bf16 pass (2x tensor rate, half the operand bytes), so 24-bit couplings cost 1.5 bf16-pass equivalents (bf16x3: 3,
-// fp16x2: 2).  A square model's diagonal (the pinning term q/2 of the MultiSpinFlip embedding, demo.jl:82-90, 64x
+// operand).  The P planes of a tile of `bn` units are STACKED along the MMA's N dimension — the coupling matrix is
+// stored tile-major [tile][plane][unit in tile][K], so one tcgen05.mma.kind::i8 of N = P * bn <= 256 columns contracts
+// the spin tile with all planes at once (the A tile is fetched and read from shared memory once per K block, not once
+// per plane) and leaves plane t EXACTLY in the int32 TMEM columns [t * bn, (t + 1) * bn) of the tile's accumulator stage;
+// the epilogue recombines field = q0 * sum_t 256^(P-1-t) acc_t — no rounding anywhere in the contraction, at any K.
+// One int8 pass costs half a bf16 pass (2x tensor rate, half the operand bytes), so 24-bit couplings cost 1.5 bf16-pass
+// equivalents (bf16x3: 3, fp16x2: 2).  A square model's diagonal (the pinning term q/2 of the MultiSpinFlip embedding, demo.jl:82-90, 64x
 // larger than the couplings) is split off and added in the epilogue from the unit's own input spin, so that the
 // fixed-point grid is scaled to the off-diagonal couplings.
 #include <cuda.h>
@@ -49,7 +51,6 @@ namespace isb {
 constexpr int TC_BM = 128;      // replicas per tile (UMMA M)
 constexpr int TC_BK = 64;       // K elements per stage, 16-bit operands (128 bytes = one swizzle span)
 constexpr int TC_BK8 = 128;     // K elements per stage, int8 digit planes (the same 128 bytes)
-constexpr int TC_I8_SLOT = 128; // int8 mode: TMEM columns per accumulator slot (4 slots), = the widest tile
 constexpr int TC_PMAX = 4;      // coupling terms / digit planes
 constexpr int TC_BN_MAX = 256;  // units per tile (UMMA N), runtime BN <= 256, multiple of 16
 constexpr int TC_STAGES = 4;     // smem ring slots, single CTAs (16 KiB of A + 32 KiB of B each)
@@ -114,6 +115,7 @@ struct TcEns {
 // One layer update (= one GEMM shape): which units are sampled, from which input layer
 struct TcLayer {
     int nout, kin, bn, n_tiles, num_kb;
+    int bn_mma;       // N of the MMA = rows of the coupling tile: bn, or P * bn for stacked int8 digit planes
     int u_off;        // global index of output unit 0 (row-sharded models: this rank's block offset), else 0
     int kb_per_blk;   // K blocks per slab of the A operand (block-major [G][R][nb] spin matrices), else num_kb
     void *out_bf;            // [R][ldo] the sampled layer in the operand format (bf16 / fp16 / int8 +-1; on entry: its
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
     uint64_t *full_bar = bars;                     // [NST]
     uint64_t *empty_bar = bars + NST;        // [NST]
     uint64_t *tfull_bar = bars + 2 * NST;    // [2]
-    uint64_t *tempty_bar = bars + 2 * NST + 2;  // [4] (two accumulator stages; int8 mode: four rotating slots)
+    uint64_t *tempty_bar = bars + 2 * NST + 2;  // [2] (two accumulator stages)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 7);
     uint64_t *sig_bar = bars + 2 * NST + 8;  // [2][TC_SIG_MAX] chain-resident mode: epilogue -> producer progress
 
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) mbar_init(&tfull_bar[a], 1);
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 2; ++a)
             mbar_init(&tempty_bar[a], CG * TC_EPI_WARPS);  // pair: the epilogue warps of both CTAs release the leader's
         if (p.persist)
             for (int i = 0; i < 2 * TC_SIG_MAX; ++i) mbar_init(&sig_bar[i], TC_EPI_WARPS);
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 const int pl = 1 - job.layer;   // the layer sampled by the previous half-step = this one's input
                 const uint32_t dep_par = (uint32_t)((job.hs >> 1) - (job.layer == 1 ? 1 : 0)) & 1u;
                 int waited = -1;
-                const int bnc = L.bn / CG;      // rows of the coupling tile this CTA loads
+                const int bnc = L.bn_mma / CG;  // rows of the coupling tile this CTA loads
                 const uint32_t tx = (uint32_t)(TC_A_BYTES + bnc * 128);
 #ifdef ISB_TC_PROBE_K1  // timing probe only: one K block per tile = the epilogue's cost without the contraction
                 const int num_kb = 1;
@@ -483,10 +485,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 const int num_kb = L.num_kb;
 #endif
                 // 16-bit terms: K block outer, term inner (all terms accumulate into one accumulator).  int8 digit
-                // planes: plane outer, K block inner (each plane has its own accumulator slot, and the next tile's
-                // first plane may start while this tile's epilogue still reads the other slots).
-                const int n_outer = I8 ? p.P : 1, n_inner = I8 ? 1 : p.P;
-                for (int to = 0; to < n_outer; ++to) {
+                // planes: one stacked coupling tile per K block (all planes in one MMA).
+                const int n_inner = I8 ? 1 : p.P;
+                {
                 int kq = 0, kr = 0;             // kb = kq * kb_per_blk + kr (slab of the A operand, block within it)
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (dep) {
@@ -498,14 +499,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                         }
                     }
                     for (int ti = 0; ti < n_inner; ++ti) {
-                        const int t = I8 ? to : ti;
+                        const int t = ti;
                         tc_wait1<CG>(&empty_bar[s], ph ^ 1u);
                         unsigned char *sa = smem + (size_t)s * STB;
                         if (elect_one()) {
                             if constexpr (CG == 1) {
                                 mbar_arrive_expect_tx(&full_bar[s], tx);
                                 tma_load_3d(sa, &maps.A[job.layer], kr * BK, job.m0, kq, &full_bar[s]);
-                                tma_load_2d(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * BK, job.n_blk * L.bn, &full_bar[s]);
+                                tma_load_2d(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * BK, job.n_blk * L.bn_mma, &full_bar[s]);
                             } else {
                                 const uint32_t lbar = mapa_rank0(&full_bar[s]);
                                 if (leader)
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                                     mbar_arrive_cluster_addr(lbar);
 #endif
                                 tma_load_3d_cg2(sa, &maps.A[job.layer], kr * BK, job.m0, kq, lbar);
-                                tma_load_2d_cg2(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * BK, job.n_blk * L.bn + crank * bnc, lbar);
+                                tma_load_2d_cg2(sa + TC_A_BYTES, &maps.B[job.layer][t], kb * BK, job.n_blk * L.bn_mma + crank * bnc, lbar);
                             }
                         }
                         __syncwarp();
@@ -556,25 +557,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             while (jobs.next(p, job)) {
                 const TcLayer &L = p.L[job.layer];
-                const uint32_t idesc = I8 ? umma_idesc_i8(TC_BM * CG, L.bn) : umma_idesc_bf16(TC_BM * CG, L.bn, F16 ? 1u : 0u);
+                const uint32_t idesc = I8 ? umma_idesc_i8(TC_BM * CG, L.bn_mma) : umma_idesc_bf16(TC_BM * CG, L.bn_mma, F16 ? 1u : 0u);
 #ifdef ISB_TC_PROBE_K1
                 const int num_kb = 1;
 #else
                 const int num_kb = L.num_kb;
 #endif
                 const int a = tl & 1;
-                // 16-bit terms: one accumulator stage per tile, all K blocks x terms into it.  int8: one slot per plane.
-                const int n_outer = I8 ? p.P : 1, iters = I8 ? num_kb : num_kb * p.P;
-                for (int to = 0; to < n_outer; ++to) {
-                    uint32_t d_tmem;
-                    if constexpr (I8) {
-                        const uint32_t use = tl * (uint32_t)p.P + (uint32_t)to;   // slot use counter: slot = use mod 4
-                        tc_wait1<CG>(&tempty_bar[use & 3u], ((use >> 2) & 1u) ^ 1u);  // epilogue has drained this slot
-                        d_tmem = tmem_u + (use & 3u) * (uint32_t)TC_I8_SLOT;
-                    } else {
-                        tc_wait1<CG>(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
-                        d_tmem = tmem_u + (uint32_t)(a * TC_BN_MAX);
-                    }
+                // one accumulator stage per tile: all K blocks x terms (16-bit), or the stacked planes (int8), into it
+                const int iters = I8 ? num_kb : num_kb * p.P;
+                {
+                    tc_wait1<CG>(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                    const uint32_t d_tmem = tmem_u + (uint32_t)(a * TC_BN_MAX);
                     tc_fence_after();
                     for (int i = 0; i < iters; ++i) {
                         tc_wait1<CG>(&full_bar[s], ph);
@@ -652,8 +646,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
               const int rr = row_ok ? r : job.m0;   // rows without a replica read / compute on a valid row, store nothing
               int8_t *out8 = reinterpret_cast<int8_t *>(L.out_bf) + (int64_t)rr * L.ldo + tile_u0;
               const int8_t *in8 = L.in_diag ? L.in_diag + (int64_t)rr * L.ld_in + tile_u0 : nullptr;
-              const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
-              const uint32_t use0 = tl * (uint32_t)p.P;
+              const uint32_t tq = taddr_t;          // plane t of the tile: columns [t * bn, (t + 1) * bn) of stage a
+              const uint32_t pstride = (uint32_t)L.bn;
               for (int g = 0; g * TC_HALVES < nchunks; ++g) {
                 const int c = g * TC_HALVES + half;
                 if (c < nfull) {
@@ -667,7 +661,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                   }
                   for (int t = 0; t < p.P; ++t) {
                       uint32_t v[16];
-                      tmem_ld16(tq + ((use0 + (uint32_t)t) & 3u) * (uint32_t)TC_I8_SLOT + (uint32_t)(c * 16), v);
+                      tmem_ld16(tq + (uint32_t)t * pstride + (uint32_t)(c * 16), v);
                       const float sf = p.i8_sf[t];
 #pragma unroll
                       for (int j = 0; j < 16; ++j) xf[j] = fmaf((float)(int)v[j], sf, xf[j]);
@@ -702,7 +696,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                   for (int j = 0; j < 16; ++j) xd[j] = 0.0;
                   for (int t = 0; t < p.P; ++t) {
                       uint32_t v[16];
-                      tmem_ld16(tq + ((use0 + (uint32_t)t) & 3u) * (uint32_t)TC_I8_SLOT + (uint32_t)(c * 16), v);
+                      tmem_ld16(tq + (uint32_t)t * pstride + (uint32_t)(c * 16), v);
                       const double sd = p.i8_sd[t];
 #pragma unroll
                       for (int j = 0; j < 16; ++j) xd[j] = fma((double)(int)v[j], sd, xd[j]);
@@ -911,14 +905,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                const int nrel = I8 ? p.P : 1;      // int8: one slot per digit plane
-                for (int t = 0; t < nrel; ++t) {
-                    uint64_t *tb = &tempty_bar[I8 ? (int)((tl * (uint32_t)p.P + (uint32_t)t) & 3u) : a];
-                    if (CG == 2 && !leader)
-                        mbar_arrive_cluster_addr(mapa_rank0(tb));
-                    else
-                        mbar_arrive(tb);
-                }
+                uint64_t *tb = &tempty_bar[a];
+                if (CG == 2 && !leader)
+                    mbar_arrive_cluster_addr(mapa_rank0(tb));
+                else
+                    mbar_arrive(tb);
             }
             if (p.persist && !fine) {
                 fence_proxy_async_global();
@@ -1123,6 +1114,28 @@ static int prec_terms(int prec) {
 }
 static bool prec_is_i8(int prec) { return prec == ISB_PREC_I8X2 || prec == ISB_PREC_I8X3 || prec == ISB_PREC_I8X4; }
 
+// Units per tile of the stacked int8 layout (fixed when the model is built: it is part of the storage order).  The MMA
+// takes N = P * bn <= 256 columns; a tile costs its N columns of tensor time plus a fixed part (the A tile is read once
+// per K block whatever N is, the accumulator hand-over), so minimise tiles x (N + 32) over the multiples of 16.
+static int i8_pick_bn(int nout, int P) {
+    if (const char *env = getenv("ISB_I8_BN")) {
+        const int v = atoi(env);
+        if (v >= 16 && v % 16 == 0 && v * P <= TC_BN_MAX) return v;
+    }
+    int best = 16;
+    long best_cost = 0;
+    for (int bn = 16; bn * P <= TC_BN_MAX; bn += 16) {
+        const long cost = (long)((nout + bn - 1) / bn) * (bn * P + 32);
+        if (best_cost == 0 || cost <= best_cost) {
+            best = bn;
+            best_cost = cost;
+        }
+    }
+    return best;
+}
+// row of (unit u, plane t) in the stacked matrix
+__host__ __device__ inline int64_t i8_stack_row(int u, int t, int bn, int P) { return ((int64_t)(u / bn) * P + t) * bn + u % bn; }
+
 // int8 digit planes of a bipartite model (host side): both orientations, the diagonal of a square model split off when
 // it dominates the couplings (the pinning term of the MultiSpinFlip embedding)
 static int bip_tc_model_init_i8(isb_model *m, TcModel *t, const double *W) {
@@ -1140,10 +1153,12 @@ static int bip_tc_model_init_i8(isb_model *m, TcModel *t, const double *W) {
     const long long maxint = i8_max_int(P);
     t->ldkv = tc_pitch(nv, 1);
     t->ldkh = tc_pitch(nh, 1);
-    t->bn_h = pick_bn(nh, TC_I8_SLOT);
-    t->bn_v = pick_bn(nv, TC_I8_SLOT);
-    t->rows_t = nh; t->cols_t = nv; t->rows_n = nv; t->cols_n = nh;
-    std::vector<std::vector<int8_t>> wt(P, std::vector<int8_t>((size_t)nh * t->ldkv, 0)), wn(P, std::vector<int8_t>((size_t)nv * t->ldkh, 0));
+    t->bn_h = i8_pick_bn(nh, P);
+    t->bn_v = i8_pick_bn(nv, P);
+    // stacked storage: [tile][plane][unit in tile][K]; rows of the padding units of the last tile stay zero
+    t->rows_t = (nh + t->bn_h - 1) / t->bn_h * t->bn_h * P; t->cols_t = nv;
+    t->rows_n = (nv + t->bn_v - 1) / t->bn_v * t->bn_v * P; t->cols_n = nh;
+    std::vector<int8_t> wt((size_t)t->rows_t * t->ldkv, 0), wn((size_t)t->rows_n * t->ldkh, 0);
     std::vector<double> dg;
     if (split) dg.assign((size_t)nv, 0.0);
     for (int i = 0; i < nv; ++i)
@@ -1156,16 +1171,14 @@ static int bip_tc_model_init_i8(isb_model *m, TcModel *t, const double *W) {
             int8_t d[TC_PMAX];
             i8_digits(i8_quantize(w, t->q0, maxint), P, d);
             for (int term = 0; term < P; ++term) {
-                wt[term][(size_t)j * t->ldkv + i] = d[term];
-                wn[term][(size_t)i * t->ldkh + j] = d[term];
+                wt[(size_t)i8_stack_row(j, term, t->bn_h, P) * t->ldkv + i] = d[term];
+                wn[(size_t)i8_stack_row(i, term, t->bn_v, P) * t->ldkh + j] = d[term];
             }
         }
-    for (int term = 0; term < P; ++term) {
-        ISB_CUDA(ctx, cudaMalloc(&t->Wt[term], wt[term].size()));
-        ISB_CUDA(ctx, cudaMalloc(&t->Wn[term], wn[term].size()));
-        ISB_CUDA(ctx, cudaMemcpy(t->Wt[term], wt[term].data(), wt[term].size(), cudaMemcpyHostToDevice));
-        ISB_CUDA(ctx, cudaMemcpy(t->Wn[term], wn[term].data(), wn[term].size(), cudaMemcpyHostToDevice));
-    }
+    ISB_CUDA(ctx, cudaMalloc(&t->Wt[0], wt.size()));
+    ISB_CUDA(ctx, cudaMalloc(&t->Wn[0], wn.size()));
+    ISB_CUDA(ctx, cudaMemcpy(t->Wt[0], wt.data(), wt.size(), cudaMemcpyHostToDevice));
+    ISB_CUDA(ctx, cudaMemcpy(t->Wn[0], wn.data(), wn.size(), cudaMemcpyHostToDevice));
     if (split) {
         std::vector<float> dgf(((size_t)nv + 15) / 16 * 16, 0.f);
         for (int i = 0; i < nv; ++i) dgf[i] = (float)dg[i];
@@ -1225,10 +1238,11 @@ int bip_tc_model_init(isb_model *m, const double *W /*[nv][nh] row-major*/) {
     }
     }
     for (int term = 0; term < TC_PMAX; ++term) {
-        const int src = term < t->P ? term : 0;
-        int rc = make_map(ctx, &t->mapWt[term], t->Wt[src], nh, nv, t->ldkv, t->bn_h, esz);
+        const int src = (term < t->P && !t->i8) ? term : 0;
+        const int sp = t->i8 ? t->P : 1;   // stacked planes: the box spans all planes of a tile
+        int rc = make_map(ctx, &t->mapWt[term], t->Wt[src], t->rows_t, t->cols_t, t->ldkv, t->bn_h * sp, esz);
         if (rc) return rc;
-        rc = make_map(ctx, &t->mapWn[term], t->Wn[src], nv, nh, t->ldkh, t->bn_v, esz);
+        rc = make_map(ctx, &t->mapWn[term], t->Wn[src], t->rows_n, t->cols_n, t->ldkh, t->bn_v * sp, esz);
         if (rc) return rc;
     }
     int rc = make_float_bias(ctx, m->bb64, nh, &t->bias_hf);
@@ -1243,14 +1257,15 @@ int bip_tc_effective_couplings(isb_model *m, double *Wout) {
     TcModel *t = (TcModel *)m->tc;
     const int nv = m->nv, nh = m->nh;
     const size_t esz = t->i8 ? 1 : 2;
-    std::vector<unsigned char> buf((size_t)nv * t->ldkh * esz);
+    std::vector<unsigned char> buf((size_t)t->rows_n * t->ldkh * esz);
     std::fill(Wout, Wout + (size_t)nv * nh, 0.0);
     for (int term = 0; term < t->P; ++term) {
-        ISB_CUDA(ctx, cudaMemcpy(buf.data(), t->Wn[term], buf.size(), cudaMemcpyDeviceToHost));
+        if (!t->i8 || term == 0)
+            ISB_CUDA(ctx, cudaMemcpy(buf.data(), t->Wn[t->i8 ? 0 : term], buf.size(), cudaMemcpyDeviceToHost));
         const double wgt = t->i8 ? t->q0 * pow(256.0, t->P - 1 - term) : 1.0 / t->wscale;
         for (int i = 0; i < nv; ++i)
             for (int j = 0; j < nh; ++j) {
-                const size_t k = (size_t)i * t->ldkh + j;
+                const size_t k = (size_t)(t->i8 ? i8_stack_row(i, term, t->bn_v, t->P) : i) * t->ldkh + j;
                 double v;
                 if (t->i8) {
                     v = (double)reinterpret_cast<const int8_t *>(buf.data())[k];
@@ -1327,7 +1342,7 @@ void bip_tc_ens_free(isb_ens *e) {
 // Coupling tensor maps of orientation `orient` (1: Wt, hidden update; 0: Wn, visible update) whose box holds `bn`
 // rows of W (the tile width, or half of it when a CTA pair shares the tile)
 static int get_maps_b(isb_ctx *ctx, TcModel *t, int orient, int bn, CUtensorMap out[TC_PMAX]) {
-    const int dflt = orient == 1 ? t->bn_h : t->bn_v;
+    const int dflt = (orient == 1 ? t->bn_h : t->bn_v) * (t->i8 ? t->P : 1);
     const int esz = t->i8 ? 1 : 2;
     if (bn == dflt) {
         for (int i = 0; i < TC_PMAX; ++i) out[i] = orient == 1 ? t->mapWt[i] : t->mapWn[i];
@@ -1342,7 +1357,7 @@ static int get_maps_b(isb_ctx *ctx, TcModel *t, int orient, int bn, CUtensorMap 
     c.orient = orient;
     c.bn = bn;
     for (int i = 0; i < TC_PMAX; ++i) {
-        const int src = i < t->P ? i : 0;
+        const int src = (i < t->P && !t->i8) ? i : 0;
         int rc = orient == 1 ? make_map(ctx, &c.m[i], t->Wt[src], t->rows_t, t->cols_t, t->ldkv, bn, esz)
                              : make_map(ctx, &c.m[i], t->Wn[src], t->rows_n, t->cols_n, t->ldkh, bn, esz);
         if (rc) return rc;
@@ -1353,10 +1368,11 @@ static int get_maps_b(isb_ctx *ctx, TcModel *t, int orient, int bn, CUtensorMap 
 }
 
 static void fill_layer(TcLayer &L, int nout, int kin, int bn, void *out_bf, int64_t ldo, const double *bias,
-                       const float *bias_f, const double *F, uint32_t domain, int bk = TC_BK) {
+                       const float *bias_f, const double *F, uint32_t domain, int bk = TC_BK, int planes = 1) {
     L.nout = nout;
     L.kin = kin;
     L.bn = bn;
+    L.bn_mma = bn * planes;
     L.n_tiles = (nout + bn - 1) / bn;
     L.num_kb = (kin + bk - 1) / bk;
     L.diag_f = nullptr;
@@ -1434,21 +1450,22 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     bool persist = rows >= 96;
     if (const char *env = getenv("ISB_TC_PERSIST")) persist = atoi(env) != 0 && e->R >= 1;
     // tile widths: least padding per CTA in chain-resident mode, fewest (waves x width) otherwise
-    const int bn_max = t->i8 ? TC_I8_SLOT : TC_BN_MAX;
-    const int bn_h = persist ? t->bn_h : pick_bn_waves(m->nh, m_tiles, ctx->num_sms / cg, bn_max);
-    const int bn_v = persist ? t->bn_v : pick_bn_waves(m->nv, m_tiles, ctx->num_sms / cg, bn_max);
+    // (int8 digit planes: the tile width is part of the stacked storage order, fixed when the model was built)
+    const int sp = t->i8 ? t->P : 1;
+    const int bn_h = (persist || t->i8) ? t->bn_h : pick_bn_waves(m->nh, m_tiles, ctx->num_sms / cg);
+    const int bn_v = (persist || t->i8) ? t->bn_v : pick_bn_waves(m->nv, m_tiles, ctx->num_sms / cg);
     TcMaps maps;
     maps.A[1] = s->mapSv;
     maps.A[0] = s->mapSh;
-    int rcm = get_maps_b(ctx, t, 1, bn_h / cg, maps.B[1]);
+    int rcm = get_maps_b(ctx, t, 1, bn_h * sp / cg, maps.B[1]);
     if (rcm) return rcm;
-    rcm = get_maps_b(ctx, t, 0, bn_v / cg, maps.B[0]);
+    rcm = get_maps_b(ctx, t, 0, bn_v * sp / cg, maps.B[0]);
     if (rcm) return rcm;
     TcParams p{};
     p.cg = cg;
     const int bk = t->i8 ? TC_BK8 : TC_BK;
-    fill_layer(p.L[1], m->nh, m->nv, bn_h, s->Sh, t->i8 ? e->ldh : t->ldkh, m->bb64, t->bias_hf, d_Fh, DOM_BIP_HIDDEN, bk);
-    fill_layer(p.L[0], m->nv, m->nh, bn_v, s->Sv, t->i8 ? e->lds : t->ldkv, m->hb64, t->bias_vf, d_Fv, DOM_BIP_VISIBLE, bk);
+    fill_layer(p.L[1], m->nh, m->nv, bn_h, s->Sh, t->i8 ? e->ldh : t->ldkh, m->bb64, t->bias_hf, d_Fh, DOM_BIP_HIDDEN, bk, sp);
+    fill_layer(p.L[0], m->nv, m->nh, bn_v, s->Sv, t->i8 ? e->lds : t->ldkv, m->hb64, t->bias_vf, d_Fv, DOM_BIP_VISIBLE, bk, sp);
     if (t->diag_d) {  // square model with the diagonal split off: unit u's own input spin is column u of the input layer
         p.L[1].diag_f = p.L[0].diag_f = t->diag_f;
         p.L[1].diag_d = p.L[0].diag_d = t->diag_d;
@@ -1547,10 +1564,8 @@ __global__ void shard_fill_kernel(int n, int row0, int nrows, uint64_t seed, dou
 }
 // int8 digit planes of the same rows: off-diagonal couplings on the grid q0, the diagonal kept apart (on the grid too)
 __global__ void shard_fill_i8_kernel(int n, int row0, int nrows, uint64_t seed, double q, const double *Wrows, int P,
-                                     double q0, long long maxint, int8_t *p0, int8_t *p1, int8_t *p2, int8_t *p3,
-                                     double *diag_d, float *diag_f) {
+                                     double q0, long long maxint, int8_t *stack, int bn, double *diag_d, float *diag_f) {
     const int64_t total = (int64_t)nrows * n;
-    int8_t *pl[TC_PMAX] = {p0, p1, p2, p3};
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(idx / n), c = (int)(idx % n);
         const double w = Wrows ? Wrows[idx] : 0.5 * (sk_coupling(seed, n, row0 + r, c) + (row0 + r == c ? q : 0.0));
@@ -1562,7 +1577,7 @@ __global__ void shard_fill_i8_kernel(int n, int row0, int nrows, uint64_t seed, 
         } else {
             i8_digits(i8_quantize(w, q0, maxint), P, d);
         }
-        for (int t = 0; t < P; ++t) pl[t][idx] = d[t];
+        for (int t = 0; t < P; ++t) stack[i8_stack_row(r, t, bn, P) * n + c] = d[t];   // [tile][plane][unit][K]
     }
 }
 __global__ void sk_rows_kernel(int n, uint64_t seed, int row0, int nrows, double *out) {
@@ -1586,15 +1601,21 @@ int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q,
     const int esz = t->i8 ? 1 : 2;
     const int n = m->nv, nb = m->shard_nb;
     t->ldkv = t->ldkh = n;
-    t->bn_h = t->bn_v = pick_bn(nb, t->i8 ? TC_I8_SLOT : TC_BN_MAX);
-    t->rows_t = t->rows_n = nb; t->cols_t = t->cols_n = n;
+    t->bn_h = t->bn_v = t->i8 ? i8_pick_bn(nb, t->P) : pick_bn(nb);
+    t->rows_t = t->rows_n = t->i8 ? (nb + t->bn_h - 1) / t->bn_h * t->bn_h * t->P : nb;
+    t->cols_t = t->cols_n = n;
     const size_t elems = (size_t)nb * n;
     double *dW = nullptr;
     if (Wrows) {
         ISB_CUDA(ctx, cudaMalloc(&dW, elems * sizeof(double)));
         ISB_CUDA(ctx, cudaMemcpyAsync(dW, Wrows, elems * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
-    for (int term = 0; term < t->P; ++term) ISB_CUDA(ctx, cudaMalloc(&t->Wt[term], elems * esz));
+    if (t->i8) {
+        ISB_CUDA(ctx, cudaMalloc(&t->Wt[0], (size_t)t->rows_t * n));
+        ISB_CUDA(ctx, cudaMemsetAsync(t->Wt[0], 0, (size_t)t->rows_t * n, ctx->stream));
+    } else {
+        for (int term = 0; term < t->P; ++term) ISB_CUDA(ctx, cudaMalloc(&t->Wt[term], elems * esz));
+    }
     if (t->i8) {
         // The grid must be the same on every rank (the trajectory may not depend on the sharding): the caller passes
         // the largest off-diagonal |W| of the WHOLE matrix (wmax); for the synthetic instance it is bounded a priori:
@@ -1609,8 +1630,7 @@ int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q,
         ISB_CUDA(ctx, cudaMalloc(&t->diag_d, (size_t)nb * sizeof(double)));
         ISB_CUDA(ctx, cudaMalloc(&t->diag_f, (size_t)nb * sizeof(float)));
         shard_fill_i8_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(
-            n, m->shard_g * nb, nb, seed, q, dW, t->P, t->q0, i8_max_int(t->P), (int8_t *)t->Wt[0], (int8_t *)t->Wt[1],
-            (int8_t *)t->Wt[2], (int8_t *)t->Wt[3], t->diag_d, t->diag_f);
+            n, m->shard_g * nb, nb, seed, q, dW, t->P, t->q0, i8_max_int(t->P), (int8_t *)t->Wt[0], t->bn_h, t->diag_d, t->diag_f);
     } else {
         shard_fill_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, m->shard_g * nb, nb, seed, q, dW, t->P, t->Wt[0],
                                                                      t->Wt[1], t->Wt[2]);
@@ -1619,8 +1639,8 @@ int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q,
     ISB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (dW) cudaFree(dW);
     for (int term = 0; term < TC_PMAX; ++term) {
-        const int src = term < t->P ? term : 0;
-        int rc = make_map(ctx, &t->mapWt[term], t->Wt[src], nb, n, n, t->bn_h, esz);
+        const int src = (term < t->P && !t->i8) ? term : 0;
+        int rc = make_map(ctx, &t->mapWt[term], t->Wt[src], t->rows_t, n, n, t->bn_h * (t->i8 ? t->P : 1), esz);
         if (rc) return rc;
     }
     int rc = make_float_bias(ctx, m->bb64, nb, &t->bias_hf);
@@ -1639,14 +1659,15 @@ int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, in
     maps.A[1 - layer] = maps.A[layer];
     const int cg = tc_cta_group();
     const int m_tiles = (R + TC_BM * cg - 1) / (TC_BM * cg);
-    const int bn = pick_bn_waves(m->shard_nb, m_tiles, ctx->num_sms / cg, t->i8 ? TC_I8_SLOT : TC_BN_MAX);
-    rc = get_maps_b(ctx, t, 1, bn / cg, maps.B[1]);  // W is symmetric: one orientation serves both half-steps
+    const int sp = t->i8 ? t->P : 1;   // int8: the tile width is part of the stacked storage order
+    const int bn = t->i8 ? t->bn_h : pick_bn_waves(m->shard_nb, m_tiles, ctx->num_sms / cg);
+    rc = get_maps_b(ctx, t, 1, bn * sp / cg, maps.B[1]);  // W is symmetric: one orientation serves both half-steps
     if (rc) return rc;
     for (int i = 0; i < TC_PMAX; ++i) maps.B[0][i] = maps.B[1][i];
     TcParams p{};
     fill_layer(p.L[layer], m->shard_nb, m->nv, bn, out_block, m->shard_nb,
                layer == 1 ? m->bb64 : m->hb64, layer == 1 ? t->bias_hf : t->bias_vf, nullptr,
-               layer == 1 ? DOM_BIP_HIDDEN : DOM_BIP_VISIBLE, bk);
+               layer == 1 ? DOM_BIP_HIDDEN : DOM_BIP_VISIBLE, bk, sp);
     p.L[layer].u_off = m->shard_g * m->shard_nb;
     p.L[layer].num_kb = m->nv / bk;
     p.L[layer].kb_per_blk = m->shard_nb / bk;
