@@ -312,14 +312,15 @@ def cpu_baselines(fn, seconds):
             "one_thread": {"value": v1, "unit": UNIT, "cores": 1, "sample": sd1}}
 
 
-def reference_arm(args):
+def reference_arm(args, out):
     """--impl reference: the reference's CPU algorithm (oracle port; Julia is not installed) on all host cores, on the
     headline's config, each step a bounded sample of the workload."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
     which = "c2" if args.workload == "all" else args.workload
     if which == "c5":
-        print(json.dumps({"impl": "reference", "unavailable": "config 5 (N=65536: J is 32 GiB in Float64) is GPU-only; see --workload c3 for the CPU arm of the same algorithm"}))
+        out.write(json.dumps({"impl": "reference", "unavailable": "config 5 (N=65536: J is 32 GiB in Float64) is GPU-only; see --workload c3 for the CPU arm of the same algorithm"}) + "\n")
+        out.flush()
         return 0
     if which in ("c3", "c4"):
         W, h, b, R, sched, desc0 = sca_workload(which)
@@ -346,7 +347,8 @@ def reference_arm(args):
                  "gpu_launches": 0,
                  "note": "CPU restatement of the reference algorithm (Julia unavailable); ms_per_step extrapolated from "
                          "the bounded sample of each step"})
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     return 0
 
 
@@ -689,10 +691,12 @@ def run_c5(rt, args, prec_name, steps, warmup):
     t_mma, t_link = flops * P / (pk["tc_burst"] * 1e12), gather / 770e9
     ach = flops / half_s / 1e12
     nccl_lines = []
-    if rt.nccl_log and os.path.exists(rt.nccl_log):
-        for ln in open(rt.nccl_log, errors="replace"):
-            if any(key in ln for key in ("nranks", "NVLS", "Connected all", "Init COMPLETE")):
-                nccl_lines.append(ln.strip()[-220:])
+    if rt.nccl_log:
+        import glob
+        for path in sorted(glob.glob(rt.nccl_log + "*")):
+            for ln in open(path, errors="replace"):
+                if any(key in ln for key in ("nranks", "NVLS", "Connected all", "Init COMPLETE", "NCCL version", "via P2P", "via NVL")):
+                    nccl_lines.append(ln.strip()[-220:])
         if len(nccl_lines) > 8:
             nccl_lines = nccl_lines[:6] + nccl_lines[-2:]
     cfg = {"workload": f"C5: dense SK J N={n} row-sharded over {rt.world} GPU(s) ({nb} rows each), {R} replicas, "
@@ -743,8 +747,13 @@ def main():
     ap.add_argument("--sca-steps", type=int, default=None, help="SCA steps per bench step (c3: 200, c4: 1000, c5: 10)")
     ap.add_argument("--sub-warmup", type=int, default=3, help="warm-up steps of the sub-workloads")
     args = ap.parse_args()
+    # ONE JSON line on stdout: whatever a library prints there (NCCL's version banner under NCCL_DEBUG, compiler chatter)
+    # is sent to stderr at the file-descriptor level; the line itself goes to the saved descriptor at the end
+    out = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     if args.impl == "reference":
-        return reference_arm(args)
+        return reference_arm(args, out)
 
     rt = Runtime(args)
     tensor_precs = args.prec.split(",") if args.prec and args.workload != "c2" else ["i8x3", "fp16x2", "bf16x3", "bf16x1"]
@@ -774,7 +783,8 @@ def main():
         if rt.rank == 0:
             line["workloads"] = subs
     if rt.rank == 0:
-        print(json.dumps(line))
+        out.write(json.dumps(line) + "\n")
+        out.flush()
     rt.close()
     return 0
 

@@ -119,6 +119,18 @@ int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const
                           int fluct_mode, const double *d_fluct, uint64_t seed, uint64_t step_offset, const double *d_T,
                           int64_t steps_per_T, int64_t trace_every, double *d_E, double *d_M, int8_t *d_S);
 
+// lattice.cu (periodic square lattices recognised by sparse_model_init)
+} // namespace isb
+#include <utility>
+#include <vector>
+namespace isb {
+void *lattice_detect(isb_ctx *ctx, int n, const std::vector<std::vector<std::pair<int, double>>> &rows);
+void lattice_free(void *lat);
+int lattice_side(const void *lat);
+int ssf_lattice_run_device(isb_ens *e, void *lat, int rule, int64_t nsteps, int start, int fluct_mode, const double *d_fluct,
+                           uint64_t seed, uint64_t step_offset, const double *d_T, int64_t steps_per_T, int64_t trace_every,
+                           double *d_E, double *d_M, int8_t *d_S);
+
 // bip_exact.cu
 int bip_run_exact_device(isb_ens *e, int rule, int64_t nsteps, int fluct_mode, const double *d_Fv,
                          const double *d_Fh, uint64_t seed, uint64_t step_offset, const double *d_T,

@@ -25,6 +25,7 @@ struct SparseModel {
     int *col = nullptr;      // [nnz] ascending within a row
     double *val = nullptr;   // [nnz]
     int maxdeg = 0;
+    void *lattice = nullptr;  // periodic square lattice recognised: sequential sweeps run in lattice.cu
 };
 
 struct SpParams {
@@ -269,6 +270,7 @@ int sparse_model_init(isb_model *m, int n, const int64_t *colptr, const int32_t 
         sm->maxdeg = std::max(sm->maxdeg, rowptr[i + 1] - rowptr[i]);
     }
     sm->nnz = (int64_t)col.size();
+    sm->lattice = lattice_detect(ctx, n, rows);
     const size_t nz = std::max<size_t>(col.size(), 1);
     ISB_CUDA(ctx, cudaMalloc(&sm->rowptr, (n + 1) * sizeof(int)));
     ISB_CUDA(ctx, cudaMalloc(&sm->col, nz * sizeof(int)));
@@ -287,6 +289,7 @@ void sparse_model_free(isb_model *m) {
     cudaFree(sm->rowptr);
     cudaFree(sm->col);
     cudaFree(sm->val);
+    lattice_free(sm->lattice);
     delete sm;
     m->sp = nullptr;
 }
@@ -316,6 +319,9 @@ int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const
     isb_ctx *ctx = m->ctx;
     SparseModel *sm = (SparseModel *)m->sp;
     if (nsteps <= 0) return ISB_OK;
+    if (sm->lattice && order == ISB_ORDER_SEQUENTIAL)
+        return ssf_lattice_run_device(e, sm->lattice, rule, nsteps, start, fluct_mode, d_fluct, seed, step_offset, d_T,
+                                      steps_per_T, trace_every, d_E, d_M, d_S);
     const int sign = rule == ISB_RULE_HOPFIELD ? -1 : +1;
     if (e->fields_rule_sign != sign) {
         int rc = sparse_field_device(e, (double *)e->fields, m->npad, m->npad, (double)sign);

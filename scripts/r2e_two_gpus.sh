@@ -1,0 +1,14 @@
+# 2 GPUs: NCCL row-shard parity (bf16 and int8 planes), the default bench line under torchrun (C2 headline + C5 sub-result),
+# then the exchange modes of C5 on the stacked int8 kernel
+set -u
+mkdir -p gpurun_out
+( timeout 400 python -m pytest tests/test_gpu_rowshard.py -m gpu -q -x ) > gpurun_out/r2e_rowshard.log 2>&1; echo "rowshard rc=$?"; tail -3 gpurun_out/r2e_rowshard.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+( timeout 900 $TR bench.py --gpus 2 > gpurun_out/r2e_bench_all_2gpu.json 2> gpurun_out/r2e_bench_all_2gpu.err ); echo "bench all 2gpu rc=$?"
+for ex in copy nccl pipelined fused; do
+  ISB_C5_EXCHANGE=$ex timeout 300 $TR bench.py --gpus 2 --workload c5 --prec i8x3 --steps 5 --warmup 3 > gpurun_out/r2e_c5_i8x3_${ex}_2gpu.json 2> gpurun_out/r2e_c5_i8x3_${ex}_2gpu.err
+  echo "c5 $ex rc=$?"; python -c "
+import json
+d=json.load(open('gpurun_out/r2e_c5_i8x3_${ex}_2gpu.json')); r=d['roofline']
+print('  value %.4g half-step %.4f ms frac_of_fused_target %.3f frac %.3f exchange %s' % (d['value'], r['kernel_ms_per_half_step'], r['frac_of_fused_target'], r['frac'], d['config']['exchange']))"
+done
