@@ -275,6 +275,44 @@ int isb_shard_halfstep_fused_dev(isb_model *m, int R, int replica_offset, int la
                                  const void *in_full_bf16, void *out_block_bf16, int n_peers,
                                  void *const *peer_blocks_bf16, uint64_t seed, uint64_t step_abs, double T);
 
+/* The step loop of the row-sharded SCA inside the library (no torch, no Python on the path): one run object per rank
+ * owns the gathered spin matrices and this rank's blocks, splits the replicas into two groups and hides one group's
+ * exchange under the other group's contraction.  The exchange after every half-step is the path's one collective
+ * (BASELINE config 5: "all-gather of the spin vector each synchronous step"):
+ *   ISB_EXCH_LOCAL  one block, no exchange;
+ *   ISB_EXCH_NCCL   ncclAllGather on a side stream.  libnccl.so.2 is resolved with dlopen at first use; give the run the
+ *                   caller's communicator (isb_shard_run_set_nccl_comm: an ncclComm_t of n_blocks ranks, this rank =
+ *                   block) or let it create one: rank 0 calls isb_nccl_unique_id, sends the 128 bytes to every rank by
+ *                   its own means (MPI, a file, torch.distributed), every rank calls isb_shard_run_init_nccl;
+ *   ISB_EXCH_COPY   copy-engine pushes into the peers' gathered matrices + flag words (CUDA IPC; one process per GPU on
+ *                   one box): every rank exports a 64-byte handle (isb_shard_run_ipc_export), the caller passes them
+ *                   around, every rank imports every other rank's (isb_shard_run_ipc_import).
+ * The trajectory depends neither on the number of blocks nor on the exchange (noise indexed by global replica, step,
+ * unit): parity tests compare with the unsharded tensor path. */
+typedef struct isb_shard_run isb_shard_run;
+enum { ISB_EXCH_LOCAL = 0, ISB_EXCH_NCCL = 1, ISB_EXCH_COPY = 2 };
+int isb_shard_run_create(isb_model *shard_model, int R, int exchange, isb_shard_run **out);
+void isb_shard_run_destroy(isb_shard_run *s);
+int isb_nccl_unique_id(void *id128);
+int isb_shard_run_init_nccl(isb_shard_run *s, const void *id128);
+int isb_shard_run_set_nccl_comm(isb_shard_run *s, void *nccl_comm);
+int isb_shard_run_ipc_export(isb_shard_run *s, void *handle64);
+int isb_shard_run_ipc_import(isb_shard_run *s, int rank, const void *handle64);
+/* Cross-rank barrier of the copy-engine exchange (every rank calls it; returns when all have). */
+int isb_shard_run_barrier(isb_shard_run *s);
+/* S: [R][ld] int8 +-1, the same on every rank; both layers start from it (sigma = tau = s, demo.jl:82-90).  Collective
+ * for ISB_EXCH_COPY (ends with the barrier). */
+int isb_shard_run_set_spins(isb_shard_run *s, const int8_t *S, int64_t ld);
+/* layer 0: the spin configuration (visible copy), 1: the hidden copy; identical on every rank. */
+int isb_shard_run_get_spins(isb_shard_run *s, int layer, int8_t *S, int64_t ld);
+/* nsteps synchronous steps of rule ISB_BIP_SCA / _MA (src/OnBipartiteGraph.jl:30-43,53-66); step k runs at
+ * Tsched[min(k, nT - 1)] and draws the noise of global step step_offset + k.  Collective: every rank calls it with the
+ * same arguments. */
+int isb_shard_run_steps(isb_shard_run *s, int rule, int64_t nsteps, const double *Tsched, int64_t nT, uint64_t seed,
+                        uint64_t step_offset);
+/* Device time (ms) and kernel launches of the last isb_shard_run_steps call, and the number of replica groups. */
+int isb_shard_run_last_stats(const isb_shard_run *s, double *device_ms, int64_t *launches, int *n_groups);
+
 /* ------------------------------------------------------------------ instrumentation */
 /* Device time (ms, CUDA events on the ensemble's stream) of the kernels of the last *_run call,
  * number of kernel launches it made, and bytes copied host->device / device->host by it. */

@@ -23,6 +23,7 @@ ORDER_SEQUENTIAL, ORDER_LIST, ORDER_RANDOM = 0, 1, 2
 FLUCT_PHILOX, FLUCT_SHARED, FLUCT_PER_REPLICA = 0, 1, 2
 PREC_F64, PREC_F32, PREC_AUTO, PREC_BF16X3, PREC_BF16X1, PREC_BF16X2, PREC_FP16X2, PREC_FP16X1 = 0, 1, 2, 3, 4, 5, 6, 7
 PREC_I8X3, PREC_I8X2, PREC_I8X4 = 8, 9, 10
+EXCH_LOCAL, EXCH_NCCL, EXCH_COPY = 0, 1, 2
 I8_PRECS = (PREC_I8X3, PREC_I8X2, PREC_I8X4)
 
 _ERR_NAMES = {1: "ISB_ERR_ARG", 2: "ISB_ERR_SIZE", 3: "ISB_ERR_NONFINITE", 4: "ISB_ERR_CUDA",
@@ -96,6 +97,18 @@ SIGNATURES = {
     "isb_model_shard_block": (_i, [_vp]),
     "isb_shard_halfstep_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _u64, _u64, _d]),
     "isb_shard_halfstep_fused_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _u64, _u64, _d]),
+    "isb_shard_run_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    "isb_shard_run_destroy": (None, [_vp]),
+    "isb_nccl_unique_id": (_i, [_vp]),
+    "isb_shard_run_init_nccl": (_i, [_vp, _vp]),
+    "isb_shard_run_set_nccl_comm": (_i, [_vp, _vp]),
+    "isb_shard_run_ipc_export": (_i, [_vp, _vp]),
+    "isb_shard_run_ipc_import": (_i, [_vp, _i, _vp]),
+    "isb_shard_run_barrier": (_i, [_vp]),
+    "isb_shard_run_set_spins": (_i, [_vp, _vp, _i64]),
+    "isb_shard_run_get_spins": (_i, [_vp, _i, _vp, _i64]),
+    "isb_shard_run_steps": (_i, [_vp, _i, _i64, _vp, _i64, _u64, _u64]),
+    "isb_shard_run_last_stats": (_i, [_vp, C.POINTER(_d), C.POINTER(_i64), C.POINTER(_i)]),
     "isb_ens_last_stats": (_i, [_vp, C.POINTER(_d), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "isb_ens_last_flips": (_i64, [_vp]),
     "isb_ens_last_near_ties": (_i64, [_vp]),
@@ -316,6 +329,86 @@ class Model:
             self.close()
         except Exception:
             pass
+
+
+class ShardRun:
+    """isb_shard_run: the step loop of the row-sharded SCA inside the library (one object per rank).  The caller only
+    carries the 128-byte NCCL id / the 64-byte IPC handles between the ranks (``wire`` does it over torch.distributed)."""
+
+    def __init__(self, model: Model, R: int, exchange: int):
+        h = _vp()
+        check(load().isb_shard_run_create(model.handle, int(R), int(exchange), C.byref(h)), model.ctx.handle)
+        self.model, self.handle, self.R, self.exchange = model, h, int(R), int(exchange)
+        self.n = model.num_visible
+
+    def close(self):
+        if self.handle:
+            load().isb_shard_run_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        check(rc, self.model.ctx.handle)
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(load().isb_nccl_unique_id(C.cast(buf, _vp)), None)
+        return buf.raw
+
+    def init_nccl(self, id128: bytes):
+        buf = C.create_string_buffer(bytes(id128), 128)
+        self._chk(load().isb_shard_run_init_nccl(self.handle, C.cast(buf, _vp)))
+
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._chk(load().isb_shard_run_ipc_export(self.handle, C.cast(buf, _vp)))
+        return buf.raw
+
+    def ipc_import(self, rank: int, handle64: bytes):
+        buf = C.create_string_buffer(bytes(handle64), 64)
+        self._chk(load().isb_shard_run_ipc_import(self.handle, int(rank), C.cast(buf, _vp)))
+
+    def wire(self, dist, group=None):
+        """Exchange the NCCL id or the IPC handles over torch.distributed (any transport would do: 128 / 64 bytes)."""
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if self.exchange == EXCH_NCCL:
+            box = [self.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            self.init_nccl(box[0])
+        elif self.exchange == EXCH_COPY:
+            handles = [None] * world
+            dist.all_gather_object(handles, self.ipc_export(), group=group)
+            for q, h in enumerate(handles):
+                if q != rank:
+                    self.ipc_import(q, h)
+            dist.barrier(group=group)
+
+    def barrier(self):
+        self._chk(load().isb_shard_run_barrier(self.handle))
+
+    def set_spins(self, S):
+        S = np.ascontiguousarray(S, dtype=np.int8).reshape(self.R, self.n)
+        self._chk(load().isb_shard_run_set_spins(self.handle, ptr(S), self.n))
+
+    def get_spins(self, layer: int = 0):
+        S = np.zeros((self.R, self.n), dtype=np.int8)
+        self._chk(load().isb_shard_run_get_spins(self.handle, int(layer), ptr(S), self.n))
+        return S
+
+    def steps(self, rule, nsteps, T, *, seed=0, step_offset=0):
+        Ta = np.ascontiguousarray(np.atleast_1d(T), dtype=np.float64)
+        self._chk(load().isb_shard_run_steps(self.handle, int(rule), int(nsteps), ptr(Ta), Ta.size, int(seed), int(step_offset)))
+
+    def last_stats(self):
+        ms, nl, ng = _d(0), _i64(0), _i(0)
+        load().isb_shard_run_last_stats(self.handle, C.byref(ms), C.byref(nl), C.byref(ng))
+        return {"device_ms": ms.value, "launches": nl.value, "groups": ng.value}
 
 
 class Ensemble:

@@ -1648,6 +1648,8 @@ int shard_model_init(isb_model *m, const double *Wrows, uint64_t seed, double q,
     return make_float_bias(ctx, m->hb64, nb, &t->bias_vf);
 }
 
+int shard_elem_size(const isb_model *m) { return ((const TcModel *)m->tc)->i8 ? 1 : 2; }
+
 int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, int rule, const void *in_full, void *out_block,
                           int n_peers, void *const *peer_blocks, uint64_t seed, uint64_t step_abs, double T) {
     isb_ctx *ctx = m->ctx;

@@ -72,13 +72,18 @@ __global__ void __launch_bounds__(256) ssf_lattice_kernel(const LatParams p) {
     const double tsc = p.tscale ? __ldg(&p.tscale[r]) : 1.0;
     unsigned long long nflips = 0, nties = 0;
 
-    // sum_j J_ij s_j in ascending j (+ / - h_i) for the site of this lane, given the four neighbour bits
-    auto field = [&](double j0, double j1, double j2, double j3, uint32_t code, bool ub, bool lb, bool rb, bool db, double hx) {
-        auto sel = [&](uint32_t k) { return k == 0 ? ub : (k == 1 ? lb : (k == 2 ? rb : db)); };
-        double acc = sel(code & 3u) ? j0 : -j0;
-        acc = __dadd_rn(acc, sel((code >> 2) & 3u) ? j1 : -j1);
-        acc = __dadd_rn(acc, sel((code >> 4) & 3u) ? j2 : -j2);
-        acc = __dadd_rn(acc, sel((code >> 6) & 3u) ? j3 : -j3);
+    // sum_j J_ij s_j in ascending j (+ / - h_i) for the site of this lane.  nbits: the neighbour spins as bits (bit 0 up,
+    // 1 left, 2 right, 3 down; 1 = +1); sh0..sh3 = which of them slot k of the ascending order is.  Branch-free: the
+    // sign of J_k s is applied by flipping the sign bit of J_k's high word.
+    auto field = [&](double j0, double j1, double j2, double j3, uint32_t sh0, uint32_t sh1, uint32_t sh2, uint32_t sh3,
+                     uint32_t nbits, double hx) {
+        auto term = [&](double j, uint32_t sh) {
+            const uint32_t flip = (((nbits >> sh) & 1u) ^ 1u) << 31;     // spin -1: negate
+            return __hiloint2double(__double2hiint(j) ^ (int)flip, __double2loint(j));
+        };
+        double acc = __dadd_rn(term(j0, sh0), term(j1, sh1));
+        acc = __dadd_rn(acc, term(j2, sh2));
+        acc = __dadd_rn(acc, term(j3, sh3));
         return __dadd_rn(acc, hx);
     };
     auto write_trace = [&](int64_t idx) {
@@ -91,8 +96,10 @@ __global__ void __launch_bounds__(256) ssf_lattice_kernel(const LatParams p) {
             const bool sb = (cur >> lane) & 1u;
             const bool lb = lane > 0 ? (cur >> (lane - 1)) & 1u : (lw >> 31) & 1u;
             const bool rb = lane < 31 ? (cur >> (lane + 1)) & 1u : rw & 1u;
+            const uint32_t code = __ldg(&p.kind[i]);
+            const uint32_t nbits = ((up >> lane) & 1u) | ((lb ? 1u : 0u) << 1) | ((rb ? 1u : 0u) << 2) | (((dn >> lane) & 1u) << 3);
             const double g = field(__ldg(&p.Jn[i]), __ldg(&p.Jn[n + i]), __ldg(&p.Jn[2 * n + i]), __ldg(&p.Jn[3 * n + i]),
-                                   __ldg(&p.kind[i]), (up >> lane) & 1u, lb, rb, (dn >> lane) & 1u, 0.0);
+                                   code & 3u, (code >> 2) & 3u, (code >> 4) & 3u, (code >> 6) & 3u, nbits, 0.0);
             const double hv = __ldg(&p.hext[i]);
             q += sb ? g : -g;
             l += sb ? hv : -hv;
@@ -122,6 +129,7 @@ __global__ void __launch_bounds__(256) ssf_lattice_kernel(const LatParams p) {
 
     int64_t t = 0;
     int site = p.start;
+    int y = site / L, x = site - y * L;   // kept incrementally: a window never crosses the end of a lattice row
     while (t < p.nsteps) {
         const int l_first = site & 31;
         int len = 32 - l_first;
@@ -170,32 +178,37 @@ __global__ void __launch_bounds__(256) ssf_lattice_kernel(const LatParams p) {
         }
         const double ftl = __dmul_rn(f, Tl);
         // the window's row segment and its neighbours
-        const int base = site - l_first, y = base / L, wc = (base - y * L) >> 5;
+        const int base = site - l_first, wc = x >> 5;
         const uint32_t cur = W[y * WPR + wc];
         const uint32_t up = W[(y == 0 ? L - 1 : y - 1) * WPR + wc], dn = W[(y == L - 1 ? 0 : y + 1) * WPR + wc];
         const uint32_t lw = W[y * WPR + (wc == 0 ? WPR - 1 : wc - 1)], rw = W[y * WPR + (wc == WPR - 1 ? 0 : wc + 1)];
-        const bool mybit = (cur >> lane) & 1u, ub = (up >> lane) & 1u, db = (dn >> lane) & 1u;
-        const bool left_old = lane > 0 ? (cur >> (lane - 1)) & 1u : (lw >> 31) & 1u;
-        bool rb = lane < 31 ? (cur >> (lane + 1)) & 1u : rw & 1u;
+        const bool mybit = (cur >> lane) & 1u;
+        const uint32_t left_old = ((cur << 1) | (lw >> 31)) >> lane & 1u;           // the spin to my left, as stored
+        const uint32_t right_old = (uint32_t)((((uint64_t)(rw & 1u) << 32) | cur) >> (lane + 1)) & 1u;
+        // neighbour bits without the left one: bit 0 up, 2 right, 3 down
+        uint32_t nb0 = ((up >> lane) & 1u) | (right_old << 2) | (((dn >> lane) & 1u) << 3);
         const int i = base + lane;
         const double j0 = __ldg(&p.Jn[i]), j1 = __ldg(&p.Jn[n + i]), j2 = __ldg(&p.Jn[2 * n + i]), j3 = __ldg(&p.Jn[3 * n + i]);
         const uint32_t code = __ldg(&p.kind[i]);
+        const uint32_t sh0 = code & 3u, sh1 = (code >> 2) & 3u, sh2 = (code >> 4) & 3u, sh3 = (code >> 6) & 3u;
         const double hx = hsign * __ldg(&p.hext[i]);
         const double fts = metro ? (mybit ? ftl : -ftl) : ftl;
         // x = 2 h_loc - f T [s_i]; new spin = +1 unless x < 0 (heaviside(0) = 1, src/SpinSystems.jl:163-171)
-        auto decide = [&](bool lb, bool rbit, double &x) {
-            x = __dsub_rn(2.0 * field(j0, j1, j2, j3, code, ub, lb, rbit, db, hx), fts);
-            return !(x < 0.0);
-        };
-        double x0, x1;
+        double x0 = __dsub_rn(2.0 * field(j0, j1, j2, j3, sh0, sh1, sh2, sh3, nb0, hx), fts);
+        double x1 = __dsub_rn(2.0 * field(j0, j1, j2, j3, sh0, sh1, sh2, sh3, nb0 | 2u, hx), fts);
+        bool t0 = !(x0 < 0.0), t1 = !(x1 < 0.0);
         if (WPR == 1 && l_first == 0) {
-            // lane 31's right neighbour is lane 0 of this window, updated first: decide lane 0 (its own left and right
-            // neighbours are later sites, still old) and hand its new value to lane 31
-            const bool b0 = decide(left_old, rb, x0);
-            const bool n0 = __shfl_sync(FULL, b0, 0);
-            if (lane == 31) rb = n0;
+            // L = 32: lane 31's right neighbour is lane 0 of this window, which is updated first (lane 0 itself depends on
+            // nothing in the window).  Only when lane 0 flips does lane 31 see something else than the stored spin.
+            const bool b0 = __shfl_sync(FULL, left_old ? t1 : t0, 0);
+            if (b0 != (bool)(cur & 1u)) {
+                const uint32_t nb31 = lane == 31 ? (nb0 ^ 4u) : nb0;
+                x0 = __dsub_rn(2.0 * field(j0, j1, j2, j3, sh0, sh1, sh2, sh3, nb31, hx), fts);
+                x1 = __dsub_rn(2.0 * field(j0, j1, j2, j3, sh0, sh1, sh2, sh3, nb31 | 2u, hx), fts);
+                t0 = !(x0 < 0.0);
+                t1 = !(x1 < 0.0);
+            }
         }
-        const bool t0 = decide(false, rb, x0), t1 = decide(true, rb, x1);
         // my site as a function of the NEW value of my left neighbour: (f0, f1) = value for left = -1 / +1.  Lanes outside
         // the window keep their spin; the first lane of the window sees its left neighbour's current value.
         bool f0 = mine ? t0 : mybit, f1 = mine ? t1 : mybit;
@@ -221,6 +234,11 @@ __global__ void __launch_bounds__(256) ssf_lattice_kernel(const LatParams p) {
         __syncwarp();
         t += len;
         site += len;
+        x += len;
+        if (x >= L) {
+            x = 0;
+            if (++y == L) y = 0;
+        }
         if (site >= n) site = 0;
         tr += (uint64_t)len;
         if (tr >= spT) {

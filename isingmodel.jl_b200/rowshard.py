@@ -246,3 +246,54 @@ class RowShardedSCA:
                 for gr in self.groups:
                     self._half(gr, layer, seed, step_offset + k, Tk)
         self._drain()
+
+
+class ShardRunSCA:
+    """The same path with the step loop INSIDE the library (isb_shard_run_*, include/ising_b200.h): the two replica
+    groups, the exchange after every half-step (``exchange="nccl"``: ncclAllGather through the library's own
+    communicator; ``"copy"``: copy-engine pushes into IPC-mapped peer matrices + stream memory operations) and their
+    ordering run in C; torch.distributed only carries the 128-byte NCCL id / the 64-byte IPC handles between the ranks
+    at construction.  What a C or Julia caller of the row-sharded path executes, step for step."""
+
+    def __init__(self, n: int, R: int, *, seed: int | None = None, q: float = 1.0, W=None, h=None, rule=_lib.BIP_SCA,
+                 prec=_lib.PREC_I8X3, device: int | None = None, group=None, exchange: str = "copy"):
+        import torch.distributed as dist
+        self.n, self.R, self.rule = int(n), int(R), rule
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.G = dist.get_world_size(group) if self.distributed else 1
+        g = dist.get_rank(group) if self.distributed else 0
+        if self.n % self.G:
+            raise ValueError("n must be divisible by the number of blocks")
+        self.nb = self.n // self.G
+        self.ctx = _lib.context(device)
+        self.esz = 1 if prec in _lib.I8_PRECS else 2
+        if W is not None:
+            Wa = np.asarray(W, dtype=np.float64)
+            wmax = float((np.abs(Wa) - np.diag(np.abs(np.diag(Wa)))).max()) if prec in _lib.I8_PRECS else 0.0
+            hb = None if h is None else 0.5 * np.asarray(h, dtype=np.float64)[g * self.nb:(g + 1) * self.nb]
+            self.model = _lib.Model.shard_rows(self.ctx, self.n, self.G, g, Wa[g * self.nb:(g + 1) * self.nb, :], hb, hb, prec, wmax=wmax)
+        else:
+            self.model = _lib.Model.shard_sk(self.ctx, self.n, self.G, g, int(seed), q, prec)
+        code = {"nccl": _lib.EXCH_NCCL, "copy": _lib.EXCH_COPY}[exchange] if self.distributed else _lib.EXCH_LOCAL
+        self.exchange = "abi-" + exchange if self.distributed else "local"
+        self.run_obj = _lib.ShardRun(self.model, self.R, code)
+        if self.distributed:
+            self.run_obj.wire(dist, group)
+        self.launches = 0
+        self.gather_bytes = 0
+
+    def set_spins(self, S):
+        self.run_obj.set_spins(S)
+
+    def get_spins(self):
+        return self.run_obj.get_spins(0)
+
+    def get_hidden(self):
+        return self.run_obj.get_spins(1)
+
+    def run(self, nsteps, T, *, seed=0, step_offset=0):
+        self.run_obj.steps(self.rule, nsteps, T, seed=seed, step_offset=step_offset)
+        st = self.run_obj.last_stats()
+        self.launches += st["launches"]
+        self.gather_bytes += 2 * int(nsteps) * (self.G - 1) * self.R * self.nb * self.esz
+        return st

@@ -1,0 +1,10 @@
+set -u
+mkdir -p gpurun_out
+( timeout 900 python -m pytest tests/test_gpu_lattice.py -m gpu -x -q ) > gpurun_out/r2h_lattice_test.log 2>&1
+echo "lattice tests rc=$?"; tail -5 gpurun_out/r2h_lattice_test.log
+timeout 600 python bench.py --workload c1 --no-cpu-baseline --steps 3 > gpurun_out/r2h_bench_c1_lattice.json 2> gpurun_out/r2h_bench_c1_lattice.err; echo "c1 rc=$?"
+python - <<'P'
+import json
+d=json.load(open("gpurun_out/r2h_bench_c1_lattice.json"))
+print("value %.4g ms/step %.1f e2e %.4g Emean %.2f latency %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["mean_final_energy"], d["single_chain_latency"]))
+P

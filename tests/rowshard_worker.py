@@ -31,6 +31,21 @@ def main():
             sca.run(nsteps, T, seed=7)
             ok = ok and np.array_equal(sca.get_spins(), emu.get_spins()) and np.array_equal(sca.get_hidden(), emu.get_hidden())
         modes.append(sca.exchange + (":" + getattr(sca, "fused_error", "") if exchange != sca.exchange else ""))
+    # the step loop inside the library (isb_shard_run_*): NCCL through the library's own communicator, and the
+    # copy-engine exchange over CUDA IPC; bf16 terms and int8 digit planes
+    for prec in (pkg._lib.PREC_BF16X3, pkg._lib.PREC_I8X3):
+        emu_p = rowshard.RowShardedSCA(n, R, seed=seed, q=1.0, prec=prec, emulate_blocks=dist.get_world_size(), device=local)
+        emu_p.set_spins(S0)
+        emu_p.run(nsteps, T, seed=7)
+        for exchange in ("nccl", "copy"):
+            abi = rowshard.ShardRunSCA(n, R, seed=seed, q=1.0, prec=prec, device=local, exchange=exchange)
+            for rep in range(2):
+                abi.set_spins(S0)
+                abi.run(nsteps, T, seed=7)
+                same = np.array_equal(abi.get_spins(), emu_p.get_spins()) and np.array_equal(abi.get_hidden(), emu_p.get_hidden())
+                ok = ok and same
+            modes.append(f"{abi.exchange}/{'i8' if prec == pkg._lib.PREC_I8X3 else 'bf16'}:{'ok' if same else 'MISMATCH'}")
+            del abi
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if dist.get_rank() == 0:

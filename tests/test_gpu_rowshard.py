@@ -82,6 +82,28 @@ def test_synthetic_sk_rows_and_generated_model(pkg, ctx, synth):
     assert E1.mean() < E0.mean()
 
 
+@pytest.mark.parametrize("prec_name,rule", [("i8x3", 0), ("bf16x3", 0), ("i8x3", 1)])
+def test_step_loop_inside_the_library_single_block(pkg, ctx, synth, prec_name, rule):
+    """isb_shard_run_* with one block (ISB_EXCH_LOCAL): the C step loop equals the Python-driven half-steps."""
+    from isingmodel_jl_b200 import _lib as L, rowshard
+    prec = {"i8x3": L.PREC_I8X3, "bf16x3": L.PREC_BF16X3}[prec_name]
+    n, R, nsteps = 256, 300, 5
+    S0 = synth.spins(21, R, n)
+    T = synth.geometric_schedule(1.5, 0.3, nsteps)
+    emu = rowshard.RowShardedSCA(n, R, seed=31, q=1.0, prec=prec, rule=rule, emulate_blocks=2)
+    emu.set_spins(S0)
+    emu.run(nsteps, T, seed=9, step_offset=3)
+    abi = rowshard.ShardRunSCA(n, R, seed=31, q=1.0, prec=prec, rule=rule)
+    assert abi.exchange == "local"
+    abi.set_spins(S0)
+    st = abi.run(nsteps, T, seed=9, step_offset=3)
+    assert st["launches"] == 2 * nsteps
+    assert np.array_equal(abi.get_spins(), emu.get_spins()) and np.array_equal(abi.get_hidden(), emu.get_hidden())
+    abi.run(2, T[-1:], seed=9, step_offset=3 + nsteps)          # continues from the device state
+    emu.run(2, T[-1:], seed=9, step_offset=3 + nsteps)
+    assert np.array_equal(abi.get_spins(), emu.get_spins())
+
+
 def test_nccl_all_gather_two_ranks(pkg, ctx):
     import torch
     if torch.cuda.device_count() < 2:
