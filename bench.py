@@ -656,8 +656,14 @@ def run_c5(rt, args, prec_name, steps, warmup):
     nb, R = args.c5_n_per_gpu, args.c5_replicas
     n = nb * rt.world
     nst = args.sca_steps or 10
-    sca = rowshard.RowShardedSCA(n, R, seed=5, q=1.0, prec=prec, device=rt.local,
-                                 exchange=os.environ.get("ISB_C5_EXCHANGE") or None)
+    # default: the step loop inside the library (isb_shard_run_*, the C-ABI entry of this path) with the copy-engine
+    # exchange; ISB_C5_EXCHANGE = abi-nccl | copy | nccl | pipelined | fused selects the alternatives (the last four
+    # drive the half-steps from Python over torch: the round-1 host loop)
+    ex = os.environ.get("ISB_C5_EXCHANGE") or "abi-copy"
+    if ex.startswith("abi-") or rt.world == 1:
+        sca = rowshard.ShardRunSCA(n, R, seed=5, q=1.0, prec=prec, device=rt.local, exchange=ex[4:] if ex.startswith("abi-") else "copy")
+    else:
+        sca = rowshard.RowShardedSCA(n, R, seed=5, q=1.0, prec=prec, device=rt.local, exchange=ex)
     S0 = synth.spins(21, R, n)   # the same initial configuration on every rank
     T = np.linspace(1.0, 0.05, nst)
     rt.last_stats = lambda: {}
@@ -702,7 +708,11 @@ def run_c5(rt, args, prec_name, steps, warmup):
     cfg = {"workload": f"C5: dense SK J N={n} row-sharded over {rt.world} GPU(s) ({nb} rows each), {R} replicas, "
                        f"SCA annealing T 1->0.05, {nst} steps per bench step, spin blocks exchanged after every half-step",
            "n": n, "rows_per_gpu": nb, "replicas": R, "coupling_storage": prec_name,
-           "collective": {"pipelined": "ncclAllGather per half-step, hidden under the other replica group's GEMM",
+           "collective": {"abi-copy": "inside the library (isb_shard_run_steps): copy-engine pushes into the peers' gathered matrices over "
+                                      "CUDA IPC + stream memory operations, hidden under the other replica group's GEMM",
+                          "abi-nccl": "inside the library (isb_shard_run_steps): ncclAllGather per half-step on a side stream, hidden "
+                                      "under the other replica group's GEMM",
+                          "pipelined": "ncclAllGather per half-step, hidden under the other replica group's GEMM",
                           "nccl": "ncclAllGather per half-step (torch.distributed)",
                           "copy": "copy-engine pushes into symmetric memory + barrier, hidden under the other replica group's GEMM",
                           "fused": "peer stores fused into the sampling epilogue (symmetric memory) + barrier",

@@ -35,6 +35,36 @@ int fail(isb_ctx *ctx, int code, const char *fmt, ...) {
     return code;
 }
 
+// absrowsum[i] = sum_j |J_ij| + |h_i|; vals = every coupling (any order), h = the fields
+double ssf_guard_from(const double *absrowsum, const double *vals, size_t nvals, const double *h, int n) {
+    // exact arithmetic: every value is an integer multiple of 2^-20 and the row sums stay below 2^30 -> every partial sum
+    // (and its doubling) is exactly representable, the incremental field equals the fresh row dot bit for bit
+    bool exact = true;
+    double big = 0.0;
+    auto dyadic = [](double v) {
+        const double s = v * 1048576.0;
+        return std::fabs(s) < 4503599627370496.0 && s == std::nearbyint(s);
+    };
+    for (size_t k = 0; k < nvals && exact; ++k) exact = dyadic(vals[k]);
+    for (int i = 0; i < n; ++i) {
+        if (exact && h) exact = dyadic(h[i]);
+        big = std::max(big, absrowsum[i]);
+    }
+    if (exact && big < 1073741824.0) return 0.0;
+    // couplings drawn from a continuum (more than 64 distinct magnitudes): an exact tie or cancellation of the reference
+    // has probability zero, and so has a decision within an ulp of one; no guard (the near-tie audit still counts them)
+    std::vector<double> mags;
+    for (size_t k = 0; k < nvals; ++k) {
+        const double a = std::fabs(vals[k]);
+        if (a == 0.0) continue;
+        if (std::find(mags.begin(), mags.end(), a) == mags.end()) {
+            mags.push_back(a);
+            if (mags.size() > 64) return 0.0;
+        }
+    }
+    return std::ldexp(big > 0.0 ? big : 1.0, -30);
+}
+
 int dev_reserve(isb_ctx *ctx, int slot, size_t bytes, void **out) {
     isb_devbuf &b = ctx->scratch[slot];
     if (bytes == 0) bytes = 16;
@@ -235,6 +265,15 @@ int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const doub
     // halved shared-memory traffic saves.  ISB_PREC_AUTO therefore means Float64 throughout for dense models.
     m->j_is_f32 = prec == ISB_PREC_F32;
     (void)lossless_f32;
+    {
+        std::vector<double> ars((size_t)n, 0.0);
+        for (int i = 0; i < n; ++i) {
+            double a = std::fabs(hn[i]);
+            for (int j = 0; j < n; ++j) a += std::fabs(Jn[(size_t)i * npad + j]);
+            ars[i] = a;
+        }
+        m->guard = prec == ISB_PREC_F32 ? 0.0 : isb::ssf_guard_from(ars.data(), Jn.data(), Jn.size(), hn.data(), n);
+    }
     const size_t nn = (size_t)npad * npad;
     int rc = ISB_OK;
     do {
@@ -285,6 +324,7 @@ int isb_model_dense(isb_ctx *ctx, int n, const double *J, int64_t ld, const doub
                 colptr[j + 1] = (int64_t)rowval.size();
             }
             rc = isb::sparse_model_init(m, n, colptr.data(), rowval.data(), nzval.data(), nullptr);
+            if (!rc) isb::sparse_model_set_guard(m, hn.data());
         }
     } while (0);
     if (rc) {
@@ -325,6 +365,7 @@ int isb_model_sparse(isb_ctx *ctx, int n, const int64_t *colptr, const int32_t *
     if (!rc) {
         cudaMemcpy(m->h64, hn.data(), m->npad * sizeof(double), cudaMemcpyHostToDevice);
         rc = isb::sparse_model_init(m, n, colptr, rowval, nzval, warn);
+        if (!rc) isb::sparse_model_set_guard(m, hn.data());
     }
     if (rc) {
         isb_model_destroy(m);

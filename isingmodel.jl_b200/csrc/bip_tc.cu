@@ -611,6 +611,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             constexpr int CW = TC_CW;
             const int nchunks = L.bn / CW;
             const int a = tl & 1;
+            // the warps of a quadrant take the chunks of a round in an order that rotates from tile to tile: when a
+            // tile's last round has fewer chunks than warps, a different warp goes ahead to the next tile each time
+            const int hrot = (half + (int)(tl % (uint32_t)TC_HALVES)) % TC_HALVES;
             const int lrow = quad * 32 + lane;
             const int r = job.m0 + lrow;
             const bool row_ok = r < p.R && (!p.persist || lrow < p.rows_per_cta);
@@ -649,7 +652,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
               const uint32_t tq = taddr_t;          // plane t of the tile: columns [t * bn, (t + 1) * bn) of stage a
               const uint32_t pstride = (uint32_t)L.bn;
               for (int g = 0; g * TC_HALVES < nchunks; ++g) {
-                const int c = g * TC_HALVES + half;
+                const int c = g * TC_HALVES + hrot;
                 if (c < nfull) {
                   // fast path (SCA, in-kernel noise, T > 0, 16 real units): field in float — every plane sum is an exact
                   // integer and every plane weight a power of two, so the only roundings are the P + 1 additions
@@ -759,7 +762,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
 #else
             for (int g = 0; g * TC_HALVES < nchunks; ++g) {
 #endif
-              const int c = g * TC_HALVES + half;
+              const int c = g * TC_HALVES + hrot;
               if (c < nfull) {
                 uint32_t v[16];
                 tmem_ld16(taddr_t + (uint32_t)(c * 16), v);

@@ -28,6 +28,9 @@ struct isb_ctx {
     std::recursive_mutex mtx;
 };
 
+// a run that starts this many sweeps (or more) after the last fresh field computation recomputes the cached fields
+#define ISB_FIELD_REFRESH_SWEEPS 64
+
 enum { ISB_KIND_DENSE = 0, ISB_KIND_BIPARTITE = 1, ISB_KIND_SHARD = 2, ISB_KIND_SPARSE = 3 };
 
 struct isb_model {
@@ -42,6 +45,9 @@ struct isb_model {
     double *J64 = nullptr;       // natural layout [npad][npad] (row i contiguous; symmetric)
     void *Jperm = nullptr;       // permuted columns, double or float, [npad][npad]
     double *h64 = nullptr;       // [npad]
+    // near-tie guard of the single-spin kernels: 0 when every coupling and field is a small dyadic number (all sums are
+    // exact), else 2^-30 of the largest row sum of |J| + |h| (see SsfParams::guard)
+    double guard = 0.0;
     // ---- bipartite: nv visible, nh hidden
     int nv = 0, nh = 0;
     double *W64 = nullptr;       // [nv][nh]  (row i = visible unit i; contiguous over hidden)
@@ -64,6 +70,10 @@ struct isb_ens {
     int64_t lds = 0, ldh = 0;    // row strides of the two arrays (bytes == elements)
     void *fields = nullptr;      // cached local fields [R][npad], double or float
     int fields_rule_sign = 0;    // 0 = invalid, +1 = J s + h (Glauber/Metropolis), -1 = J s - h (Hopfield)
+    // The cached fields are maintained incrementally (+-2 J[i,:] per accepted flip); for couplings whose sums round, the
+    // incremental value drifts from a fresh row dot by a few ulp per flip.  A run that starts after this many steps
+    // since the last fresh computation recomputes them first (sequential row dots, the reference's order).
+    int64_t steps_since_refresh = 0;
     unsigned long long *d_flips = nullptr;   // [R]
     unsigned long long *d_counters = nullptr; // [0] near ties
     double tie_eps = 0.0;
@@ -77,6 +87,9 @@ struct isb_ens {
 namespace isb {
 
 int fail(isb_ctx *ctx, int code, const char *fmt, ...);
+// Near-tie guard of a general-graph model from its couplings (n values per row at vals[i * ld + j], or a flat list with
+// rows given by rowptr) and fields: see isb_model::guard.
+double ssf_guard_from(const double *absrowsum, const double *vals, size_t nvals, const double *h, int n);
 // Grow-only device scratch buffer `slot` of the context, at least `bytes` long.
 int dev_reserve(isb_ctx *ctx, int slot, size_t bytes, void **out);
 enum { SCR_NODES = 0, SCR_FLUCT = 1, SCR_T = 2, SCR_E = 3, SCR_M = 4, SCR_FLUCT2 = 5, SCR_OUT = 6, SCR_TMP = 7,
@@ -113,6 +126,7 @@ int config_histogram_device(isb_ctx *ctx, const int8_t *d_S, int64_t count, int 
 // sparse.cu
 int sparse_model_init(isb_model *m, int n, const int64_t *colptr, const int32_t *rowval, const double *nzval, int *warn);
 void sparse_model_free(isb_model *m);
+void sparse_model_set_guard(isb_model *m, const double *h_host);  // near-tie guard from the stored couplings and h
 int sparse_field_device(isb_ens *e, double *d_out, int64_t ld, int nout, double hsign);
 int sparse_energy_device(isb_ens *e, double *d_E);
 int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_t *d_nodes, int start,

@@ -147,6 +147,7 @@ struct isb_shard_run {
     uint64_t epoch[SR_MAX_GROUPS][2] = {};          // exchanges completed per (group, layer)
     uint64_t bar_epoch = 0;
     uint64_t *stage = nullptr;                      // [SR_MAX_GROUPS * 2 + 1] local words the signals are copied from
+    int8_t *hostfmt = nullptr;                      // [R][n] int8 staging of set_spins / get_spins
     int64_t launches = 0;
     double last_ms = 0.0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -226,6 +227,7 @@ int isb_shard_run_create(isb_model *m, int R, int exchange, isb_shard_run **out)
         }
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&gr.sampled, cudaEventDisableTiming);
     }
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->hostfmt, (size_t)R * s->n);
     if (ce == cudaSuccess) ce = cudaMalloc(&s->stage, (SR_MAX_GROUPS * 2 + 1) * sizeof(uint64_t));
     if (ce == cudaSuccess) ce = cudaMemset(s->stage, 0, (SR_MAX_GROUPS * 2 + 1) * sizeof(uint64_t));
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&s->xstream, cudaStreamNonBlocking);
@@ -261,6 +263,7 @@ void isb_shard_run_destroy(isb_shard_run *s) {
         }
         cudaFree(s->arena);
         cudaFree(s->stage);
+        cudaFree(s->hostfmt);
         if (s->xstream) cudaStreamDestroy(s->xstream);
         if (s->ev0) cudaEventDestroy(s->ev0);
         if (s->ev1) cudaEventDestroy(s->ev1);
@@ -374,15 +377,15 @@ int isb_shard_run_set_spins(isb_shard_run *s, const int8_t *S, int64_t ld) {
     ISB_LOCK(ctx);
     if (!S) return fail(ctx, ISB_ERR_ARG, "isb_shard_run_set_spins: S is NULL");
     if (ld < s->n) return fail(ctx, ISB_ERR_SIZE, "isb_shard_run_set_spins: leading dimension %lld < n = %d", (long long)ld, s->n);
-    for (int r = 0; r < s->R; ++r)
-        for (int i = 0; i < s->n; ++i) {
-            const int8_t v = S[(int64_t)r * ld + i];
-            if (v != 1 && v != -1) return fail(ctx, ISB_ERR_ARG, "isb_shard_run_set_spins: spin [%d, replica %d] = %d is not +1 / -1", i, r, (int)v);
-        }
+    for (int r = 0; r < s->R; ++r) {
+        const int8_t *row = S + (int64_t)r * ld;
+        unsigned bad = 0;  // branch-free so that the host compiler vectorises the scan
+        for (int i = 0; i < s->n; ++i) bad |= (unsigned)((row[i] != 1) & (row[i] != -1));
+        if (bad) return fail(ctx, ISB_ERR_ARG, "isb_shard_run_set_spins: replica %d holds a spin that is not +1 / -1", r);
+    }
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     ISB_CUDA(ctx, cudaStreamSynchronize(s->xstream));
-    int8_t *dS;
-    ISB_CUDA(ctx, cudaMalloc(&dS, (size_t)s->R * s->n));
+    int8_t *dS = s->hostfmt;
     cudaError_t ce = cudaMemcpy2DAsync(dS, (size_t)s->n, S, (size_t)ld, (size_t)s->n, (size_t)s->R, cudaMemcpyHostToDevice, ctx->stream);
     for (int gi = 0; gi < s->ngroups && ce == cudaSuccess; ++gi) {
         SrGroup &gr = s->grp[gi];
@@ -395,7 +398,6 @@ int isb_shard_run_set_spins(isb_shard_run *s, const int8_t *S, int64_t ld) {
     }
     if (ce == cudaSuccess) ce = cudaGetLastError();
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
-    cudaFree(dS);
     if (ce != cudaSuccess) return fail(ctx, ISB_ERR_CUDA, "isb_shard_run_set_spins: %s", cudaGetErrorString(ce));
     // no peer may push into this rank's matrices before they hold the initial configuration
     int rc = sr_barrier(s);
@@ -412,8 +414,7 @@ int isb_shard_run_get_spins(isb_shard_run *s, int layer, int8_t *S, int64_t ld) 
     if (ld < s->n) return fail(ctx, ISB_ERR_SIZE, "isb_shard_run_get_spins: leading dimension %lld < n = %d", (long long)ld, s->n);
     ISB_CUDA(ctx, cudaSetDevice(ctx->device));
     ISB_CUDA(ctx, cudaStreamSynchronize(s->xstream));
-    int8_t *dS;
-    ISB_CUDA(ctx, cudaMalloc(&dS, (size_t)s->R * s->n));
+    int8_t *dS = s->hostfmt;
     for (int gi = 0; gi < s->ngroups; ++gi) {
         SrGroup &gr = s->grp[gi];
         isb::shard_collect_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(gr.full[layer], gr.r0, gr.R, s->G, s->nb, s->esz, dS, s->n);
@@ -422,7 +423,6 @@ int isb_shard_run_get_spins(isb_shard_run *s, int layer, int8_t *S, int64_t ld) 
     if (ce == cudaSuccess)
         ce = cudaMemcpy2DAsync(S, (size_t)ld, dS, (size_t)s->n, (size_t)s->n, (size_t)s->R, cudaMemcpyDeviceToHost, ctx->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
-    cudaFree(dS);
     if (ce != cudaSuccess) return fail(ctx, ISB_ERR_CUDA, "isb_shard_run_get_spins: %s", cudaGetErrorString(ce));
     return ISB_OK;
 }

@@ -26,6 +26,8 @@ struct SparseModel {
     double *val = nullptr;   // [nnz]
     int maxdeg = 0;
     void *lattice = nullptr;  // periodic square lattice recognised: sequential sweeps run in lattice.cu
+    std::vector<double> ars;  // row sums of |J| (near-tie guard, completed with |h| by the caller)
+    std::vector<double> vals;
 };
 
 struct SpParams {
@@ -54,6 +56,8 @@ struct SpParams {
     unsigned long long *flips, *near_ties;
     double tie_eps;
     int chains_per_cta;
+    double guard;   // near-tie guard (see SsfParams::guard): 0 = arithmetic exact, no guard
+    double hsign;
 };
 
 template <bool LIST>
@@ -83,6 +87,15 @@ __global__ void ssf_sparse_kernel(const SpParams p) {
         for (int e = a + lane; e < b; e += 32) fld[__ldg(&p.col[e])] += d * __ldg(&p.val[e]);
         if (lane == 0) sp[i] = up ? (int8_t)1 : (int8_t)-1;
         __syncwarp();
+    };
+    // the reference's fresh field of site i: stored neighbours in ascending index (the skipped terms are +-0), then +- h_i
+    auto exact_field = [&](int i) -> double {
+        double acc = 0.0;
+        for (int e = __ldg(&p.rowptr[i]); e < __ldg(&p.rowptr[i + 1]); ++e) {
+            const double v = __ldg(&p.val[e]);
+            acc = __dadd_rn(acc, sp[__ldg(&p.col[e])] > 0 ? v : -v);
+        }
+        return __dadd_rn(acc, p.hsign * __ldg(&p.hext[i]));
     };
     auto fluct_at = [&](int64_t tl) -> double {
         if (rule == 0) return 0.0;
@@ -128,9 +141,15 @@ __global__ void ssf_sparse_kernel(const SpParams p) {
             bool mybit = sp[i] > 0;
             uint32_t rem = __ballot_sync(FULL, mine);
             while (true) {
-                const double h2 = 2.0 * fld[i];
+                double h2 = 2.0 * fld[i];
                 const double fts = metro ? (mybit ? ftl : -ftl) : ftl;
-                const double x = __dsub_rn(h2, fts);
+                double x = __dsub_rn(h2, fts);
+                if (p.guard > 0.0 && fabs(x) < p.guard && ((rem >> lane) & 1u)) {   // rare: decide on the fresh row dot
+                    const double ex = exact_field(i);
+                    fld[i] = ex;
+                    h2 = 2.0 * ex;
+                    x = __dsub_rn(h2, fts);
+                }
                 const bool nb = !(x < 0.0);
                 const uint32_t fm = __ballot_sync(FULL, nb != mybit) & rem;
                 if (audit) {
@@ -160,7 +179,14 @@ __global__ void ssf_sparse_kernel(const SpParams p) {
             const double T = __dmul_rn(__ldg(&p.Tsched[t / p.steps_per_T]), tsc);
             const double ft = __dmul_rn(fluct_at(t), T);
             const bool mybit = sp[i] > 0;
-            const double x = __dsub_rn(2.0 * fld[i], metro ? (mybit ? ft : -ft) : ft);
+            double x = __dsub_rn(2.0 * fld[i], metro ? (mybit ? ft : -ft) : ft);
+            if (p.guard > 0.0 && fabs(x) < p.guard) {
+                const double ex = exact_field(i);
+                __syncwarp();
+                if (lane == 0) fld[i] = ex;
+                __syncwarp();
+                x = __dsub_rn(2.0 * ex, metro ? (mybit ? ft : -ft) : ft);
+            }
             const bool nb = !(x < 0.0);
             if (audit && fabs(x) < p.tie_eps) ++nties;
             if (nb != mybit) {
@@ -271,6 +297,13 @@ int sparse_model_init(isb_model *m, int n, const int64_t *colptr, const int32_t 
     }
     sm->nnz = (int64_t)col.size();
     sm->lattice = lattice_detect(ctx, n, rows);
+    {
+        std::vector<double> ars((size_t)n, 0.0);
+        for (int i = 0; i < n; ++i)
+            for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) ars[i] += fabs(val[e]);
+        sm->ars = ars;
+        sm->vals = val;
+    }
     const size_t nz = std::max<size_t>(col.size(), 1);
     ISB_CUDA(ctx, cudaMalloc(&sm->rowptr, (n + 1) * sizeof(int)));
     ISB_CUDA(ctx, cudaMalloc(&sm->col, nz * sizeof(int)));
@@ -281,6 +314,15 @@ int sparse_model_init(isb_model *m, int n, const int64_t *colptr, const int32_t 
         ISB_CUDA(ctx, cudaMemcpy(sm->val, val.data(), val.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     return ISB_OK;
+}
+
+void sparse_model_set_guard(isb_model *m, const double *h_host) {
+    SparseModel *sm = (SparseModel *)m->sp;
+    std::vector<double> ars = sm->ars;
+    for (int i = 0; i < m->n; ++i) ars[i] += fabs(h_host[i]);
+    m->guard = ssf_guard_from(ars.data(), sm->vals.data(), sm->vals.size(), h_host, m->n);
+    sm->ars.clear();
+    sm->vals.clear();
 }
 
 void sparse_model_free(isb_model *m) {
@@ -323,12 +365,15 @@ int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const
         return ssf_lattice_run_device(e, sm->lattice, rule, nsteps, start, fluct_mode, d_fluct, seed, step_offset, d_T,
                                       steps_per_T, trace_every, d_E, d_M, d_S);
     const int sign = rule == ISB_RULE_HOPFIELD ? -1 : +1;
+    if (e->steps_since_refresh >= (int64_t)ISB_FIELD_REFRESH_SWEEPS * m->n) e->fields_rule_sign = 0;  // bound the drift
     if (e->fields_rule_sign != sign) {
         int rc = sparse_field_device(e, (double *)e->fields, m->npad, m->npad, (double)sign);
         if (rc) return rc;
         e->fields_rule_sign = sign;
+        e->steps_since_refresh = 0;
         e->last_launches += 1;
     }
+    e->steps_since_refresh += nsteps;
     const size_t per_chain = (size_t)m->npad * 9;
     int chains = (int)std::min<size_t>(24, (ctx->smem_optin - 1024) / per_chain);
     if (chains < 1)
@@ -347,6 +392,9 @@ int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const
     p.Tsched = d_T; p.tscale = e->d_tscale; p.steps_per_T = steps_per_T; p.trace_every = trace_every;
     p.out_E = d_E; p.out_M = d_M; p.out_S = d_S; p.ldS = m->n; p.flips = e->d_flips; p.near_ties = e->d_counters; p.tie_eps = e->tie_eps;
     p.chains_per_cta = chains;
+    p.guard = m->guard;
+    if (const char *env_g = getenv("ISB_SSF_GUARD")) p.guard = atof(env_g);
+    p.hsign = rule == ISB_RULE_HOPFIELD ? -1.0 : 1.0;
     const size_t smem = per_chain * chains;
     cudaError_t ce;
     if (order != ISB_ORDER_SEQUENTIAL) {

@@ -215,8 +215,10 @@ int config_histogram_device(isb_ctx *ctx, const int8_t *d_S, int64_t count, int 
 
 // (Re)compute the cached local fields for the given h sign (+1: J s + h, -1: J s - h).
 int ssf_ensure_fields(isb_ens *e, int sign) {
-    if (e->fields_rule_sign == sign) return ISB_OK;
     isb_model *m = e->model;
+    if (e->steps_since_refresh >= (int64_t)ISB_FIELD_REFRESH_SWEEPS * m->n) e->fields_rule_sign = 0;  // bound the drift
+    if (e->fields_rule_sign == sign) return ISB_OK;
+    e->steps_since_refresh = 0;
     dim3 grid((m->npad + 255) / 256, e->R);
     const double hs = (double)sign;
     if (m->prec == ISB_PREC_F32) {
@@ -314,6 +316,11 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
     p.nw = nw;
     p.NG = NG;
     p.keys = philox_keys(seed);
+    p.guard = m->guard;
+    if (const char *env_g = getenv("ISB_SSF_GUARD")) p.guard = atof(env_g);   // 0 disables the near-tie guard (A/B measurements)
+    p.J64 = m->J64;
+    p.ld64 = m->npad;
+    p.hsign = rule == ISB_RULE_HOPFIELD ? -1.0 : 1.0;
     p.od_ratio = 0.8f;
     if (const char *env_od = getenv("ISB_SSF_OD_RATIO")) p.od_ratio = (float)atof(env_od);
 
@@ -328,6 +335,7 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
         return fail(ctx, ISB_ERR_CUDA, "ssf_kernel launch failed: %s (grid %d x %d threads, %zu B smem, cluster %d)",
                     cudaGetErrorString(ce), ctas, threads, smem, cl);
     e->last_launches += 1;
+    e->steps_since_refresh += nsteps;
     return ISB_OK;
 }
 

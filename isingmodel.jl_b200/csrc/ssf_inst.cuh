@@ -33,6 +33,12 @@ static cudaError_t launch_one(const SsfParams &p, bool list, bool tma, int cl, i
         return list ? go(ssf_kernel<HT, JT, NPL, true, true, 2>, 2) : go(ssf_kernel<HT, JT, NPL, false, true, 2>, 2);
     if (tma && cl == 4)
         return list ? go(ssf_kernel<HT, JT, NPL, true, true, 4>, 4) : go(ssf_kernel<HT, JT, NPL, false, true, 4>, 4);
+    if constexpr (std::is_same<HT, double>::value) {
+        if (p.guard > 0.0) {   // couplings from a small non-dyadic alphabet: the instantiation with the near-tie guard
+            if (list) return tma ? go(ssf_kernel<HT, JT, NPL, true, true, 1, true>, 1) : go(ssf_kernel<HT, JT, NPL, true, false, 1, true>, 1);
+            return tma ? go(ssf_kernel<HT, JT, NPL, false, true, 1, true>, 1) : go(ssf_kernel<HT, JT, NPL, false, false, 1, true>, 1);
+        }
+    }
     if (list) return tma ? go(ssf_kernel<HT, JT, NPL, true, true>, 1) : go(ssf_kernel<HT, JT, NPL, true, false>, 1);
     return tma ? go(ssf_kernel<HT, JT, NPL, false, true>, 1) : go(ssf_kernel<HT, JT, NPL, false, false>, 1);
 }

@@ -65,6 +65,16 @@ struct SsfParams {
     // count and streams the next epoch iff flips >= od_ratio * steps (low temperatures go on-demand).
     float od_ratio;
     PhiloxKeys keys;  // the ten Philox round keys of `seed` (read straight from the constant bank)
+    // Near-tie guard (couplings whose sums round: guard > 0).  The incrementally maintained field differs from the
+    // reference's fresh row dot (src/SpinSystems.jl:80-83) by a few ulp; when a decision quantity is closer to zero than
+    // `guard`, the lane recomputes its field as that sequential dot (natural J64 rows, ascending j) before it decides,
+    // so that exact ties and exact cancellations of the reference are reproduced.  0 (and the kernel instantiated
+    // without the guard) for models whose arithmetic is exact (integer / dyadic couplings) and for couplings drawn from
+    // a continuum (more than 64 distinct magnitudes: exact ties have probability zero; the near-tie audit still counts).
+    double guard;
+    const double *J64;  // natural layout [npad][ld64]
+    int64_t ld64;
+    double hsign;       // +1: J s + h, -1: J s - h (Hopfield)
 };
 constexpr int SSF_EPOCH = 1024;        // steps per streamed epoch
 constexpr int SSF_EPOCH_OD = 8 * 1024;  // steps per on-demand epoch: chains re-synchronise 8x less often
@@ -116,10 +126,36 @@ __device__ __forceinline__ HT field_sel(const HT (&hf)[NPL], int k) {
     return v;
 }
 
+// hf[k] = v for a warp-uniform run-time k (the counterpart of field_sel; rare path)
+template <typename HT, int NPL>
+__device__ __forceinline__ void field_set(HT (&hf)[NPL], int k, HT v) {
+    static_for<0, NPL>([&](auto I) {
+        if (I.value == k) hf[I.value] = v;
+    });
+}
+// The reference's fresh local field of site i: sum_j J[i][j] s_j sequentially over ascending j, then +- h_i.  The
+// chain's spins are spread over the warp (site j <-> lane j % 32, bit j / 32 of sw): every lane walks the same loop,
+// lanes with `want` accumulate their own row.  Rare (near ties only), deliberately not inlined.
+static __device__ __noinline__ double ssf_exact_field(const double *J64, int64_t ld64, const double *hext, double hsign, int n,
+                                               uint32_t sw, int i, bool want) {
+    double acc = 0.0;
+    const double *row = J64 + (int64_t)i * ld64;
+    for (int j = 0; j < n; ++j) {
+        const uint32_t w = __shfl_sync(0xffffffffu, sw, j & 31);
+        if (want) {
+            const double v = __ldg(row + j);
+            acc = __dadd_rn(acc, ((w >> (j >> 5)) & 1u) ? v : -v);
+        }
+    }
+    return want ? __dadd_rn(acc, hsign * __ldg(hext + i)) : 0.0;
+}
+
 // CL > 1: the CTAs of a thread-block cluster (same GPC) walk the same row sequence, so the leader CTA's
 // producer issues each J row ONCE as a multicast bulk copy that lands in every CTA's ring (one L2 read for CL
 // SMs).  Followers arm their own full barriers and tell the leader (remote mbarrier arrive) when their slot is free.
-template <typename HT, typename JT, int NPL, bool LIST, bool TMA, int CL = 1>
+// GUARD: the near-tie guard (SsfParams::guard) is compiled in — a separate instantiation, because its rare slow path
+// costs the hot loop registers (measured: 195 -> 232 ms on the C2 schedule when it is merely present).
+template <typename HT, typename JT, int NPL, bool LIST, bool TMA, int CL = 1, bool GUARD = false>
 __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(const SsfParams p) {
     static_assert(CL == 1 || TMA, "clusters only make sense with the TMA ring");
     constexpr int G = SSF_G;
@@ -429,9 +465,21 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
             const int kpos = (k / VEC) * (32 * VEC) + lane * VEC + (k % VEC);
             uint32_t rem = __ballot_sync(FULL, mine);
             while (true) {
-                const double h2 = 2.0 * (double)hk;
+                double h2 = 2.0 * (double)hk;
                 const double fts = metro ? (mybit ? ftl : -ftl) : ftl;
-                const double x = __dsub_rn(h2, fts);
+                double x = __dsub_rn(h2, fts);
+                if constexpr (GUARD) {
+                    const bool near = fabs(x) < p.guard && ((rem >> lane) & 1u);
+                    if (__any_sync(FULL, near)) {   // rare: decide on the reference's fresh sequential row dot
+                        const double ex = ssf_exact_field(p.J64, p.ld64, p.hext, p.hsign, p.n, sw, k * 32 + lane, near);
+                        if (near) {
+                            hk = (HT)ex;
+                            h2 = 2.0 * (double)hk;
+                            x = __dsub_rn(h2, fts);
+                        }
+                        field_set<HT, NPL>(hf, k, hk);
+                    }
+                }
                 const bool nb = !(x < 0.0);  // heaviside(0) = 1, src/SpinSystems.jl:163-171
                 const uint32_t fm = __ballot_sync(FULL, nb != mybit) & rem;
                 if (audit) {
@@ -514,9 +562,20 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
             const int k = site >> 5, l = site & 31;
             const double ft = __dmul_rn(f, Tcur);
             const bool mybit = (sw >> k) & 1u;
-            const double h2 = 2.0 * (double)field_sel<HT, NPL>(hf, k);
+            double h2 = 2.0 * (double)field_sel<HT, NPL>(hf, k);
             const double fts = metro ? (mybit ? ft : -ft) : ft;
-            const double x = __dsub_rn(h2, fts);
+            double x = __dsub_rn(h2, fts);
+            if constexpr (GUARD) {
+                const bool near = lane == l && fabs(x) < p.guard;
+                if (__any_sync(FULL, near)) {
+                    const double ex = ssf_exact_field(p.J64, p.ld64, p.hext, p.hsign, p.n, sw, site, near);
+                    if (near) {
+                        field_set<HT, NPL>(hf, k, (HT)ex);
+                        h2 = 2.0 * (double)(HT)ex;
+                        x = __dsub_rn(h2, fts);
+                    }
+                }
+            }
             const bool nb = !(x < 0.0);
             uint32_t code = (nb != mybit ? 1u : 0u) | (nb ? 2u : 0u) | (fabs(x) < p.tie_eps ? 4u : 0u);
             code = __shfl_sync(FULL, code, l);
