@@ -31,13 +31,11 @@ class StochasticCellularAutomata(MultiSpinUpdatingAlgorithm):
         if pinningParameter is None:
             pinningParameter = 0.5 * float(np.linalg.eigvalsh(J)[-1])  # demo.jl:82
         self.pinningParameter = float(pinningParameter)
-        s = spinSystem.spinConfiguration
         self.spinSystem = spinSystem
-        self.bipartite = OnBipartiteGraph.StochasticCellularAutomata(
-            SpinSystemOnBipartiteGraph(s.copy(), s.copy(), 0.5 * (J + self.pinningParameter * np.eye(n)),
-                                       0.5 * spinSystem.externalMagneticField,
-                                       0.5 * spinSystem.externalMagneticField, device=spinSystem._device, prec=prec),
-            temperature)
+        self._prec = prec
+        self.bipartite = OnBipartiteGraph.StochasticCellularAutomata.__new__(OnBipartiteGraph.StochasticCellularAutomata)
+        self.bipartite.temperature = float(temperature)
+        self._embed()
         self.distribution = self.bipartite.distribution
 
     @property
@@ -48,12 +46,38 @@ class StochasticCellularAutomata(MultiSpinUpdatingAlgorithm):
     def temperature(self, T):
         self.bipartite.temperature = float(T)
 
+    def _embed(self):
+        ss = self.spinSystem
+        J = ss.couplingCoefficients
+        J = J.toarray() if hasattr(J, "toarray") else J
+        n = J.shape[0]
+        s = np.array(ss.spinConfiguration, copy=True)
+        self.bipartite = OnBipartiteGraph.StochasticCellularAutomata(
+            SpinSystemOnBipartiteGraph(s, s.copy(), 0.5 * (J + self.pinningParameter * np.eye(n)),
+                                       0.5 * ss.externalMagneticField, 0.5 * ss.externalMagneticField,
+                                       device=ss._device, prec=self._prec), self.temperature)
+        self._J_id, self._h_id = ss.couplingCoefficients, ss.externalMagneticField
+
+    def _sync_in(self):
+        """Changes made to the general-graph system since the last step (setSpinConfiguration, setCouplingCoefficients,
+        setExternalMagneticField: src/SpinSystems.jl:61-66) reach the embedded bipartite system before it steps."""
+        ss = self.spinSystem
+        if ss.couplingCoefficients is not self._J_id or ss.externalMagneticField is not self._h_id:
+            self._embed()
+            return
+        cur = np.atleast_2d(ss.spinConfiguration)
+        b = self.bipartite.spinSystem
+        if not np.array_equal(cur, np.atleast_2d(b.spinConfiguration)):
+            b.spinConfiguration = cur.copy()
+            b.hiddenLayer = cur.copy()
+
     def _sync_back(self):
         self.spinSystem.spinConfiguration = self.bipartite.spinSystem.spinConfiguration
 
 
 def update_(ua: StochasticCellularAutomata, fluctuationForSpinConfiguration, fluctuationForHiddenLayer):
     """One synchronous (all-spin) SCA step of the embedded system; the visible layer is the spin configuration."""
+    ua._sync_in()
     OnBipartiteGraph.update_(ua.bipartite, fluctuationForSpinConfiguration, fluctuationForHiddenLayer)
     ua._sync_back()
     return ua.spinSystem.spinConfiguration

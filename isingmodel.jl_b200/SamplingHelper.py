@@ -34,6 +34,8 @@ def update_(ua, rng=None):
         updatedNode = int(rng.integers(0, n))
         fluctuation = float(ua.distribution.rand(rng))
         return SingleSpinFlip.update_(ua, updatedNode, fluctuation)
+    if isinstance(ua, MultiSpinFlip.MultiSpinUpdatingAlgorithm):
+        ua._sync_in()
     b = _bip(ua)
     ss = b.spinSystem
     fv = b.distribution.rand(rng, ss._host_s.shape[1])
@@ -99,6 +101,8 @@ def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offse
         if T is not None and maxMCSteps > 0:
             ua.temperature = float(T[-1])
         return out
+    if isinstance(ua, MultiSpinFlip.MultiSpinUpdatingAlgorithm):
+        ua._sync_in()
     b = _bip(ua)
     ss = b.spinSystem
     ens = ss._ensemble()

@@ -60,19 +60,23 @@ struct SpParams {
     double hsign;
 };
 
-template <bool LIST>
+// GLOBALF: the chain's fields and spins stay in global memory (models too large for 9 N bytes of shared memory per
+// chain: the reference has no size limit); same code, the working set is served by L1 / L2.
+template <bool LIST, bool GLOBALF = false>
 __global__ void ssf_sparse_kernel(const SpParams p) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * p.chains_per_cta + warp;
     if (r >= p.R) return;
     const size_t per_chain = (size_t)p.npad * sizeof(double) + (size_t)p.npad;
-    double *fld = reinterpret_cast<double *>(sm_raw + (size_t)warp * per_chain);
-    int8_t *sp = reinterpret_cast<int8_t *>(fld + p.npad);
+    double *fld = GLOBALF ? p.fields + (int64_t)r * p.npad : reinterpret_cast<double *>(sm_raw + (size_t)warp * per_chain);
+    int8_t *sp = GLOBALF ? p.spins + (int64_t)r * p.lds : reinterpret_cast<int8_t *>(fld + p.npad);
     constexpr uint32_t FULL = 0xffffffffu;
-    for (int i = lane; i < p.npad; i += 32) {
-        fld[i] = p.fields[(int64_t)r * p.npad + i];
-        sp[i] = i < p.n ? p.spins[(int64_t)r * p.lds + i] : (int8_t)1;
+    if constexpr (!GLOBALF) {
+        for (int i = lane; i < p.npad; i += 32) {
+            fld[i] = p.fields[(int64_t)r * p.npad + i];
+            sp[i] = i < p.n ? p.spins[(int64_t)r * p.lds + i] : (int8_t)1;
+        }
     }
     __syncwarp();
     const int rule = p.rule;
@@ -200,9 +204,11 @@ __global__ void ssf_sparse_kernel(const SpParams p) {
         }
     }
     __syncwarp();
-    for (int i = lane; i < p.npad; i += 32) {
-        p.fields[(int64_t)r * p.npad + i] = fld[i];
-        if (i < p.n) p.spins[(int64_t)r * p.lds + i] = sp[i];
+    if constexpr (!GLOBALF) {
+        for (int i = lane; i < p.npad; i += 32) {
+            p.fields[(int64_t)r * p.npad + i] = fld[i];
+            if (i < p.n) p.spins[(int64_t)r * p.lds + i] = sp[i];
+        }
     }
     if (lane == 0) {
         p.flips[r] = nflips;
@@ -376,8 +382,11 @@ int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const
     e->steps_since_refresh += nsteps;
     const size_t per_chain = (size_t)m->npad * 9;
     int chains = (int)std::min<size_t>(24, (ctx->smem_optin - 1024) / per_chain);
-    if (chains < 1)
-        return fail(ctx, ISB_ERR_UNSUPPORTED, "sparse single-spin sweeps keep a chain's fields in shared memory: N = %d is too large", m->n);
+    // N above ~25 000 sites: 9 N bytes per chain no longer fit the shared memory; the chain's fields and spins then stay
+    // in global memory (ISB_SPARSE_GLOBAL=1 forces this variant, for tests)
+    bool globalf = chains < 1;
+    if (const char *env = getenv("ISB_SPARSE_GLOBAL")) globalf = globalf || atoi(env) != 0;
+    if (globalf) chains = 8;
     // spread the chains over the SMs first (one warp = one chain)
     const int per_sm = (e->R + ctx->num_sms - 1) / ctx->num_sms;
     chains = std::max(1, std::min(chains, per_sm));
@@ -395,9 +404,14 @@ int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const
     p.guard = m->guard;
     if (const char *env_g = getenv("ISB_SSF_GUARD")) p.guard = atof(env_g);
     p.hsign = rule == ISB_RULE_HOPFIELD ? -1.0 : 1.0;
-    const size_t smem = per_chain * chains;
-    cudaError_t ce;
-    if (order != ISB_ORDER_SEQUENTIAL) {
+    const size_t smem = globalf ? 0 : per_chain * chains;
+    cudaError_t ce = cudaSuccess;
+    if (globalf) {
+        if (order != ISB_ORDER_SEQUENTIAL)
+            ssf_sparse_kernel<true, true><<<grid, 32 * chains, 0, ctx->stream>>>(p);
+        else
+            ssf_sparse_kernel<false, true><<<grid, 32 * chains, 0, ctx->stream>>>(p);
+    } else if (order != ISB_ORDER_SEQUENTIAL) {
         ce = cudaFuncSetAttribute(ssf_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce == cudaSuccess) ssf_sparse_kernel<true><<<grid, 32 * chains, smem, ctx->stream>>>(p);
     } else {

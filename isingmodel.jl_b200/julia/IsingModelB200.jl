@@ -151,6 +151,42 @@ function bip_run!(e, rule, nsteps; Fv = nothing, Fh = nothing, per_replica = fal
                     steps_per_T, trace_every, _optr(E, Float64), snapV, size(snapV, 1), snapH, size(snapH, 1)), context())
     end
 end
+# ---- row-sharded synchronous SCA (BASELINE config 5): one process per GPU, the step loop inside the library
+const ShardRun = Ptr{Cvoid}
+const EXCH_LOCAL, EXCH_NCCL, EXCH_COPY = Cint(0), Cint(1), Cint(2)
+function shard_model_sk(n::Integer, n_blocks::Integer, block::Integer, seed::Integer, q::Real; prec = PREC_I8X3)
+    m = Ref{Model}(C_NULL)
+    check(ccall((:isb_shard_model_sk, libisb), Cint, (Ctx, Cint, Cint, Cint, UInt64, Float64, Cint, Ref{Model}),
+                context(), n, n_blocks, block, seed, q, prec, m), context())
+    m[]
+end
+# Wrows: the rows [block nb + 1, (block + 1) nb] of the symmetric W as an n x nb Julia matrix (column r = row r of the
+# block: the C side reads [nb][n] row-major); wmax = largest off-diagonal |W| of the WHOLE matrix (int8 planes)
+function shard_model_rows(n::Integer, n_blocks::Integer, block::Integer, Wrows::Matrix{Float64}, h_blk::Vector{Float64},
+                          b_blk::Vector{Float64}; prec = PREC_I8X3, wmax = 0.0)
+    m = Ref{Model}(C_NULL)
+    check(ccall((:isb_shard_model_rows_q, libisb), Cint,
+                (Ctx, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Ref{Model}),
+                context(), n, n_blocks, block, Wrows, h_blk, b_blk, prec, wmax, m), context())
+    m[]
+end
+function shard_run_create(m::Model, R::Integer, exchange::Cint)
+    s = Ref{ShardRun}(C_NULL)
+    check(ccall((:isb_shard_run_create, libisb), Cint, (Model, Cint, Cint, Ref{ShardRun}), m, R, exchange, s), context())
+    s[]
+end
+shard_run_destroy(s::ShardRun) = ccall((:isb_shard_run_destroy, libisb), Cvoid, (ShardRun,), s)
+nccl_unique_id() = (id = Vector{UInt8}(undef, 128); check(ccall((:isb_nccl_unique_id, libisb), Cint, (Ptr{UInt8},), id), C_NULL); id)
+shard_run_init_nccl(s::ShardRun, id::Vector{UInt8}) = check(ccall((:isb_shard_run_init_nccl, libisb), Cint, (ShardRun, Ptr{UInt8}), s, id), context())
+shard_run_set_nccl_comm(s::ShardRun, comm::Ptr{Cvoid}) = check(ccall((:isb_shard_run_set_nccl_comm, libisb), Cint, (ShardRun, Ptr{Cvoid}), s, comm), context())
+shard_run_ipc_export(s::ShardRun) = (h = Vector{UInt8}(undef, 64); check(ccall((:isb_shard_run_ipc_export, libisb), Cint, (ShardRun, Ptr{UInt8}), s, h), context()); h)
+shard_run_ipc_import(s::ShardRun, rank::Integer, h::Vector{UInt8}) = check(ccall((:isb_shard_run_ipc_import, libisb), Cint, (ShardRun, Cint, Ptr{UInt8}), s, rank, h), context())
+shard_run_barrier(s::ShardRun) = check(ccall((:isb_shard_run_barrier, libisb), Cint, (ShardRun,), s), context())
+shard_run_set_spins!(s::ShardRun, S::Matrix{Int8}) = check(ccall((:isb_shard_run_set_spins, libisb), Cint, (ShardRun, Ptr{Int8}, Int64), s, S, stride(S, 2)), context())
+shard_run_get_spins!(s::ShardRun, layer::Integer, S::Matrix{Int8}) = (check(ccall((:isb_shard_run_get_spins, libisb), Cint, (ShardRun, Cint, Ptr{Int8}, Int64), s, layer, S, stride(S, 2)), context()); S)
+shard_run_steps!(s::ShardRun, rule::Cint, nsteps::Integer, T::Vector{Float64}; seed = 0, step_offset = 0) =
+    check(ccall((:isb_shard_run_steps, libisb), Cint, (ShardRun, Cint, Int64, Ptr{Float64}, Int64, UInt64, UInt64),
+                s, rule, nsteps, T, length(T), seed, step_offset), context())
 end # module CABI
 
 # ------------------------------------------------------------------ SpinSystems (src/SpinSystems.jl)
@@ -539,6 +575,59 @@ function update!(ua::StochasticCellularAutomata, Fv::AbstractVector{<:AbstractFl
     OnBipartiteGraph.update!(ua.bipartite, Fv, Fh)
     _sync_out!(ua)
     ua.spinSystem.spinConfiguration
+end
+# The same synchronous SCA for a model too large for one GPU (BASELINE config 5): rank `block` of `n_blocks` processes
+# (one per GPU) owns n / n_blocks rows of W = (J + qI)/2; the freshly sampled blocks are exchanged after every half-step
+# inside the library (isb_shard_run_steps).  `wire!` carries the NCCL id (128 bytes, from rank 0) or the IPC handles
+# (64 bytes per rank) between the processes with whatever the application uses (MPI.jl: `bcast` / `Allgather`).
+mutable struct ShardedStochasticCellularAutomata <: MultiSpinUpdatingAlgorithm
+    temperature::AbstractFloat
+    n::Int
+    replicas::Int
+    block::Int
+    n_blocks::Int
+    model::Ptr{Cvoid}
+    run::Ptr{Cvoid}
+    # synthetic Sherrington-Kirkpatrick instance generated on the device (never materialised in full)
+    function ShardedStochasticCellularAutomata(n::Integer, replicas::Integer, temperature::AbstractFloat; block::Integer,
+                                               n_blocks::Integer, seed::Integer, pinningParameter::Real = 1.0,
+                                               exchange = OnBipartiteGraph.CABI.EXCH_NCCL, prec = OnBipartiteGraph.CABI.PREC_I8X3)
+        C = OnBipartiteGraph.CABI
+        m = C.shard_model_sk(n, n_blocks, block, seed, pinningParameter; prec = prec)
+        r = C.shard_run_create(m, replicas, n_blocks == 1 ? C.EXCH_LOCAL : exchange)
+        ua = new(temperature, n, replicas, block, n_blocks, m, r)
+        finalizer(ua) do u
+            u.run != C_NULL && C.shard_run_destroy(u.run)
+            u.model != C_NULL && C.model_destroy(u.model)
+            u.run = C_NULL; u.model = C_NULL
+        end
+    end
+end
+# every rank: wire!(ua; nccl_id = the 128 bytes drawn on rank 0)   or   wire!(ua; ipc_handles = all ranks' 64-byte handles)
+function wire!(ua::ShardedStochasticCellularAutomata; nccl_id = nothing, ipc_handles = nothing)
+    C = OnBipartiteGraph.CABI
+    nccl_id === nothing || C.shard_run_init_nccl(ua.run, Vector{UInt8}(nccl_id))
+    if ipc_handles !== nothing
+        for (q, h) in enumerate(ipc_handles)
+            q - 1 == ua.block || C.shard_run_ipc_import(ua.run, q - 1, Vector{UInt8}(h))
+        end
+    end
+    ua
+end
+ipcHandle(ua::ShardedStochasticCellularAutomata) = OnBipartiteGraph.CABI.shard_run_ipc_export(ua.run)
+ncclUniqueId() = OnBipartiteGraph.CABI.nccl_unique_id()
+# S: n x replicas (+-1), the same on every rank
+setSpinConfiguration!(ua::ShardedStochasticCellularAutomata, S::AbstractMatrix{<:Number}) =
+    OnBipartiteGraph.CABI.shard_run_set_spins!(ua.run, Matrix{Int8}(S))
+getSpinConfiguration(ua::ShardedStochasticCellularAutomata) =
+    Int.(OnBipartiteGraph.CABI.shard_run_get_spins!(ua.run, 0, Matrix{Int8}(undef, ua.n, ua.replicas)))
+# nsteps synchronous steps, step k at annealingSchedule(k) (collective: every rank calls it with the same arguments)
+function run!(ua::ShardedStochasticCellularAutomata, nsteps::Integer; annealingSchedule::Function = k -> ua.temperature,
+              seed::Integer = 0, stepOffset::Integer = 0)
+    T = Float64[annealingSchedule(k) for k in 1:nsteps]
+    OnBipartiteGraph.CABI.shard_run_steps!(ua.run, OnBipartiteGraph.CABI.BIP_SCA, nsteps, T; seed = seed, step_offset = stepOffset)
+    nsteps > 0 && (ua.temperature = T[end])
+    ua
 end
 end # module MultiSpinFlip
 

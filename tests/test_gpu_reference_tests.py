@@ -142,3 +142,75 @@ def test_makesampler_bipartite_replays_every_step(pkg, ctx, orc, synth):
             assert np.array_equal(states[k + 1][0], s) and np.array_equal(states[k + 1][1], t), k
             assert abs(states[k + 1][2] - orc.bip_energy(W, h, b, s, t)) < 1e-9
         assert np.array_equal(ss.spinConfiguration, s) and np.array_equal(ss.hiddenLayer, t)
+
+
+def test_makesampler_early_close_and_consumer_assignment(pkg, ctx, orc, synth):
+    """The sampler reads ahead (one library call per chunk); what a consumer can observe must still be the reference's
+    lazy, unbuffered Channel (src/SamplingHelper.jl:42-50): stopping early leaves the system in the last yielded state
+    (a later update_ continues from it), and spins assigned between two items are what the next step starts from."""
+    import itertools
+    N, n = 9, 60
+    J = synth.lattice_J(3, -1.0)
+    s0 = synth.spins(4, 1, N)[0]
+    sched = lambda k: 2.0 * 0.97 ** k  # noqa: E731
+    rng = np.random.default_rng(5)
+    nodes = rng.integers(0, N, n).astype(np.int32)
+    ssd = pkg.SingleSpinFlip.GlauberDynamics(pkg.SpinSystems.SpinSystem(s0.copy(), J, np.zeros(N)), 2.0)
+    fl = ssd.distribution.rand(rng, n)
+    T = np.array([sched(k) for k in range(n + 1)])
+
+    def oracle_after(k, s=None, k0=0):
+        s = s0.copy() if s is None else s.copy()
+        for j in range(k0, k):
+            s, *_ = orc.ssf_run(1, J, np.zeros(N), s, 1, nodes=nodes[j:j + 1], fluct=fl[j:j + 1], T=T[j + 1:j + 2])
+        return s
+
+    # (a) break after 7 of 60 steps (the device had run the whole chunk ahead)
+    ua = pkg.SingleSpinFlip.GlauberDynamics(pkg.SpinSystems.SpinSystem(s0.copy(), J, np.zeros(N)), 2.0)
+    for item in itertools.islice(pkg.SamplingHelper.makeSampler_(ua, n, annealingSchedule=sched, rng=np.random.default_rng(5)), 8):
+        pass
+    s7 = oracle_after(7)
+    assert np.array_equal(ua.spinSystem.spinConfiguration, s7)
+    assert abs(pkg.SpinSystems.calcEnergy(ua) - orc.energy(J, np.zeros(N), s7)) < 1e-9
+    assert ua.temperature == T[7]
+    pkg.SingleSpinFlip.update_(ua, 4, 0.3)           # continues from the state the consumer saw, not from step 60
+    s8, *_ = orc.ssf_run(1, J, np.zeros(N), s7, 1, nodes=np.array([4], dtype=np.int32), fluct=np.array([0.3]), T=T[7:8])
+    assert np.array_equal(ua.spinSystem.spinConfiguration, s8)
+
+    # (b) the consumer flips all spins after item 10: the remaining 50 steps start from its configuration
+    ua = pkg.SingleSpinFlip.GlauberDynamics(pkg.SpinSystems.SpinSystem(s0.copy(), J, np.zeros(N)), 2.0)
+    count = 0
+    for k, item in enumerate(pkg.SamplingHelper.makeSampler_(ua, n, annealingSchedule=sched, rng=np.random.default_rng(5))):
+        count += 1
+        if k == 10:
+            assert np.array_equal(item.spinSystem.spinConfiguration, oracle_after(10))
+            pkg.SpinSystems.setSpinConfiguration(item, -item.spinSystem.spinConfiguration)
+    assert count == n + 1
+    assert np.array_equal(ua.spinSystem.spinConfiguration, oracle_after(n, -oracle_after(10), 10))
+
+    # (c) a rejected assignment (not +-1) changes nothing, on the host or on the device
+    before = ua.spinSystem.spinConfiguration.copy()
+    with pytest.raises(ValueError):
+        ua.spinSystem.spinConfiguration = np.zeros(N)
+    assert np.array_equal(ua.spinSystem.spinConfiguration, before)
+    assert abs(pkg.SpinSystems.calcEnergy(ua) - orc.energy(J, np.zeros(N), before)) < 1e-9
+
+
+def test_multispinflip_sees_changes_of_its_spin_system(pkg, ctx, orc, synth):
+    """setSpinConfiguration / setCouplingCoefficients on the general-graph system of a MultiSpinFlip algorithm
+    (src/SpinSystems.jl:61-66) reach the embedded bipartite system before the next step."""
+    N = 32
+    J, h = synth.sk_J(N, 14), np.zeros(N)
+    s0, s1 = synth.spins(15, 1, N)[0], synth.spins(16, 1, N)[0]
+    ua = pkg.MultiSpinFlip.StochasticCellularAutomata(pkg.SpinSystems.SpinSystem(s0, J, h), 0.5, pinningParameter=1.0)
+    Fv, Fh = synth.logistic(17, (2, N), 1), synth.logistic(17, (2, N), 2)
+    pkg.SpinSystems.setSpinConfiguration(ua, s1)
+    pkg.MultiSpinFlip.update_(ua, Fv[0], Fh[0])
+    W = 0.5 * (J + np.eye(N))
+    s, t, _ = orc.bip_run(0, W, h, h, s1, s1, 1, Fv[:1], Fh[:1], np.array([0.5]))
+    assert np.array_equal(ua.spinSystem.spinConfiguration, s)
+    J2 = synth.sk_J(N, 18)
+    pkg.SpinSystems.setCouplingCoefficients(ua, J2)
+    pkg.MultiSpinFlip.update_(ua, Fv[1], Fh[1])
+    s2, _, _ = orc.bip_run(0, 0.5 * (J2 + np.eye(N)), h, h, s, s, 1, Fv[1:], Fh[1:], np.array([0.5]))
+    assert np.array_equal(ua.spinSystem.spinConfiguration, s2)

@@ -253,3 +253,37 @@ def test_configuration_histogram(pkg, ctx, synth):
     tv = 0.5 * np.abs(hist / hist.sum() - p).sum()
     assert tv < 0.05, tv
     assert 0.5 * np.abs(1 / 512 - p).sum() > 0.2       # the target is far from uniform, so the bound above is a real check
+
+
+def test_fields_in_global_memory_variant(ctx, orc, synth, monkeypatch):
+    """Models whose fields do not fit the shared memory (N above ~25 000 sites) keep them in global memory; the variant is
+    forced here on a small model and must follow the oracle bit for bit, then a 40 000-site random graph runs through it
+    (traced energies against isb_ens_energy)."""
+    L = _lib()
+    monkeypatch.setenv("ISB_SPARSE_GLOBAL", "1")
+    n, R, nsteps = 600, 9, 600 * 3 + 5
+    A = _random_sparse(synth, n, 6, 300, False)
+    J, h = A.toarray(), synth.gaussian(5, n) * 0.3
+    S0 = synth.spins(6, R, n)
+    fl = synth.logistic(8, (R, nsteps))
+    T = synth.geometric_schedule(2.0, 0.2, 4)
+    spT = (nsteps + 3) // 4
+    for order in ("seq", "list"):
+        nodes = synth.nodes(7, n, nsteps) if order == "list" else None
+        e = L.Ensemble(L.Model.sparse(ctx, A, h), R)
+        e.set_spins(S0)
+        out = e.ssf_run(1, nsteps, nodes=nodes, start=17 if order == "seq" else 0, fluct=fl, fluct_per_replica=True, T=T,
+                        steps_per_T=spT, trace_every=nsteps // 2)
+        S = e.get_spins()
+        for r in range(R):
+            s, flips, E, M = orc.ssf_run(1, J, h, S0[r], nsteps, nodes=nodes, start=17 if order == "seq" else 0, fluct=fl[r], T=T,
+                                         steps_per_T=spT, trace_every=nsteps // 2)
+            assert np.array_equal(s, S[r]) and flips == out["flips"][r] and _close(out["E"][:, r], E)
+    monkeypatch.delenv("ISB_SPARSE_GLOBAL")
+    n, R = 40000, 3                                        # 9 N bytes = 360 kB per chain: beyond the shared memory
+    A = _random_sparse(synth, n, 4, 301, True)
+    e = L.Ensemble(L.Model.sparse(ctx, A, np.zeros(n)), R)
+    e.set_spins(synth.spins(9, R, n))
+    E0 = e.energy()
+    out = e.ssf_run(2, 2 * n, seed=3, T=np.array([0.5]), steps_per_T=2 * n, trace_every=2 * n)
+    assert _close(out["E"][-1], e.energy()) and np.all(e.energy() < E0)

@@ -45,8 +45,9 @@ def c_kind(decl):
 JL = {
     "Cint": {"i32"}, "Int32": {"i32"}, "Int64": {"i64"}, "UInt64": {"u64"}, "UInt32": {"u32"},
     "Cdouble": {"f64"}, "Float64": {"f64"}, "Csize_t": {"u64"},
-    "Ctx": {"ptr:handle"}, "Model": {"ptr:handle"}, "Ens": {"ptr:handle"},
+    "Ctx": {"ptr:handle"}, "Model": {"ptr:handle"}, "Ens": {"ptr:handle"}, "ShardRun": {"ptr:handle"},
     "Ref{Ctx}": {"ptr:handle_out"}, "Ref{Model}": {"ptr:handle_out"}, "Ref{Ens}": {"ptr:handle_out"},
+    "Ref{ShardRun}": {"ptr:handle_out"}, "Ptr{UInt8}": {"ptr:void"},
     "Ptr{Float64}": {"ptr:f64"}, "Ptr{Int8}": {"ptr:i8"}, "Ptr{Int32}": {"ptr:i32"}, "Ptr{Int64}": {"ptr:i64"},
     "Ptr{UInt32}": {"ptr:u32"}, "Ptr{UInt64}": {"ptr:u64"}, "Ref{Cint}": {"ptr:i32"}, "Ref{Int64}": {"ptr:i64"},
     "Ptr{Cvoid}": {"ptr:void", "ptr:handle"}, "Cstring": {"ptr:char"},
@@ -247,7 +248,10 @@ def test_shim_keeps_reference_object_semantics():
     txt = open(SHIM).read()
     bound = {c[0] for c in julia_ccalls()}
     for need in ("isb_model_retain", "isb_model_destroy", "isb_ens_clone", "isb_ens_destroy", "isb_ssf_run_snap",
-                 "isb_bip_run_snap"):
+                 "isb_bip_run_snap", "isb_shard_model_sk", "isb_shard_model_rows_q", "isb_shard_run_create",
+                 "isb_shard_run_destroy", "isb_nccl_unique_id", "isb_shard_run_init_nccl", "isb_shard_run_set_nccl_comm",
+                 "isb_shard_run_ipc_export", "isb_shard_run_ipc_import", "isb_shard_run_barrier", "isb_shard_run_set_spins",
+                 "isb_shard_run_get_spins", "isb_shard_run_steps"):
         assert need in bound, need
     assert len(re.findall(r"Base\.deepcopy_internal\((?:ss)::(SpinSystem|SpinSystemOnBipartiteGraph), dict::IdDict\)", txt)) == 2
     assert txt.count("finalizer(_release!, ss)") == 4            # both constructors of both system types
