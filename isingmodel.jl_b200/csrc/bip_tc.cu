@@ -40,6 +40,7 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -90,6 +91,7 @@ struct TcModel {
     // a square model is kept apart (diag_d / diag_f, multiples of q0) and added by the epilogue
     bool i8 = false;
     double q0 = 1.0;
+    bool i8_wide = false;    // every row's L1 norm (both orientations) < 2^31 quanta: the fast path recombines all planes in int32
     double *diag_d = nullptr;
     float *diag_f = nullptr;
     int ldkv = 0, ldkh = 0;            // K pitch (elements) of the two operand orientations
@@ -156,6 +158,7 @@ struct TcParams {
     int r_off;               // global replica index of row 0 (a run may hold a slice of the replicas): Philox only
     uint32_t fmt;            // operand format: 0 bf16 terms, 1 fp16 terms, 2 int8 digit planes (selects the instantiation)
     float acc_scale;         // accumulator -> field: 1 / (power-of-two pre-scale of the fp16 couplings), 1 for bf16
+    int i8_comb;             // int8 fast path: how the plane sums recombine (i8_field16): 0 per plane, 1 exact pairs, 2 all in int32
     float i8_sf[TC_PMAX];    // int8: weight of plane t, q0 * 256^(P-1-t) (powers of two), as float and as double
     double i8_sd[TC_PMAX];
     int64_t nsteps, k0;      // steps of the whole run (fluctuation array pitch), first step of this launch
@@ -352,6 +355,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same load without the wait: several loads in flight, one tmem_ld_wait() before the first use
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // K-major, 128B-swizzled operand tile (rows x 64 bf16): SBO = 1024 B (8 rows), LBO = 1 (unused), version 1.
 __device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem_tile) {
     const uint32_t lo = ((smem_u32(smem_tile) >> 4) & 0x3FFFu) | (1u << 16);
@@ -367,6 +380,52 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int bn, uint32_t f16)
 // kind::i8 instruction descriptor: D = s32 (c_format 2 at bit 4), A / B = signed 8-bit (1 at bits 7 / 10), K-major
 __device__ __forceinline__ uint32_t umma_idesc_i8(int m, int bn) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// int8 digit planes, fast sampling path: the fields of 16 units from their P exact int32 plane sums.  On entry xf holds the
+// biases.  COMB = 2 (P = 3): the planes recombine EXACTLY in int32, (v0 2^8 + v1) 2^8 + v2 — the model builder checked that
+// every row's L1 norm stays below 2^31 quanta — one conversion and one FFMA per unit; COMB = 1: exact pairs 2^8 v_2i + v_2i+1
+// (|.| <= 32896 K < 2^31 for the K <= 65000 the host admits); COMB = 0: one conversion and one FFMA per plane.  The unsigned
+// shifts wrap modulo 2^32, which is the exact two's-complement result whenever the true value fits.
+template <int P, int COMB>
+__device__ __forceinline__ void i8_field16(uint32_t tq, uint32_t pstride, const float *sf, float (&xf)[16]) {
+    if constexpr (COMB == 0) {
+#pragma unroll
+        for (int t = 0; t < P; ++t) {
+            uint32_t v[16];
+            tmem_ld16(tq + (uint32_t)t * pstride, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xf[j] = fmaf((float)(int)v[j], sf[t], xf[j]);
+        }
+    } else {
+        uint32_t hi[16], v1[16];
+        tmem_ld16_nowait(tq, hi);
+        tmem_ld16_nowait(tq + pstride, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hi[j] = (hi[j] << 8) + v1[j];
+        if constexpr (P == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xf[j] = fmaf((float)(int)hi[j], sf[1], xf[j]);
+        } else if constexpr (P == 3) {
+            tmem_ld16(tq + 2u * pstride, v1);
+            if constexpr (COMB == 2) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) xf[j] = fmaf((float)(int)((hi[j] << 8) + v1[j]), sf[2], xf[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) xf[j] = fmaf((float)(int)hi[j], sf[1], fmaf((float)(int)v1[j], sf[2], xf[j]));
+            }
+        } else {
+            uint32_t lo[16];
+            tmem_ld16_nowait(tq + 2u * pstride, lo);
+            tmem_ld16_nowait(tq + 3u * pstride, v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                xf[j] = fmaf((float)(int)hi[j], sf[1], fmaf((float)(int)((lo[j] << 8) + v1[j]), sf[3], xf[j]));
+        }
+    }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -462,6 +521,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
     jobs.init(p, crank);
     TcJob job;
 
+    // ISB_TC_REGSPLIT (16 sampling warps): the four service warps (TMA producer, MMA issuer, TMEM allocator, spare) hand
+    // registers to the sampling warps (launch: 96 per thread).  The two setmaxnreg sit at the head of code paths that
+    // only meet again at the kernel's last barrier, so that ptxas budgets each path separately.
+    if (warp < 4) {
+#ifdef ISB_TC_REGSPLIT
+    static_assert(TC_EPI_WARPS == 16, "register split is sized for 16 sampling warps");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ISB_TC_REGS_SERVICE) : "memory");
+#endif
     if (warp == 0) {
         // ================================================================ TMA producer
         // (the whole warp walks the loop, one elected lane issues: see the MMA issuer below)
@@ -576,9 +643,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                         const unsigned char *sa = smem + (size_t)s * STB;
                         const uint64_t adesc = umma_desc_sw128(sa);
                         const uint64_t bdesc = umma_desc_sw128(sa + TC_A_BYTES);
+                        // the last K block of a layer may hold fewer than 4 x 32 bytes of real input units (K = 784: 16 of
+                        // 128): the rest of the slot is zero fill, its MMAs are skipped
+                        const int kb_i = I8 ? i : i / p.P;
+                        const int nk = (L.kb_per_blk == L.num_kb && kb_i == num_kb - 1) ? min(4, (L.kin - kb_i * BK + BK / 4 - 1) / (BK / 4)) : 4;
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {  // 4 x 32 operand bytes per slot row: advance 2 descriptor units along K
+                                if (k >= nk) break;
                                 if constexpr (I8)
                                     umma_i8<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
                                 else
@@ -598,46 +670,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 ++tl;
             }
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+#ifdef ISB_TC_REGSPLIT
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ISB_TC_REGS_SAMPLE) : "memory");
+#endif
         // ================================================================ epilogue (sampling rule)
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may read: lanes 32*(warpid % 4) ..
         const int half = ew >> 2;           // the warps of a quadrant interleave the 16-column chunks
         const PhiloxKeys keys = philox_keys(p.seed);
         uint32_t tl = 0;
-        while (jobs.next(p, job)) {
-            const TcLayer &L = p.L[job.layer];
+        int rot = 0;                        // tl % TC_HALVES, kept incrementally
+        // Temperature-derived constants of this thread's replica.  In chain-resident mode they change once per step (the
+        // replica of a thread is fixed), so the schedule load (an L2 round trip), the 64-bit division and the float
+        // reciprocal run once per half-step instead of once per tile: with K <= 784 a tile is only 64-80 units wide, and
+        // this per-tile prologue was 40 % of the sampling warps' instructions (ncu, profiles/r2o_c4_i8x3_ncu_summary.txt).
+        double Td = 0.0;
+        float Tf = 0.f, cS = 0.f, cE = 0.f;
+        bool fast_hs = false;
+        // One tile of layer LY.  The layer index is a compile-time constant (two copies of the tile code): every field of
+        // p.L[LY] is then a direct constant-bank operand instead of an indexed LDC with its scoreboard wait — the per-tile
+        // prologue of the 64-80 unit tiles of config 4 was a fifth of the sampling warps' time (ncu source page).
+        auto epi_tile = [&](auto lyc) {
+            constexpr int LY = decltype(lyc)::value;
+            const TcLayer &L = p.L[LY];
             const uint64_t step_abs = p.step_abs0 + (uint64_t)(job.k - p.k0);
             constexpr int CW = TC_CW;
             const int nchunks = L.bn / CW;
             const int a = tl & 1;
             // the warps of a quadrant take the chunks of a round in an order that rotates from tile to tile: when a
             // tile's last round has fewer chunks than warps, a different warp goes ahead to the next tile each time
-            const int hrot = (half + (int)(tl % (uint32_t)TC_HALVES)) % TC_HALVES;
+            const int hrot = half + rot >= TC_HALVES ? half + rot - TC_HALVES : half + rot;
             const int lrow = quad * 32 + lane;
             const int r = job.m0 + lrow;
             const bool row_ok = r < p.R && (!p.persist || lrow < p.rows_per_cta);
-            // temperature of this thread's replica (per-replica factors make it a per-row quantity); fetched BEFORE the
-            // wait for the accumulator, so that the schedule load (an L2 round trip per tile) overlaps the MMAs instead
-            // of sitting on the MMA -> epilogue -> next half-step critical path
-            double Td = p.Tsched ? __ldg(&p.Tsched[job.k / p.steps_per_T]) : p.T_direct;
-            if (p.tscale && row_ok) Td = __dmul_rn(Td, __ldg(&p.tscale[r]));
-            const float Tf = (float)Td;
-            const float cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2
-            const float cE = Tf > 0.f ? -2.0f * 1.4426950408889634f / Tf : 0.f;  // e^{-2x/T} = 2^{cE x}
+            if (!p.persist || job.hs_first) {
+                // temperature of this thread's replica (per-replica factors make it a per-row quantity); fetched BEFORE
+                // the wait for the accumulator, so that the schedule load overlaps the MMAs
+                Td = p.Tsched ? __ldg(&p.Tsched[job.k / p.steps_per_T]) : p.T_direct;
+                if (p.tscale && row_ok) Td = __dmul_rn(Td, __ldg(&p.tscale[r]));
+                Tf = (float)Td;
+                cS = 0.5f * Tf * 0.69314718055994531f;  // (T/2) ln 2
+                cE = Tf > 0.f ? -2.0f * 1.4426950408889634f / Tf : 0.f;  // e^{-2x/T} = 2^{cE x}
+                // Fast path for the common case (SCA, in-kernel noise, every replica of the warp at T > 0, no peer copies,
+                // a chunk of CW real units): a branch-free body with everything tile-invariant hoisted.  The rule is
+                // evaluated with three fma-pipe operations per unit:
+                //   u (1 + e^{-2x/T}) > 1,  u = (w + 1/2) 2^-32    <=>    (float)w (1 + 2^{cE x}) > 2^32
+                // (x = acc + bias: FADD; cE x: FMUL; the left side: one FFMA; the compare and the sign packing run on the
+                // ALU pipe, the conversion and the exponential on the XU).
+                fast_hs = !EXTF && CW == 16 && p.rule == ISB_BIP_SCA && L.npeer == 0 && !__any_sync(0xFFFFFFFFu, !(Tf > 0.f));
+            }
             tc_wait<CG>(&tfull_bar[a], (tl >> 1) & 1);
             tc_fence_after();
-            const int gpt = p.sig_gpt[job.layer];
+            const int gpt = p.sig_gpt[LY];
             const bool fine = p.persist && job.n_blk >= L.n_tiles - p.sig_fine;
-            uint64_t *sig = sig_bar + job.layer * TC_SIG_MAX + job.n_blk * gpt;
-            // Fast path for the common case (SCA, in-kernel noise, every replica of the warp at T > 0, no peer copies,
-            // a chunk of CW real units): a branch-free body with everything tile-invariant hoisted.  The sampling
-            // epilogue is bound by the fma pipe (Philox's IMAD.WIDE issue at 1 per 4 cycles, FADD/FMUL/FFMA at 1 per
-            // 2), so the rule is evaluated with three fma-pipe operations per unit:
-            //   u (1 + e^{-2x/T}) > 1,  u = (w + 1/2) 2^-32    <=>    (float)w (1 + 2^{cE x}) > 2^32
-            // (x = acc + bias: FADD; cE x: FMUL; the left side: one FFMA; the compare and the sign packing run on the
-            // ALU pipe, the conversion and the exponential on the XU).
-            const bool fastp = !EXTF && CW == 16 && p.rule == ISB_BIP_SCA && L.npeer == 0 && !__any_sync(0xFFFFFFFFu, !(Tf > 0.f));
+            uint64_t *sig = sig_bar + LY * TC_SIG_MAX + job.n_blk * gpt;
+            const bool fastp = fast_hs;
             const int tile_u0 = job.n_blk * L.bn;
             const int nfull = fastp ? min(L.bn, L.nout - tile_u0) / CW : 0;   // chunks the fast path takes
             const float *bias_t = L.bias_f + tile_u0;
@@ -651,23 +740,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
               const int8_t *in8 = L.in_diag ? L.in_diag + (int64_t)rr * L.ld_in + tile_u0 : nullptr;
               const uint32_t tq = taddr_t;          // plane t of the tile: columns [t * bn, (t + 1) * bn) of stage a
               const uint32_t pstride = (uint32_t)L.bn;
+#ifdef ISB_TC_PROBE_NO_EPI  // timing probe only: the contraction without the sampling epilogue
+              for (int g = 0; false;) {
+#else
               for (int g = 0; g * TC_HALVES < nchunks; ++g) {
+#endif
                 const int c = g * TC_HALVES + hrot;
                 if (c < nfull) {
                   // fast path (SCA, in-kernel noise, T > 0, 16 real units): field in float — every plane sum is an exact
-                  // integer and every plane weight a power of two, so the only roundings are the P + 1 additions
+                  // integer and every plane weight a power of two (i8_field16: the planes are recombined in int32 where that is exact)
                   float xf[16];
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
                       const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias_t + c * 16) + q);
                       xf[4 * q] = b4.x; xf[4 * q + 1] = b4.y; xf[4 * q + 2] = b4.z; xf[4 * q + 3] = b4.w;
                   }
-                  for (int t = 0; t < p.P; ++t) {
-                      uint32_t v[16];
-                      tmem_ld16(tq + (uint32_t)t * pstride + (uint32_t)(c * 16), v);
-                      const float sf = p.i8_sf[t];
-#pragma unroll
-                      for (int j = 0; j < 16; ++j) xf[j] = fmaf((float)(int)v[j], sf, xf[j]);
+                  {
+                      const uint32_t tc0 = tq + (uint32_t)(c * 16);
+                      switch (p.i8_comb * 8 + p.P) {     // warp-uniform (kernel parameters)
+                          case 2 * 8 + 3: i8_field16<3, 2>(tc0, pstride, p.i8_sf, xf); break;
+                          case 1 * 8 + 3: i8_field16<3, 1>(tc0, pstride, p.i8_sf, xf); break;
+                          case 1 * 8 + 2: i8_field16<2, 1>(tc0, pstride, p.i8_sf, xf); break;
+                          case 1 * 8 + 4: i8_field16<4, 1>(tc0, pstride, p.i8_sf, xf); break;
+                          case 0 * 8 + 2: i8_field16<2, 0>(tc0, pstride, p.i8_sf, xf); break;
+                          case 0 * 8 + 3: i8_field16<3, 0>(tc0, pstride, p.i8_sf, xf); break;
+                          default: i8_field16<4, 0>(tc0, pstride, p.i8_sf, xf); break;
+                      }
                   }
                   if (in8) {  // the unit's own coupling (square models): diag * own input spin
                       const uint4 sv = __ldcg(reinterpret_cast<const uint4 *>(in8 + c * 16));
@@ -684,7 +782,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                   Philox4 blk[4];
 #pragma unroll
                   for (int q = 0; q < 4; ++q)
+#ifdef ISB_TC_PROBE_NO_PHILOX  // timing probe only: how much of a half-step is the noise generation?
+                      blk[q] = Philox4{(uint32_t)step_abs * 2654435761u + pc2, (pc3 + (uint32_t)(c * 4 + q)) * 40503u, pc2 << 7, keys.k0[3]};
+#else
                       blk[q] = philox4x32_10k((uint32_t)step_abs, (uint32_t)(step_abs >> 32), pc2, pc3 + (uint32_t)(c * 4 + q), keys);
+#endif
                   uint32_t wb[4] = {0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u};
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
@@ -692,7 +794,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                       if (fmaf(wf, ex2_approx(cE * xf[j]), wf) > 4294967296.0f) wb[j >> 2] |= 0xFEu << (8 * (j & 3));
                   }
                   if (row_ok) *reinterpret_cast<uint4 *>(out8 + c * 16) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
-                } else if (c < nchunks) do {
+                } else if (c < nchunks && tile_u0 + c * 16 < L.nout) do {   // (chunks of padding units: nothing to do)
                   // general path: the field in double, EXACT (every term is a multiple of the quantum q0)
                   double xd[16];
 #pragma unroll
@@ -921,6 +1023,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                     for (int g = 0; g < gpt; ++g) mbar_arrive(&sig[g]);
             }
             ++tl;
+            if (++rot == TC_HALVES) rot = 0;
+        };
+        while (jobs.next(p, job)) {
+            if (job.layer)
+                epi_tile(std::integral_constant<int, 1>{});
+            else
+                epi_tile(std::integral_constant<int, 0>{});
         }
     }
     tc_fence_before();
@@ -1164,6 +1273,8 @@ static int bip_tc_model_init_i8(isb_model *m, TcModel *t, const double *W) {
     std::vector<int8_t> wt((size_t)t->rows_t * t->ldkv, 0), wn((size_t)t->rows_n * t->ldkh, 0);
     std::vector<double> dg;
     if (split) dg.assign((size_t)nv, 0.0);
+    // L1 norms (in quanta) of the rows of both orientations: a contraction with +-1 spins cannot exceed them
+    std::vector<long long> l1v((size_t)nv, 0), l1h((size_t)nh, 0);
     for (int i = 0; i < nv; ++i)
         for (int j = 0; j < nh; ++j) {
             const double w = W[(size_t)i * nh + j];
@@ -1172,12 +1283,19 @@ static int bip_tc_model_init_i8(isb_model *m, TcModel *t, const double *W) {
                 continue;
             }
             int8_t d[TC_PMAX];
-            i8_digits(i8_quantize(w, t->q0, maxint), P, d);
+            const long long wi = i8_quantize(w, t->q0, maxint);
+            l1v[i] += wi < 0 ? -wi : wi;
+            l1h[j] += wi < 0 ? -wi : wi;
+            i8_digits(wi, P, d);
             for (int term = 0; term < P; ++term) {
                 wt[(size_t)i8_stack_row(j, term, t->bn_h, P) * t->ldkv + i] = d[term];
                 wn[(size_t)i8_stack_row(i, term, t->bn_v, P) * t->ldkh + j] = d[term];
             }
         }
+    long long l1max = 0;
+    for (long long v : l1v) l1max = std::max(l1max, v);
+    for (long long v : l1h) l1max = std::max(l1max, v);
+    t->i8_wide = l1max < (1ll << 31);
     ISB_CUDA(ctx, cudaMalloc(&t->Wt[0], wt.size()));
     ISB_CUDA(ctx, cudaMalloc(&t->Wn[0], wn.size()));
     ISB_CUDA(ctx, cudaMemcpy(t->Wt[0], wt.data(), wt.size(), cudaMemcpyHostToDevice));
@@ -1479,6 +1597,10 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
         p.i8_sd[term] = term < t->P ? t->q0 * pow(256.0, t->P - 1 - term) : 0.0;
         p.i8_sf[term] = (float)p.i8_sd[term];
     }
+    // plane recombination of the fast sampling path (i8_field16): pairs are exact up to K = 65000, all three planes of
+    // 24-bit couplings when the model's row L1 norms allow it; ISB_I8_COMB = 0 | 1 forces the simpler forms (A/B runs)
+    p.i8_comb = std::max(m->nv, m->nh) <= 65000 ? ((t->P == 3 && t->i8_wide) ? 2 : 1) : 0;
+    if (const char *env = getenv("ISB_I8_COMB")) p.i8_comb = std::min(p.i8_comb, std::max(0, atoi(env)));
     p.R = e->R;
     p.P = t->P;
     p.rule = rule;
@@ -1688,6 +1810,8 @@ int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, in
         p.i8_sd[term] = term < t->P ? t->q0 * pow(256.0, t->P - 1 - term) : 0.0;
         p.i8_sf[term] = (float)p.i8_sd[term];
     }
+    p.i8_comb = (int64_t)m->shard_nb * m->shard_G <= 65000 ? 1 : 0;   // (row L1 norms of generated rows are not known here: no all-int32 form)
+    if (const char *env = getenv("ISB_I8_COMB")) p.i8_comb = std::min(p.i8_comb, std::max(0, atoi(env)));
     p.L[1 - layer] = p.L[layer];
     p.R = R;
     p.r_off = replica_offset;

@@ -1,0 +1,26 @@
+# three accumulator stages + tile-per-warp sampling in chain-resident mode: parity, C4 both ways, bf16 too
+set -u
+mkdir -p gpurun_out
+( timeout 1200 python -m pytest tests/test_gpu_i8.py tests/test_gpu_rowshard.py tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -x -q ) > gpurun_out/r2u_test.log 2>&1
+echo "tests rc=$?"; tail -4 gpurun_out/r2u_test.log
+run() {
+  tag=$1; shift
+  env "$@" timeout 200 python bench.py --no-cpu-baseline --steps 10 $ARGS > gpurun_out/r2u_bench_${tag}.json 2> gpurun_out/r2u_bench_${tag}.err
+  echo "$tag rc=$?"; python -c "
+import json
+d=json.load(open('gpurun_out/r2u_bench_${tag}.json')); r=d['roofline']
+print('  value %.4g frac %.3f half-step %.4f ms clocks %s' % (d['value'], r['frac'], r['kernel_ms_per_half_step'], d['clocks']['sm_mhz']))"
+}
+ARGS="--workload c4 --prec i8x3"
+run c4_tpw A=1
+run c4_wide ISB_TC_TPW=0
+run c4_tpw_bn32 ISB_I8_BN=32
+ARGS="--workload c4 --prec i8x2"
+run c4_i8x2_tpw A=1
+ARGS="--workload c4 --prec bf16x1"
+run c4_bf16x1_tpw A=1
+run c4_bf16x1_wide ISB_TC_TPW=0
+ARGS="--workload c4 --prec fp16x2"
+run c4_fp16x2_tpw A=1
+ARGS="--workload c3 --prec i8x3"
+run c3 A=1
