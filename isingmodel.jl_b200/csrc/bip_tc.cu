@@ -428,6 +428,12 @@ __device__ __forceinline__ void i8_field16(uint32_t tq, uint32_t pstride, const 
     }
 }
 
+#ifdef ISB_TC_TIMING   // measurement build only (scripts/tc_timing.py): where the sampling warps' cycles go
+__device__ long long g_tc_timing[296 * 16 * 4];
+#define TC_TIME(var) const long long var = clock64()
+#else
+#define TC_TIME(var)
+#endif
 // ------------------------------------------------------------------ the kernel
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -682,6 +688,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
         const PhiloxKeys keys = philox_keys(p.seed);
         uint32_t tl = 0;
         int rot = 0;                        // tl % TC_HALVES, kept incrementally
+#ifdef ISB_TC_TIMING
+        long long tm_wait = 0, tm_chunk = 0, tm_post = 0;
+        const long long tm_start = clock64();
+#endif
         // Temperature-derived constants of this thread's replica.  In chain-resident mode they change once per step (the
         // replica of a thread is fixed), so the schedule load (an L2 round trip), the 64-bit division and the float
         // reciprocal run once per half-step instead of once per tile: with K <= 784 a tile is only 64-80 units wide, and
@@ -721,8 +731,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 // ALU pipe, the conversion and the exponential on the XU).
                 fast_hs = !EXTF && CW == 16 && p.rule == ISB_BIP_SCA && L.npeer == 0 && !__any_sync(0xFFFFFFFFu, !(Tf > 0.f));
             }
+            TC_TIME(tw0);
             tc_wait<CG>(&tfull_bar[a], (tl >> 1) & 1);
             tc_fence_after();
+            TC_TIME(tw1);
             const int gpt = p.sig_gpt[LY];
             const bool fine = p.persist && job.n_blk >= L.n_tiles - p.sig_fine;
             uint64_t *sig = sig_bar + LY * TC_SIG_MAX + job.n_blk * gpt;
@@ -1007,6 +1019,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
               }
             }
             }
+            TC_TIME(tw2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -1024,6 +1037,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             }
             ++tl;
             if (++rot == TC_HALVES) rot = 0;
+#ifdef ISB_TC_TIMING
+            tm_wait += tw1 - tw0;
+            tm_chunk += tw2 - tw1;
+            tm_post += clock64() - tw2;
+#endif
         };
         while (jobs.next(p, job)) {
             if (job.layer)
@@ -1031,6 +1049,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             else
                 epi_tile(std::integral_constant<int, 0>{});
         }
+#ifdef ISB_TC_TIMING
+        if (lane == 0 && blockIdx.x < 296) {
+            long long *o = g_tc_timing + ((size_t)blockIdx.x * 16 + (warp & 15)) * 4;
+            o[0] = clock64() - tm_start; o[1] = tm_wait; o[2] = tm_chunk; o[3] = tm_post;
+        }
+#endif
     }
     tc_fence_before();
     if constexpr (CG == 2)
@@ -1042,6 +1066,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
         tmem_dealloc<CG>(tmem_base, 512);
     }
 }
+
+#ifdef ISB_TC_TIMING
+extern "C" int isb_debug_tc_timing(long long *out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_tc_timing, sizeof(long long) * (size_t)std::min(n, 296 * 16 * 4));
+}
+#endif
 
 __global__ void bias_to_float_kernel(const double *b, int n, int npad, float *o) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
