@@ -1,4 +1,4 @@
-"""torchrun worker (2 ranks, NCCL): the all-gather variant of the row-sharded SCA equals the emulation."""
+"""torchrun worker (one rank per GPU, NCCL): the all-gather variant of the row-sharded SCA equals the emulation."""
 import os
 import sys
 

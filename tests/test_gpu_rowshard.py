@@ -1,6 +1,6 @@
 """GPU tests of the row-sharded synchronous SCA (BASELINE config 5): the result must not depend on the number of
 row blocks, must equal the unsharded tensor-core path (itself checked against the oracle), and the NCCL
-all-gather variant (2 processes, needs 2 GPUs) must equal the single-process emulation."""
+all-gather variants (2, 4 and 8 processes, one per GPU) must equal the single-process emulation."""
 import os
 import subprocess
 import sys
@@ -104,12 +104,15 @@ def test_step_loop_inside_the_library_single_block(pkg, ctx, synth, prec_name, r
     assert np.array_equal(abi.get_spins(), emu.get_spins())
 
 
-def test_nccl_all_gather_two_ranks(pkg, ctx):
+@pytest.mark.parametrize("ranks", [2, 4, 8])
+def test_nccl_all_gather_ranks(pkg, ctx, ranks):
+    """One process per GPU under torchrun: every exchange mode (NCCL all-gather, the two-group pipeline, copy-engine pushes,
+    peer stores in the epilogue, and the library's own isb_shard_run_* loops) against the single-process emulation."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29671",
+    if torch.cuda.device_count() < ranks:
+        pytest.skip(f"needs {ranks} GPUs (gpurun --gpus {ranks})")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29671 + ranks),
                           os.path.join(ROOT, "tests", "rowshard_worker.py")], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "ROWSHARD-OK" in res.stdout
