@@ -34,9 +34,32 @@ def _checked_spins(value, shape, name):
     a = np.atleast_2d(np.asarray(value))
     if a.shape != shape:
         raise ValueError(f"{name} has the wrong shape")
-    if not np.all(np.abs(np.asarray(a, dtype=np.float64)) == 1.0):
+    if a.dtype == np.int8:
+        # the common case (and the bench's 33 MB layers): one pass over the bytes instead of a Float64 copy —
+        # +1 = 0x01 and -1 = 0xFF are the only bytes x with (x + 1) & 0xFD == 0
+        ok = not np.any((a.view(np.uint8) + np.uint8(1)) & np.uint8(0xFD))
+    else:
+        ok = bool(np.all(np.abs(np.asarray(a, dtype=np.float64)) == 1.0))
+    if not ok:
         raise ValueError("spins must be +1 / -1")
     return np.ascontiguousarray(a, dtype=np.int8)
+
+
+def _device_validates(value, shape, ens):
+    """int8 layers of the right shape go to the library unchecked by the host mirror: isb_ens_set_spins / _set_hidden scan
+    for +-1 themselves and reject BEFORE anything changes (one pass over the bytes instead of two more here: the layers
+    of config 3 are 33 MB each)."""
+    a = np.asarray(value)
+    return ens is not None and a.dtype == np.int8 and np.atleast_2d(a).shape == shape
+
+
+def _set_on_device(setter, v):
+    try:
+        setter(v)
+    except _lib.IsbError as e:
+        if e.code == _lib.ERR_ARG:
+            raise ValueError("spins must be +1 / -1") from e
+        raise
 
 
 def _squeeze(self, arr):
@@ -175,6 +198,13 @@ class SpinSystem:
 
     @spinConfiguration.setter
     def spinConfiguration(self, value):
+        if _device_validates(value, self._host_spins.shape, self._ens):
+            v = np.ascontiguousarray(np.atleast_2d(np.asarray(value)))
+            _set_on_device(self._ens.set_spins, v)           # validated there BEFORE anything changes
+            self._snap = None
+            self._host_spins = v
+            self._dev_newer = False
+            return
         v = _checked_spins(value, self._host_spins.shape, "spin configuration")   # validated BEFORE anything changes
         self._snap = None       # during a replay (makeSampler_) the consumer's state wins: the sampler resumes from it
         self._host_spins = v
@@ -314,10 +344,14 @@ class SpinSystemOnBipartiteGraph:
             self._ens.set_hidden(self._host_t)
         return self._ens
 
-    def _pull(self):
+    def _pull(self, overwriting=None):
+        """Bring the host copies up to date; `overwriting` = "s" / "t": that layer is about to be replaced, skip its
+        download (33 MB per layer at config 3)."""
         if self._dev_newer:
-            self._host_s = self._ens.get_spins()
-            self._host_t = self._ens.get_hidden()
+            if overwriting != "s":
+                self._host_s = self._ens.get_spins()
+            if overwriting != "t":
+                self._host_t = self._ens.get_hidden()
             self._dev_newer = False
 
     def _invalidate_model(self):
@@ -333,12 +367,14 @@ class SpinSystemOnBipartiteGraph:
 
     @spinConfiguration.setter
     def spinConfiguration(self, value):
-        v = _checked_spins(value, self._host_s.shape, "spin configuration")
+        on_dev = _device_validates(value, self._host_s.shape, self._ens)
+        v = np.ascontiguousarray(np.atleast_2d(np.asarray(value))) if on_dev else \
+            _checked_spins(value, self._host_s.shape, "spin configuration")
         self._restore_snapshot()    # during a replay the other layer keeps the shown state, the sampler resumes from here
-        self._pull()
-        self._host_s = v
+        self._pull(overwriting="s")
         if self._ens is not None:
-            self._ens.set_spins(v)
+            _set_on_device(self._ens.set_spins, v)           # (an int8 layer is validated there, before it changes anything)
+        self._host_s = v
 
     @property
     def hiddenLayer(self):
@@ -349,12 +385,14 @@ class SpinSystemOnBipartiteGraph:
 
     @hiddenLayer.setter
     def hiddenLayer(self, value):
-        v = _checked_spins(value, self._host_t.shape, "hidden layer")
+        on_dev = _device_validates(value, self._host_t.shape, self._ens)
+        v = np.ascontiguousarray(np.atleast_2d(np.asarray(value))) if on_dev else \
+            _checked_spins(value, self._host_t.shape, "hidden layer")
         self._restore_snapshot()
-        self._pull()
-        self._host_t = v
+        self._pull(overwriting="t")
         if self._ens is not None:
-            self._ens.set_hidden(v)
+            _set_on_device(self._ens.set_hidden, v)
+        self._host_t = v
 
     @property
     def couplingCoefficients(self):

@@ -447,7 +447,7 @@ class Ensemble:
         self._chk(load().isb_ens_set_spins(self.handle, ptr(S), S.shape[1]))
 
     def get_spins(self):
-        S = np.zeros((self.R, self.nv), dtype=np.int8)
+        S = np.empty((self.R, self.nv), dtype=np.int8)
         self._chk(load().isb_ens_get_spins(self.handle, ptr(S), self.nv))
         return S
 
@@ -456,7 +456,7 @@ class Ensemble:
         self._chk(load().isb_ens_set_hidden(self.handle, ptr(Tm), Tm.shape[1]))
 
     def get_hidden(self):
-        Tm = np.zeros((self.R, self.nh), dtype=np.int8)
+        Tm = np.empty((self.R, self.nh), dtype=np.int8)
         self._chk(load().isb_ens_get_hidden(self.handle, ptr(Tm), self.nh))
         return Tm
 

@@ -96,53 +96,57 @@ __global__ void __launch_bounds__(BIPX_THREADS) bip_half_kernel(const BipHalfPar
 }
 
 // E_r = -sum_i sigma_i (sum_j W_ij tau_j) - sum_i h_i sigma_i - sum_j b_j tau_j.
-// Pass 1: CTA (x, y) covers 128 visible units of BIPX_CH chains (one coalesced read of a W row serves all of
-// them, as in bip_half_kernel) and writes one partial sum per chain; pass 2 adds the partials of a chain in a
-// fixed order (no atomics: the energies are reproducible bit for bit).
+// Pass 1: CTA (x, y) covers 128 visible units of BIPE_CH chains (one coalesced read of a W row serves all of them: W is
+// pulled from L2 R / 32 times per call — 32 chains instead of bip_half_kernel's 8 took config 3's energies from 37 to
+// ~12 ms) and writes one partial sum per chain; pass 2 adds the partials of a chain in a fixed order (no atomics: the
+// energies are reproducible bit for bit).  Every chain's sums run over ascending j like before: same values.
+constexpr int BIPE_CH = 32;
 __global__ void __launch_bounds__(BIPX_THREADS)
 bip_energy_partial_kernel(const double *__restrict__ Wt /*[nh][nv]*/, const double *__restrict__ h,
                           const double *__restrict__ b, const int8_t *sig, int64_t lds, const int8_t *tau, int64_t ldh,
                           int nv, int nh, int R, double *partial /*[gridDim.x][R]*/) {
-    extern __shared__ unsigned char tmask[];  // [nh] bit c = hidden spin of chain c is +1
-    __shared__ double red[BIPX_THREADS / 32][BIPX_CH];
-    const int r0 = blockIdx.y * BIPX_CH;
-    const int nch = min(BIPX_CH, R - r0);
+    extern __shared__ uint32_t tmask[];  // [nh] bit c = hidden spin of chain c is +1
+    __shared__ double red[BIPX_THREADS / 32][BIPE_CH];
+    const int r0 = blockIdx.y * BIPE_CH;
+    const int nch = min(BIPE_CH, R - r0);
     for (int j = threadIdx.x; j < nh; j += blockDim.x) {
-        unsigned m = 0;
+        uint32_t m = 0;
         for (int c = 0; c < nch; ++c) m |= (tau[(int64_t)(r0 + c) * ldh + j] > 0 ? 1u : 0u) << c;
-        tmask[j] = (unsigned char)m;
+        tmask[j] = m;
     }
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double part[BIPX_CH];
+    double part[BIPE_CH];
 #pragma unroll
-    for (int c = 0; c < BIPX_CH; ++c) part[c] = 0.0;
+    for (int c = 0; c < BIPE_CH; ++c) part[c] = 0.0;
     if (i < nv) {
-        double row[BIPX_CH];
+        double row[BIPE_CH];
 #pragma unroll
-        for (int c = 0; c < BIPX_CH; ++c) row[c] = 0.0;
+        for (int c = 0; c < BIPE_CH; ++c) row[c] = 0.0;
         for (int j = 0; j < nh; ++j) {
             const double w = __ldg(Wt + (int64_t)j * nv + i);
-            const unsigned m = tmask[j];
+            const uint32_t m = tmask[j];
 #pragma unroll
-            for (int c = 0; c < BIPX_CH; ++c) row[c] += ((m >> c) & 1u) ? w : -w;
+            for (int c = 0; c < BIPE_CH; ++c) row[c] += ((m >> c) & 1u) ? w : -w;
         }
         const double hi = h[i];
-        for (int c = 0; c < nch; ++c) {
-            const double si = (double)sig[(int64_t)(r0 + c) * lds + i];
-            part[c] = -(si * row[c] + hi * si);
-        }
+#pragma unroll
+        for (int c = 0; c < BIPE_CH; ++c)
+            if (c < nch) {
+                const double si = (double)sig[(int64_t)(r0 + c) * lds + i];
+                part[c] = -(si * row[c] + hi * si);
+            }
     }
     if (blockIdx.x == 0)  // the hidden-bias term, once per chain
         for (int j = threadIdx.x; j < nh; j += blockDim.x) {
             const double bj = b[j];
-            const unsigned m = tmask[j];
+            const uint32_t m = tmask[j];
 #pragma unroll
-            for (int c = 0; c < BIPX_CH; ++c) part[c] -= ((m >> c) & 1u) ? bj : -bj;
+            for (int c = 0; c < BIPE_CH; ++c) part[c] -= ((m >> c) & 1u) ? bj : -bj;
         }
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int c = 0; c < BIPX_CH; ++c) {
+    for (int c = 0; c < BIPE_CH; ++c) {
         const double v = warp_sum(part[c]);
         if (lane == 0) red[w][c] = v;
     }
@@ -194,8 +198,14 @@ int bip_energy_device(isb_ens *e, double *d_E) {
     double *partial;
     int rc = dev_reserve(ctx, SCR_TC0, (size_t)nparts * e->R * sizeof(double), (void **)&partial);
     if (rc) return rc;
-    dim3 grid(nparts, (e->R + BIPX_CH - 1) / BIPX_CH);
-    bip_energy_partial_kernel<<<grid, BIPX_THREADS, m->nh, ctx->stream>>>(m->Wt64, m->hb64, m->bb64, e->spins, e->lds,
+    dim3 grid(nparts, (e->R + BIPE_CH - 1) / BIPE_CH);
+    const size_t mask_bytes = (size_t)m->nh * sizeof(uint32_t);
+    if (mask_bytes > 48 * 1024) {
+        if (mask_bytes + 8192 > ctx->smem_optin)
+            return fail(ctx, ISB_ERR_UNSUPPORTED, "bipartite energy: %d hidden units exceed the shared memory", m->nh);
+        ISB_CUDA(ctx, cudaFuncSetAttribute(bip_energy_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_bytes));
+    }
+    bip_energy_partial_kernel<<<grid, BIPX_THREADS, mask_bytes, ctx->stream>>>(m->Wt64, m->hb64, m->bb64, e->spins, e->lds,
                                                                           e->hidden, e->ldh, m->nv, m->nh, e->R, partial);
     bip_energy_reduce_kernel<<<(e->R + 255) / 256, 256, 0, ctx->stream>>>(partial, nparts, e->R, d_E);
     ISB_CUDA(ctx, cudaGetLastError());
