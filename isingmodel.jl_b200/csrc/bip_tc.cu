@@ -347,6 +347,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+#ifdef ISB_TC_PROBE_NO_LDTM   // timing probe only: how much of a chunk is the tcgen05.ld latency?
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = taddr * 2654435761u + (uint32_t)j * 40503u;
+    return;
+#endif
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -357,6 +362,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 // the same load without the wait: several loads in flight, one tmem_ld_wait() before the first use
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+#ifdef ISB_TC_PROBE_NO_LDTM
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = taddr * 2654435761u + (uint32_t)j * 40503u;
+    return;
+#endif
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -805,7 +815,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                       const float wf = (float)philox_pick(blk[j >> 2], (uint32_t)(j & 3));
                       if (fmaf(wf, ex2_approx(cE * xf[j]), wf) > 4294967296.0f) wb[j >> 2] |= 0xFEu << (8 * (j & 3));
                   }
+#ifdef ISB_TC_PROBE_NO_STORE   // timing probe only: the sampled spins are (almost) never stored
+                  if (row_ok && (wb[0] ^ (wb[1] << 1) ^ (wb[2] << 2) ^ (wb[3] << 3)) == 0x12345678u) *reinterpret_cast<uint4 *>(out8 + c * 16) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+#else
                   if (row_ok) *reinterpret_cast<uint4 *>(out8 + c * 16) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+#endif
                 } else if (c < nchunks && tile_u0 + c * 16 < L.nout) do {   // (chunks of padding units: nothing to do)
                   // general path: the field in double, EXACT (every term is a multiple of the quantum q0)
                   double xd[16];
