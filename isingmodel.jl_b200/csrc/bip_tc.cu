@@ -167,6 +167,8 @@ struct TcParams {
     int64_t steps_per_T;
     double T_direct;         // temperature when Tsched is NULL
     uint64_t seed, step_abs0;  // Philox step of k0
+    PhiloxKeys keys;           // the ten round keys of `seed`, filled by the host: constant-bank operands of the Philox
+                               // rounds instead of twenty registers of every sampling thread
 };
 
 // The tile jobs of a CTA, enumerated identically by the producer, the MMA issuer and the epilogue warps.
@@ -649,6 +651,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                 const int a = tl & 1;
                 // one accumulator stage per tile: all K blocks x terms (16-bit), or the stacked planes (int8), into it
                 const int iters = I8 ? num_kb : num_kb * p.P;
+                // the last K block of a layer may hold fewer than 4 x 32 bytes of real input units (K = 784: 16 of 128): the
+                // rest of the slot is zero fill, its MMAs are skipped.  (No division in the issue loop: it is the kernel's
+                // critical thread, see above.)
+                const int i_tail = L.kb_per_blk == L.num_kb ? iters - (I8 ? 1 : p.P) : iters;   // first iteration of the last K block
+                const int nk_tail = min(4, (L.kin - (num_kb - 1) * BK + BK / 4 - 1) / (BK / 4));
                 {
                     tc_wait1<CG>(&tempty_bar[a], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                     const uint32_t d_tmem = tmem_u + (uint32_t)(a * TC_BN_MAX);
@@ -659,18 +666,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                         const unsigned char *sa = smem + (size_t)s * STB;
                         const uint64_t adesc = umma_desc_sw128(sa);
                         const uint64_t bdesc = umma_desc_sw128(sa + TC_A_BYTES);
-                        // the last K block of a layer may hold fewer than 4 x 32 bytes of real input units (K = 784: 16 of
-                        // 128): the rest of the slot is zero fill, its MMAs are skipped
-                        const int kb_i = I8 ? i : i / p.P;
-                        const int nk = (L.kb_per_blk == L.num_kb && kb_i == num_kb - 1) ? min(4, (L.kin - kb_i * BK + BK / 4 - 1) / (BK / 4)) : 4;
+                        const int nk = i >= i_tail ? nk_tail : 4;
                         if (elect_one()) {
+                            if (nk == 4) {   // (the common block, kept as four back-to-back issues)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {  // 4 x 32 operand bytes per slot row: advance 2 descriptor units along K
-                                if (k >= nk) break;
-                                if constexpr (I8)
-                                    umma_i8<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
-                                else
-                                    umma_bf16<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+                                for (int k = 0; k < 4; ++k) {  // 4 x 32 operand bytes per slot row: advance 2 descriptor units along K
+                                    if constexpr (I8)
+                                        umma_i8<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+                                    else
+                                        umma_bf16<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+                                }
+                            } else {
+                                for (int k = 0; k < nk; ++k) {
+                                    if constexpr (I8)
+                                        umma_i8<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+                                    else
+                                        umma_bf16<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+                                }
                             }
                             umma_commit<CG>(&empty_bar[s]);  // slot free (in both CTAs of a pair) when these MMAs have read it
                         }
@@ -695,7 +707,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may read: lanes 32*(warpid % 4) ..
         const int half = ew >> 2;           // the warps of a quadrant interleave the 16-column chunks
-        const PhiloxKeys keys = philox_keys(p.seed);
+        const PhiloxKeys &keys = p.keys;
         uint32_t tl = 0;
         int rot = 0;                        // tl % TC_HALVES, kept incrementally
 #ifdef ISB_TC_TIMING
@@ -779,15 +791,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
                   }
                   {
                       const uint32_t tc0 = tq + (uint32_t)(c * 16);
-                      switch (p.i8_comb * 8 + p.P) {     // warp-uniform (kernel parameters)
-                          case 2 * 8 + 3: i8_field16<3, 2>(tc0, pstride, p.i8_sf, xf); break;
-                          case 1 * 8 + 3: i8_field16<3, 1>(tc0, pstride, p.i8_sf, xf); break;
-                          case 1 * 8 + 2: i8_field16<2, 1>(tc0, pstride, p.i8_sf, xf); break;
-                          case 1 * 8 + 4: i8_field16<4, 1>(tc0, pstride, p.i8_sf, xf); break;
-                          case 0 * 8 + 2: i8_field16<2, 0>(tc0, pstride, p.i8_sf, xf); break;
-                          case 0 * 8 + 3: i8_field16<3, 0>(tc0, pstride, p.i8_sf, xf); break;
-                          default: i8_field16<4, 0>(tc0, pstride, p.i8_sf, xf); break;
-                      }
+                      const int form = p.i8_comb * 8 + p.P;   // warp-uniform (kernel parameters); a chain of uniform
+                      if (form == 2 * 8 + 3)                   // branches, the common forms first (a jump table costs an
+                          i8_field16<3, 2>(tc0, pstride, p.i8_sf, xf);   // indirect branch per chunk)
+                      else if (form == 1 * 8 + 3)
+                          i8_field16<3, 1>(tc0, pstride, p.i8_sf, xf);
+                      else if (form == 1 * 8 + 2)
+                          i8_field16<2, 1>(tc0, pstride, p.i8_sf, xf);
+                      else if (form == 1 * 8 + 4)
+                          i8_field16<4, 1>(tc0, pstride, p.i8_sf, xf);
+                      else if (form == 0 * 8 + 2)
+                          i8_field16<2, 0>(tc0, pstride, p.i8_sf, xf);
+                      else if (form == 0 * 8 + 3)
+                          i8_field16<3, 0>(tc0, pstride, p.i8_sf, xf);
+                      else
+                          i8_field16<4, 0>(tc0, pstride, p.i8_sf, xf);
                   }
                   if (in8) {  // the unit's own coupling (square models): diag * own input spin
                       const uint4 sv = __ldcg(reinterpret_cast<const uint4 *>(in8 + c * 16));
@@ -1057,11 +1075,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bip_tc_kernel(const __grid_cons
             tm_post += clock64() - tw2;
 #endif
         };
-        while (jobs.next(p, job)) {
-            if (job.layer)
-                epi_tile(std::integral_constant<int, 1>{});
-            else
-                epi_tile(std::integral_constant<int, 0>{});
+        // The sampling warps walk their tiles with plain nested loops (the same sequence TcJobIter produces for the producer
+        // and the issuer): the generic iterator cost them ~36 instructions and three spilled words per tile.
+        {
+            const int nst_loop = p.persist ? p.nsteps_seg : 1;
+            const int stride = gridDim.x / p.cg;
+            job.hs = 0;
+            for (int step = 0; step < nst_loop; ++step) {
+                job.k = p.k0 + step;
+                for (int pass = 0; pass < (p.persist ? 2 : 1); ++pass) {
+                    const int layer = p.persist ? 1 - pass : p.layer;
+                    const int nt = p.L[layer].n_tiles;
+                    const int first = p.persist ? 0 : blockIdx.x / p.cg;
+                    const int last = p.persist ? nt : p.m_tiles * nt;
+                    job.layer = layer;
+                    for (int tile = first; tile < last; tile += p.persist ? 1 : stride) {
+                        if (p.persist) {
+                            job.m0 = blockIdx.x * p.rows_per_cta;
+                            job.n_blk = tile;
+                            job.hs_first = tile == 0;
+                        } else {
+                            job.m0 = (tile / nt) * (TC_BM * p.cg) + crank * TC_BM;
+                            job.n_blk = tile % nt;
+                            job.hs_first = false;
+                        }
+                        if (layer)
+                            epi_tile(std::integral_constant<int, 1>{});
+                        else
+                            epi_tile(std::integral_constant<int, 0>{});
+                    }
+                }
+            }
         }
 #ifdef ISB_TC_TIMING
         if (lane == 0 && blockIdx.x < 296) {
@@ -1654,6 +1698,7 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     p.tscale = e->d_tscale;
     p.steps_per_T = steps_per_T;
     p.seed = seed;
+    p.keys = philox_keys(seed);
     p.fmt = t->i8 ? 2u : (t->f16 ? 1u : 0u);
     p.acc_scale = (float)(1.0 / t->wscale);
     p.m_tiles = m_tiles;
@@ -1868,6 +1913,7 @@ int shard_halfstep_device(isb_model *m, int R, int replica_offset, int layer, in
     p.T_direct = T;
     p.steps_per_T = 1;
     p.seed = seed;
+    p.keys = philox_keys(seed);
     p.step_abs0 = step_abs;
     p.persist = 0;
     p.layer = layer;
