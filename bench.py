@@ -501,17 +501,17 @@ def run_c1(rt, args, steps, warmup, cpu=True):
     flips = float(np.mean([s["flips"] for s in stats]))
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     line = base_line(upd_step * steps * rt.world / t_dev, rt.world, steps, warmup, 1e3 * t_dev / steps, "f64", c1_config(args))
-    # issue-slot roofline: no J streaming at all (4 neighbours per site), the kernel is bound by the instructions it
-    # issues per update; the count comes from the SASS of the steady-state loop and the peak is
+    # issue-slot roofline: no J streaming at all (4 neighbours per site, spins as bits in shared memory), the kernel is bound
+    # by the instructions it issues; the count per 32-site window comes from ncu (profiles/) and the peak is
     # 4 warp-instructions / clk / SM
     ipu = C1_INSTR_PER_UPDATE
     issue_peak = 4.0 * 32.0 * rt.sms * sm_mhz * 1e6 / ipu          # updates/s at 100 % issue utilisation
     line["roofline"] = {"bound": "issue", "achieved": upd_step / kern_s, "peak": issue_peak, "unit": "updates/s",
                         "frac": upd_step / kern_s / issue_peak, "traffic": None, "kernel": C1_KERNEL, "kernel_ms": 1e3 * kern_s,
                         "accept_rate": flips / upd_step,
-                        "accounting": f"issue slots: {ipu} thread-instructions per update (SASS count of the kernel's steady-state "
-                                      f"loop, DESIGN.md) at 4 warp-instructions/clk/SM x {rt.sms} SMs x {sm_mhz:.0f} MHz; the working "
-                                      "set of a chain is on chip: no HBM traffic in steady state",
+                        "accounting": f"issue slots: {ipu} warp instructions per 32-site window of a chain (ncu count of the committed "
+                                      f"kernel, profiles/r2o_c1_lattice_ncu_summary.txt) at 4 warp-instructions/clk/SM x {rt.sms} SMs x "
+                                      f"{sm_mhz:.0f} MHz; the working set of a chain is on chip: no HBM traffic in steady state",
                         "hbm_accounting_GBps": flips * 4 * 12.0 / kern_s / 1e9}
     line["e2e"] = {"value": upd_step * n_e2e * rt.world / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(pin.nbytes),
                    "d2h_bytes_per_step": int(S.nbytes + E.nbytes), "mean_final_energy": float(E.mean()),
@@ -525,9 +525,11 @@ def run_c1(rt, args, steps, warmup, cpu=True):
     return line
 
 
-# instructions per update of C1's dominant kernel (SASS count) and its name
-C1_KERNEL = "isb::ssf_sparse_kernel"
-C1_INSTR_PER_UPDATE = 60.0
+# C1's dominant kernel and the warp instructions it executes per 32-site window (= thread-instructions per update with all
+# 32 lanes counted): ncu of the committed kernel, 14 617 209 657 warp instructions / 39 321 600 windows
+# (profiles/r2o_c1_lattice_ncu_summary.txt)
+C1_KERNEL = "isb::ssf_lattice_kernel"
+C1_INSTR_PER_UPDATE = 371.7
 
 
 # ---------------------------------------------------------------------------------------------- C3 / C4: contractions
