@@ -1658,6 +1658,15 @@ static int launch_steps(isb_ens *e, int rule, int fluct_mode, const double *d_Fv
     rows = std::min(rows, TC_BM);
     bool persist = rows >= 96;
     if (const char *env = getenv("ISB_TC_PERSIST")) persist = atoi(env) != 0 && e->R >= 1;
+    // A CTA's time per step does not depend on how many of its 128 tile rows hold replicas, and these runs are POWER-capped
+    // (C4: ~1000 W, 1.75 GHz of 1.965): full tiles on fewer SMs do the same work per cycle with fewer SMs drawing power —
+    // 16384 chains as 128 CTAs x 128 rows instead of 148 x 111 measured 0.313 -> 0.326 of the bf16 burst rate at 1.84 GHz.
+    // ISB_TC_ROWS overrides (A/B runs; 0 = spread over all SMs).
+    if (persist) {
+        int want = TC_BM;
+        if (const char *env = getenv("ISB_TC_ROWS")) want = atoi(env);
+        if (want >= rows && want <= TC_BM) rows = want;
+    }
     // tile widths: least padding per CTA in chain-resident mode, fewest (waves x width) otherwise
     // (int8 digit planes: the tile width is part of the stacked storage order, fixed when the model was built)
     const int sp = t->i8 ? t->P : 1;
