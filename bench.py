@@ -765,7 +765,7 @@ def run_c5(rt, args, prec_name, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10, help="timed steps (default 10: a C2 step is 195 ms, so the timed region is 2 s)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sweeps", type=int, default=1000, help="c2: annealing sweeps per step (SURVEY §8d C2: 1000)")
