@@ -227,6 +227,15 @@ class Runtime:
             self.dist.destroy_process_group()
 
 
+def captured_traffic(key):
+    """DRAM bytes per launch of a dominant kernel from its committed `ncu --set full` capture (profiles/roofline_traffic.json)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["other_kernels"][key]
+        return float(d["bytes"]), d["source"]
+    except Exception:
+        return None, None
+
+
 def tensor_peak(pk, t_dev):
     """The tensor-roofline denominator for a timed region of `t_dev` device seconds, as MEASURED_PEAKS.json defines its two
     figures: the cuBLAS bf16 BURST rate for a kernel timed alone in a short region, the SUSTAINED rate (cuBLAS back to back
@@ -519,6 +528,9 @@ def run_c1(rt, args, steps, warmup, cpu=True):
                                       f"kernel, profiles/r2o_c1_lattice_ncu_summary.txt) at 4 warp-instructions/clk/SM x {rt.sms} SMs x "
                                       f"{sm_mhz:.0f} MHz; the working set of a chain is on chip: no HBM traffic in steady state",
                         "hbm_accounting_GBps": flips * 4 * 12.0 / kern_s / 1e9}
+    tb, tsrc = captured_traffic("ssf_lattice_kernel_c1_per_300_sweep_launch")
+    if tb:
+        line["roofline"].update({"traffic": tb, "traffic_source": tsrc + "; independent of the sweep count (spins in, bits on chip)"})
     line["e2e"] = {"value": upd_step * n_e2e * rt.world / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(pin.nbytes),
                    "d2h_bytes_per_step": int(S.nbytes + E.nbytes), "mean_final_energy": float(E.mean()),
                    "exact_mean_energy_kaufman": -1468.4}
@@ -650,6 +662,16 @@ def run_sca(rt, args, which, precs, steps, warmup, cpu=True):
                                          "W'sigma / W tau, once); executed = passes x algorithmic in bf16-pass equivalents "
                                          "(an int8 pass runs at twice the bf16 tensor rate and moves half the bytes)",
                            "storage": PREC_NOTE[prec_name]}
+        if prec_name == "i8x3":
+            launches_per_step = float(np.mean([s["launches"] for s in stats]))
+            if which == "c3" and launches_per_step == 2 * nst:          # one launch per half-step, as captured
+                tb, tsrc = captured_traffic("bip_tc_kernel_c3_i8x3_per_half_step_launch")
+                if tb:
+                    res["roofline"].update({"traffic": tb, "traffic_source": tsrc})
+            elif which == "c4" and launches_per_step == 1:              # chain-resident: one launch per bench step
+                tb, tsrc = captured_traffic("bip_tc_kernel_c4_i8x3_per_100_step_launch")
+                if tb:
+                    res["roofline"].update({"traffic": tb * nst / 100.0, "traffic_source": tsrc + f"; scaled from 100 to {nst} SCA steps per launch"})
         res["gpu_launches"] = int(sum(s["launches"] for s in stats))
         res["clocks"] = clocks
         if e2e:
