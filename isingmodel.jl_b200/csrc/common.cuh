@@ -121,7 +121,7 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 }
 
 // ------------------------------------------------------------------ Philox4x32-10
-// Salmon, Moraes, Dror, Shaw, SC'11.  Checked word for word against oracle/ (tests/test_philox.py).
+// Salmon, Moraes, Dror, Shaw, SC'11.  Checked word for word against oracle/ and the Random123 known answers (tests/test_oracle.py, tests/test_gpu_parity.py::test_philox_raw_matches_oracle_and_kat).
 struct Philox4 {
     uint32_t x, y, z, w;
 };
