@@ -510,6 +510,16 @@ def run_c1(rt, args, steps, warmup, cpu=True):
         e1.set_spins(pin[:1])
         e1.ssf_run(L.RULE_METROPOLIS, lat_sweeps * N, seed=7, T=Tarr, steps_per_T=lat_sweeps * N)
     lat_ms = e1.last_stats()["kernel_ms"]
+    # beside the reference's sequential sweep: the two-colour sweep order (ISB_ORDER_CHECKERBOARD, SURVEY §8f rank 1 — one
+    # particular site list of the 3-argument update!, executed 32 sites at a time), same model, same rule, same noise words
+    cb = {}
+    for name, eX, reps in (("all_replicas", ens, 1), ("single_chain", e1, 2)):
+        sw = sweeps if name == "all_replicas" else lat_sweeps
+        for _ in range(1 + reps):
+            eX.set_spins(pin if name == "all_replicas" else pin[:1])
+            eX.ssf_run(L.RULE_METROPOLIS, sw * N, order=L.ORDER_CHECKERBOARD, seed=7, T=Tarr, steps_per_T=sw * N)
+        cb[name] = (sw, eX.last_stats()["kernel_ms"])
+    cb_Emean = float(ens.energy().mean())
     if rt.rank != 0:
         return None
     kern_s = float(np.mean([s["kernel_ms"] for s in stats])) / 1e3
@@ -536,6 +546,13 @@ def run_c1(rt, args, steps, warmup, cpu=True):
                    "exact_mean_energy_kaufman": -1468.4}
     line["single_chain_latency"] = {"replicas": 1, "sweeps": lat_sweeps, "kernel_ms": lat_ms,
                                     "us_per_sweep": 1e3 * lat_ms / lat_sweeps, "updates_per_s": lat_sweeps * N / (lat_ms / 1e3)}
+    line["checkerboard_order"] = {
+        "note": "NOT the headline: the same model and rule swept in two-colour order (all sites with x + y even, then the others) "
+                "instead of the reference's sequential site order; bit-exact with the oracle walking that site list "
+                "(tests/test_gpu_lattice.py), kernel isb::ssf_lattice_cb_kernel",
+        "value": N * R * cb["all_replicas"][0] / (cb["all_replicas"][1] / 1e3), "unit": UNIT, "kernel_ms": cb["all_replicas"][1],
+        "mean_final_energy": cb_Emean,
+        "single_chain_us_per_sweep": 1e3 * cb["single_chain"][1] / cb["single_chain"][0]}
     line["gpu_launches"] = int(sum(s["launches"] for s in stats))
     line["clocks"] = clocks
     if cpu and rt.world == 1 and not args.no_cpu_baseline:

@@ -57,7 +57,11 @@ enum { ISB_BIP_SCA = 0, ISB_BIP_MA = 1 };
 enum {
     ISB_ORDER_SEQUENTIAL = 0, /* node = (start + k) mod N                                        */
     ISB_ORDER_LIST = 1,       /* node = nodes[k]   (SamplingHelper.jl:39 pre-drawn list)         */
-    ISB_ORDER_RANDOM = 2      /* node drawn by the library's Philox stream, shared by replicas    */
+    ISB_ORDER_RANDOM = 2,     /* node drawn by the library's Philox stream, shared by replicas    */
+    ISB_ORDER_CHECKERBOARD = 3 /* periodic L x L lattices only: position k of a sweep (start = first position) visits the
+                                * k-th site with (x + y) even in ascending site index, then the sites with (x + y) odd —
+                                * the site list a caller of the 3-argument update! would pass for a two-colour sweep; the
+                                * sites of one colour do not interact, the library updates 32 of them at once */
 };
 /* how an externally supplied fluctuation array is indexed */
 enum {

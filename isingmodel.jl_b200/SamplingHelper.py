@@ -93,7 +93,8 @@ def run_(ua, maxMCSteps, annealingSchedule=None, rng=None, *, seed=0, step_offse
             if ua._rule != _lib.RULE_HOPFIELD:
                 per_rep = per_replica_noise and R > 1
                 fluct = ua.distribution.rand(rng, (R, maxMCSteps) if per_rep else maxMCSteps)
-        o = _lib.ORDER_SEQUENTIAL if order == "sequential" else (_lib.ORDER_LIST if nodes is not None else _lib.ORDER_RANDOM)
+        o = {"sequential": _lib.ORDER_SEQUENTIAL, "checkerboard": _lib.ORDER_CHECKERBOARD}.get(
+            order, _lib.ORDER_LIST if nodes is not None else _lib.ORDER_RANDOM)
         out = ens.ssf_run(ua._rule, maxMCSteps, order=o, nodes=nodes, start=start, fluct=fluct,
                           fluct_per_replica=per_rep, seed=seed, step_offset=step_offset, T=Tsteps,
                           steps_per_T=steps_per_T, trace_every=trace_every, hist=hist)

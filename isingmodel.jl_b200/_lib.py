@@ -19,7 +19,7 @@ CSRC = os.path.join(_HERE, "csrc")
 OK, ERR_ARG, ERR_SIZE, ERR_NONFINITE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NCCL, ERR_STATE = range(8)
 RULE_HOPFIELD, RULE_GLAUBER, RULE_METROPOLIS = 0, 1, 2
 BIP_SCA, BIP_MA = 0, 1
-ORDER_SEQUENTIAL, ORDER_LIST, ORDER_RANDOM = 0, 1, 2
+ORDER_SEQUENTIAL, ORDER_LIST, ORDER_RANDOM, ORDER_CHECKERBOARD = 0, 1, 2, 3
 FLUCT_PHILOX, FLUCT_SHARED, FLUCT_PER_REPLICA = 0, 1, 2
 PREC_F64, PREC_F32, PREC_AUTO, PREC_BF16X3, PREC_BF16X1, PREC_BF16X2, PREC_FP16X2, PREC_FP16X1 = 0, 1, 2, 3, 4, 5, 6, 7
 PREC_I8X3, PREC_I8X2, PREC_I8X4 = 8, 9, 10

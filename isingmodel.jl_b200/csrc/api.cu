@@ -773,7 +773,9 @@ static int ssf_run_impl(isb_ens *e, int rule, int64_t nsteps, int order, const i
     if (!general_graph(m)) return fail(ctx, ISB_ERR_STATE, "%s: not a general-graph ensemble", who);
     if (rule < ISB_RULE_HOPFIELD || rule > ISB_RULE_METROPOLIS) return fail(ctx, ISB_ERR_ARG, "%s: unknown rule %d", who, rule);
     if (nsteps < 0) return fail(ctx, ISB_ERR_ARG, "%s: nsteps = %lld is negative", who, (long long)nsteps);
-    if (order < ISB_ORDER_SEQUENTIAL || order > ISB_ORDER_RANDOM) return fail(ctx, ISB_ERR_ARG, "%s: unknown order %d", who, order);
+    if (order < ISB_ORDER_SEQUENTIAL || order > ISB_ORDER_CHECKERBOARD) return fail(ctx, ISB_ERR_ARG, "%s: unknown order %d", who, order);
+    if (order == ISB_ORDER_CHECKERBOARD && !(m->kind == ISB_KIND_SPARSE || !m->fast_ok))
+        return fail(ctx, ISB_ERR_UNSUPPORTED, "%s: ISB_ORDER_CHECKERBOARD needs a periodic L x L lattice given as a sparse model", who);
     if (fluct_mode < ISB_FLUCT_PHILOX || fluct_mode > ISB_FLUCT_PER_REPLICA)
         return fail(ctx, ISB_ERR_ARG, "%s: unknown fluct_mode %d", who, fluct_mode);
     if (trace_every < 0) return fail(ctx, ISB_ERR_ARG, "%s: trace_every is negative", who);
@@ -785,7 +787,7 @@ static int ssf_run_impl(isb_ens *e, int rule, int64_t nsteps, int order, const i
         for (int64_t k = 0; k < nsteps; ++k)
             if (nodes[k] < 0 || nodes[k] >= m->n)
                 return fail(ctx, ISB_ERR_ARG, "%s: nodes[%lld] = %d outside [0, %d)", who, (long long)k, nodes[k], m->n);
-    } else if (order == ISB_ORDER_SEQUENTIAL) {
+    } else if (order == ISB_ORDER_SEQUENTIAL || order == ISB_ORDER_CHECKERBOARD) {
         if (start < 0 || start >= m->n) return fail(ctx, ISB_ERR_ARG, "%s: start = %d outside [0, %d)", who, start, m->n);
     }
     if (fluct_mode != ISB_FLUCT_PHILOX) {
@@ -810,7 +812,7 @@ static int ssf_run_impl(isb_ens *e, int rule, int64_t nsteps, int order, const i
 
     int32_t *d_nodes = nullptr;
     double *d_fluct = nullptr, *d_T = nullptr, *d_E = nullptr, *d_M = nullptr;
-    if (order != ISB_ORDER_SEQUENTIAL) {
+    if (order == ISB_ORDER_LIST || order == ISB_ORDER_RANDOM) {
         ISB_TRY(isb::dev_reserve(ctx, isb::SCR_NODES, (size_t)nsteps * sizeof(int32_t), (void **)&d_nodes));
         if (order == ISB_ORDER_LIST)
             ISB_TRY(h2d(ctx, d_nodes, nodes, (size_t)nsteps * sizeof(int32_t), &e->last_h2d));

@@ -141,7 +141,7 @@ namespace isb {
 void *lattice_detect(isb_ctx *ctx, int n, const std::vector<std::vector<std::pair<int, double>>> &rows);
 void lattice_free(void *lat);
 int lattice_side(const void *lat);
-int ssf_lattice_run_device(isb_ens *e, void *lat, int rule, int64_t nsteps, int start, int fluct_mode, const double *d_fluct,
+int ssf_lattice_run_device(isb_ens *e, void *lat, int rule, int64_t nsteps, int order, int start, int fluct_mode, const double *d_fluct,
                            uint64_t seed, uint64_t step_offset, const double *d_T, int64_t steps_per_T, int64_t trace_every,
                            double *d_E, double *d_M, int8_t *d_S);
 

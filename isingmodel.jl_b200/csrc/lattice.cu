@@ -36,7 +36,7 @@ struct LatParams {
     int64_t lds;
     int L, n, R, rule;
     int64_t nsteps;
-    int start;
+    int start;             // first site (sequential order) / first position of the sweep order (checkerboard order)
     int fluct_mode;
     const double *fluct;
     uint64_t step_offset;
@@ -259,6 +259,177 @@ __global__ void __launch_bounds__(256) ssf_lattice_kernel(const LatParams p) {
     }
 }
 
+// ISB_ORDER_CHECKERBOARD ("checkerboard colouring"): a sweep visits the sites of colour (x + y) even in
+// ascending site index, then the sites of the other colour — one particular site list of the reference's 3-argument
+// update! (src/SingleSpinFlip.jl:46-55; tests replay exactly that list through the oracle).  The four neighbours of a
+// site all have the other colour, so the 32 sites of a window do not depend on each other: every lane decides its site
+// from the stored spins (one field evaluation, no scan), and the decisions of 16 lanes are spread over the colour's bit
+// positions of one word.  Everything else — rules, noise words per step, schedules, traces — as in ssf_lattice_kernel.
+__global__ void __launch_bounds__(256) ssf_lattice_cb_kernel(const LatParams p) {
+    extern __shared__ uint32_t lat_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * p.chains_per_cta + warp;
+    if (r >= p.R) return;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int L = p.L, n = p.n, WPR = L >> 5, nwords = n >> 5, Lh = L >> 1, n2 = n >> 1;
+    uint32_t *W = lat_smem + (size_t)warp * nwords;
+    for (int wi = 0; wi < nwords; ++wi) {
+        const uint32_t m = __ballot_sync(FULL, p.spins[(int64_t)r * p.lds + wi * 32 + lane] > 0);
+        if (lane == 0) W[wi] = m;
+    }
+    __syncwarp();
+    const int rule = p.rule;
+    const bool metro = rule == 2, audit = p.tie_eps > 0.0;
+    const double hsign = rule == 0 ? -1.0 : 1.0;
+    const double tsc = p.tscale ? __ldg(&p.tscale[r]) : 1.0;
+    unsigned long long nflips = 0, nties = 0;
+    auto bit = [&](int yy, int xx) { return (W[yy * WPR + (xx >> 5)] >> (xx & 31)) & 1u; };
+    // sum_j J_ij s_j in ascending j (+ / - h_i): the reference's row-dot order (src/SpinSystems.jl:80-83)
+    auto field_at = [&](int i, uint32_t nbits, double hx) {
+        const uint32_t code = __ldg(&p.kind[i]);
+        auto term = [&](int k) {
+            const double j = __ldg(&p.Jn[(size_t)k * n + i]);
+            const uint32_t flip = (((nbits >> ((code >> (2 * k)) & 3u)) & 1u) ^ 1u) << 31;     // spin -1: negate
+            return __hiloint2double(__double2hiint(j) ^ (int)flip, __double2loint(j));
+        };
+        double acc = __dadd_rn(term(0), term(1));
+        acc = __dadd_rn(acc, term(2));
+        acc = __dadd_rn(acc, term(3));
+        return __dadd_rn(acc, hx);
+    };
+    auto nbits_at = [&](int y, int x) {
+        const int yu = y == 0 ? L - 1 : y - 1, yd = y == L - 1 ? 0 : y + 1, xl = x == 0 ? L - 1 : x - 1, xr = x == L - 1 ? 0 : x + 1;
+        return bit(yu, x) | (bit(y, xl) << 1) | (bit(y, xr) << 2) | (bit(yd, x) << 3);
+    };
+    auto write_trace = [&](int64_t idx) {
+        double q = 0.0, l = 0.0;
+        int m = 0;
+        for (int wi = 0; wi < nwords; ++wi) {
+            const int i = wi * 32 + lane, y = i / L, x = i - y * L;
+            const bool sb = bit(y, x);
+            const double g = field_at(i, nbits_at(y, x), 0.0);
+            const double hv = __ldg(&p.hext[i]);
+            q += sb ? g : -g;
+            l += sb ? hv : -hv;
+            m += sb ? 1 : -1;
+        }
+        q = warp_sum(q);
+        l = warp_sum(l);
+        m = warp_sum_int(m);
+        if (lane == 0) {
+            if (p.out_E) p.out_E[idx * p.R + r] = -0.5 * q - l;
+            if (p.out_M) p.out_M[idx * p.R + r] = (double)m;
+        }
+        if (p.out_S)
+            for (int wi = 0; wi < nwords; ++wi)
+                p.out_S[(idx * p.R + r) * p.ldS + wi * 32 + lane] = ((W[wi] >> lane) & 1u) ? (int8_t)1 : (int8_t)-1;
+    };
+    int64_t next_trace = p.trace_every > 0 ? p.trace_every : INT64_MAX, trace_idx = 0;
+    const uint64_t spT = (uint64_t)p.steps_per_T;
+    uint64_t ti = 0, tr = 0;  // t = ti * spT + tr
+    int64_t cached_ti = -1;
+    double cachedT = 0.0;
+    Philox4 blk{0, 0, 0, 0};   // Philox blocks of 128 consecutive steps, as in ssf_lattice_kernel
+    uint64_t cb = 0;
+    bool have_blk = false;
+
+    int64_t t = 0;
+    int pos = p.start;         // position in the sweep order: [0, n/2) first colour, [n/2, n) second colour
+    while (t < p.nsteps) {
+        const int c = pos >= n2 ? 1 : 0;
+        const int pc = pos - c * n2;
+        const int l_first = pc & 31;          // windows are aligned to 32 positions of a colour (n / 2 is a multiple of 32)
+        int len = 32 - l_first;
+        if (p.nsteps - t < len) len = (int)(p.nsteps - t);
+        if (next_trace - t < len) len = (int)(next_trace - t);
+        const int off = lane - l_first;
+        const bool mine = off >= 0 && off < len;
+        double Tl;
+        {
+            const uint64_t a_hi = tr + (uint64_t)(len - 1);
+            if (a_hi < spT) {
+                if ((int64_t)ti != cached_ti) {
+                    cachedT = __dmul_rn(__ldg(&p.Tsched[ti]), tsc);
+                    cached_ti = (int64_t)ti;
+                }
+                Tl = cachedT;
+            } else {
+                const uint64_t a = tr + (uint64_t)(mine ? off : 0);
+                Tl = __dmul_rn(__ldg(&p.Tsched[ti + a / spT]), tsc);
+            }
+        }
+        double f = 0.0;
+        if (rule != 0) {
+            const int64_t tl = t + (mine ? off : 0);
+            if (p.fluct_mode == ISB_FLUCT_PHILOX) {
+                const uint64_t g0 = p.step_offset + (uint64_t)t;
+                if (!have_blk || ((g0 + 31) >> 2) >= cb + 32 || (g0 >> 2) < cb) {
+                    cb = g0 >> 2;
+                    const uint64_t q = cb + (uint64_t)lane;
+                    blk = philox4x32_10k((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)r, DOM_SSF_FLUCT << 28, p.keys);
+                    have_blk = true;
+                }
+                const uint64_t gs = p.step_offset + (uint64_t)tl;
+                const int src = (int)((gs >> 2) - cb);
+                const uint32_t wx = __shfl_sync(FULL, blk.x, src), wy = __shfl_sync(FULL, blk.y, src);
+                const uint32_t wz = __shfl_sync(FULL, blk.z, src), ww = __shfl_sync(FULL, blk.w, src);
+                const uint32_t pick = (uint32_t)(gs & 3u);
+                f = ssf_fluct_from_word(rule, pick == 0 ? wx : (pick == 1 ? wy : (pick == 2 ? wz : ww)));
+            } else if (p.fluct_mode == ISB_FLUCT_SHARED) {
+                f = __ldg(&p.fluct[tl]);
+            } else {
+                f = __ldg(&p.fluct[(int64_t)r * p.nsteps + tl]);
+            }
+        }
+        const double ftl = __dmul_rn(f, Tl);
+        // my site: the (pc - l_first + lane)-th site of colour c in ascending site index
+        const int pl = pc - l_first + lane;
+        const int y = pl / Lh, j = pl - y * Lh;
+        const int par = (y + c) & 1;
+        const int x = 2 * j + par, i = y * L + x;
+        const uint32_t mybit = bit(y, x);
+        const double hx = hsign * __ldg(&p.hext[i]);
+        const double fts = metro ? (mybit ? ftl : -ftl) : ftl;
+        // x = 2 h_loc - f T [s_i]; new spin = +1 unless x < 0 (heaviside(0) = 1, src/SpinSystems.jl:163-171)
+        const double xv = __dsub_rn(2.0 * field_at(i, nbits_at(y, x), hx), fts);
+        const bool nb = mine ? !(xv < 0.0) : (bool)mybit;
+        nflips += __popc(__ballot_sync(FULL, mine && nb != (bool)mybit));
+        if (audit) nties += __popc(__ballot_sync(FULL, mine && fabs(xv) < p.tie_eps));
+        // lanes 0-15 and 16-31 each hold the 16 sites of colour c of one 32-bit word (same row, x = 2 j + par)
+        const uint32_t b = __ballot_sync(FULL, nb);
+        uint32_t v = (b >> (lane & 16)) & 0xFFFFu;
+        v = (v | (v << 8)) & 0x00FF00FFu;      // spread the 16 decisions over every other bit
+        v = (v | (v << 4)) & 0x0F0F0F0Fu;
+        v = (v | (v << 2)) & 0x33333333u;
+        v = (v | (v << 1)) & 0x55555555u;
+        __syncwarp();
+        if ((lane & 15) == 0) {
+            uint32_t *wp = &W[y * WPR + (x >> 5)];
+            *wp = (*wp & ~(0x55555555u << par)) | (v << par);
+        }
+        __syncwarp();
+        t += len;
+        pos += len;
+        if (pos >= n) pos = 0;
+        tr += (uint64_t)len;
+        if (tr >= spT) {
+            ti += tr / spT;
+            tr %= spT;
+        }
+        if (t == next_trace) {
+            write_trace(trace_idx++);
+            next_trace += p.trace_every;
+        }
+    }
+    __syncwarp();
+    for (int wi = 0; wi < nwords; ++wi)
+        p.spins[(int64_t)r * p.lds + wi * 32 + lane] = ((W[wi] >> lane) & 1u) ? (int8_t)1 : (int8_t)-1;
+    if (lane == 0) {
+        p.flips[r] = nflips;
+        if (nties) atomicAdd(p.near_ties, nties);
+    }
+}
+
 // ------------------------------------------------------------------ host
 struct LatticeModel {
     int L = 0;
@@ -315,7 +486,7 @@ void lattice_free(void *lat) {
 
 int lattice_side(const void *lat) { return lat ? ((const LatticeModel *)lat)->L : 0; }
 
-int ssf_lattice_run_device(isb_ens *e, void *lat, int rule, int64_t nsteps, int start, int fluct_mode, const double *d_fluct,
+int ssf_lattice_run_device(isb_ens *e, void *lat, int rule, int64_t nsteps, int order, int start, int fluct_mode, const double *d_fluct,
                            uint64_t seed, uint64_t step_offset, const double *d_T, int64_t steps_per_T, int64_t trace_every,
                            double *d_E, double *d_M, int8_t *d_S) {
     isb_model *m = e->model;
@@ -341,9 +512,10 @@ int ssf_lattice_run_device(isb_ens *e, void *lat, int rule, int64_t nsteps, int 
     p.chains_per_cta = chains;
     const int grid = (e->R + chains - 1) / chains;
     const size_t smem = per_chain * chains;
-    cudaError_t ce = cudaFuncSetAttribute(ssf_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = order == ISB_ORDER_CHECKERBOARD ? ssf_lattice_cb_kernel : ssf_lattice_kernel;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce == cudaSuccess) {
-        ssf_lattice_kernel<<<grid, 32 * chains, smem, ctx->stream>>>(p);
+        kern<<<grid, 32 * chains, smem, ctx->stream>>>(p);
         ce = cudaGetLastError();
     }
     if (ce != cudaSuccess) return fail(ctx, ISB_ERR_CUDA, "ssf_lattice_kernel launch failed: %s", cudaGetErrorString(ce));

@@ -367,8 +367,10 @@ int ssf_sparse_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const
     isb_ctx *ctx = m->ctx;
     SparseModel *sm = (SparseModel *)m->sp;
     if (nsteps <= 0) return ISB_OK;
-    if (sm->lattice && order == ISB_ORDER_SEQUENTIAL)
-        return ssf_lattice_run_device(e, sm->lattice, rule, nsteps, start, fluct_mode, d_fluct, seed, step_offset, d_T,
+    if (order == ISB_ORDER_CHECKERBOARD && !sm->lattice)
+        return fail(ctx, ISB_ERR_UNSUPPORTED, "ISB_ORDER_CHECKERBOARD needs a periodic L x L lattice (L a multiple of 32) with four neighbours per site");
+    if (sm->lattice && (order == ISB_ORDER_SEQUENTIAL || order == ISB_ORDER_CHECKERBOARD))
+        return ssf_lattice_run_device(e, sm->lattice, rule, nsteps, order, start, fluct_mode, d_fluct, seed, step_offset, d_T,
                                       steps_per_T, trace_every, d_E, d_M, d_S);
     const int sign = rule == ISB_RULE_HOPFIELD ? -1 : +1;
     if (e->steps_since_refresh >= (int64_t)ISB_FIELD_REFRESH_SWEEPS * m->n) e->fields_rule_sign = 0;  // bound the drift

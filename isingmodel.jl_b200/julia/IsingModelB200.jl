@@ -37,7 +37,7 @@ import ..libisb
 const Ctx = Ptr{Cvoid}; const Model = Ptr{Cvoid}; const Ens = Ptr{Cvoid}
 const RULE_HOPFIELD, RULE_GLAUBER, RULE_METROPOLIS = Cint(0), Cint(1), Cint(2)
 const BIP_SCA, BIP_MA = Cint(0), Cint(1)
-const ORDER_SEQUENTIAL, ORDER_LIST, ORDER_RANDOM = Cint(0), Cint(1), Cint(2)
+const ORDER_SEQUENTIAL, ORDER_LIST, ORDER_RANDOM, ORDER_CHECKERBOARD = Cint(0), Cint(1), Cint(2), Cint(3)
 const FLUCT_PHILOX, FLUCT_SHARED, FLUCT_PER_REPLICA = Cint(0), Cint(1), Cint(2)
 const PREC_F64, PREC_F32, PREC_AUTO, PREC_BF16X3, PREC_BF16X1, PREC_BF16X2 = Cint(0), Cint(1), Cint(2), Cint(3), Cint(4), Cint(5)
 const PREC_FP16X2, PREC_FP16X1 = Cint(6), Cint(7)
@@ -108,10 +108,13 @@ _optr(::Nothing, T) = Ptr{T}(C_NULL)
 _optr(a::Array, T) = a
 # nodes are 1-based on the Julia side, 0-based across the ABI.  With `snap` (an N x R x ntr Int8 array) the call is
 # isb_ssf_run_snap: the state after every `trace_every`-th step is recorded (and its energy into `E`, R x ntr).
+# `checkerboard = true` (periodic L x L lattices given as sparse J): ISB_ORDER_CHECKERBOARD, `start` = first position of the
+# two-colour sweep order.
 function ssf_run!(e, rule, nsteps; nodes = nothing, start = 1, fluct = nothing, per_replica = false, seed = 0,
-                  step_offset = 0, T = Float64[], steps_per_T = 1, trace_every = 0, E = nothing, snap = nothing)
+                  step_offset = 0, T = Float64[], steps_per_T = 1, trace_every = 0, E = nothing, snap = nothing,
+                  checkerboard = false)
     n0 = nodes === nothing ? nothing : Vector{Int32}(nodes .- 1)
-    order = nodes === nothing ? ORDER_SEQUENTIAL : ORDER_LIST
+    order = nodes === nothing ? (checkerboard ? ORDER_CHECKERBOARD : ORDER_SEQUENTIAL) : ORDER_LIST
     mode = fluct === nothing ? FLUCT_PHILOX : (per_replica ? FLUCT_PER_REPLICA : FLUCT_SHARED)
     f = fluct === nothing ? nothing : Vector{Float64}(vec(fluct))
     Tv = Vector{Float64}(T)

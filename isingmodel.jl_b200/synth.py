@@ -93,3 +93,11 @@ def geometric_schedule(T0: float, Tf: float, n: int) -> np.ndarray:
     if n == 1:
         return np.array([T0])
     return T0 * (Tf / T0) ** (np.arange(n) / (n - 1.0))
+
+
+def checkerboard_nodes(L: int) -> np.ndarray:
+    """The site list of one ISB_ORDER_CHECKERBOARD sweep of an L x L lattice (site i = x + L y, 0-based): the sites with
+    (x + y) even in ascending index, then those with (x + y) odd."""
+    i = np.arange(L * L)
+    colour = ((i % L) + (i // L)) & 1
+    return np.concatenate([i[colour == 0], i[colour == 1]]).astype(np.int32)

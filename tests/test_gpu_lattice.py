@@ -129,3 +129,78 @@ def test_non_lattice_graphs_are_not_misdetected(ctx, orc, synth):
     for r in range(R):
         s, *_ = orc.ssf_run(2, J, np.zeros(n), S0[r], nsteps, fluct=fl[r], T=np.array([2.0]), steps_per_T=nsteps)
         assert np.array_equal(s, S[r])
+
+
+CB_CASES = [  # L, bonds, rule, R, nsteps, start (position in the two-colour sweep order), per-replica noise
+    (32, "gauss", 2, 12, 32 * 32 * 2 + 77, 0, True), (32, "pmj", 1, 7, 32 * 32 * 3, 523, False),
+    (32, "ferro", 2, 33, 1500, 500, True), (64, "gauss", 1, 6, 64 * 64 * 2 + 13, 64 * 32 + 17, True),
+    (64, "gauss", 0, 4, 64 * 64 + 5, 3, False), (96, "pmj", 2, 3, 96 * 96 + 100, 96 * 48 - 5, True),
+]
+
+
+@pytest.mark.parametrize("Lside,bonds,rule,R,nsteps,start,per_rep", CB_CASES)
+def test_checkerboard_order_equals_its_site_list(ctx, orc, synth, Lside, bonds, rule, R, nsteps, start, per_rep):
+    """ISB_ORDER_CHECKERBOARD is ONE site list of the reference's 3-argument update! (all sites of one colour in
+    ascending index, then the other colour); sites of a colour do not interact, so the kernel decides 32 of them at
+    once — and must give, bit for bit, what the oracle gives when it walks that list one site at a time
+    (src/SingleSpinFlip.jl:31-36,46-55,65-74), and what the library's own list order gives on the same model."""
+    L = _lib()
+    n = Lside * Lside
+    A = _lattice(synth, Lside, bonds, 60 + Lside)
+    J = A.toarray()
+    h = synth.gaussian(61, n) * (0.0 if bonds == "ferro" else 0.3)
+    S0 = synth.spins(62, R, n)
+    gen = synth.logistic if rule == 1 else synth.exponential
+    fl = None if rule == 0 else gen(63, (R, nsteps) if per_rep else nsteps)
+    T = synth.geometric_schedule(3.0, 0.3, 5)
+    spT = (nsteps + 4) // 5                                   # the schedule changes in the middle of windows
+    tr = max(1, nsteps // 3)
+    sweep = synth.checkerboard_nodes(Lside)
+    nodes = np.resize(np.roll(sweep, -start), nsteps)         # the list from position `start` on, sweep after sweep
+    e = L.Ensemble(L.Model.sparse(ctx, A, h), R)
+    e.set_spins(S0)
+    out = e.ssf_run(rule, nsteps, order=L.ORDER_CHECKERBOARD, start=start, fluct=fl, fluct_per_replica=per_rep, T=T,
+                    steps_per_T=spT, trace_every=tr, want_S=True)
+    S = e.get_spins()
+    assert e.last_stats()["launches"] == 1
+    for r in list(range(min(R, 6))) + [R - 1]:
+        s, flips, E, M = orc.ssf_run(rule, J, h, S0[r], nsteps, nodes=nodes, fluct=None if fl is None else (fl[r] if per_rep else fl),
+                                     T=T, steps_per_T=spT, trace_every=tr)
+        assert np.array_equal(s, S[r]), f"replica {r}"
+        assert flips == out["flips"][r]
+        assert np.array_equal(M, out["M"][:, r]) and _close(out["E"][:, r], E)
+    e2 = L.Ensemble(L.Model.sparse(ctx, A, h), R)              # the list order of the library (neighbour-list kernel)
+    e2.set_spins(S0)
+    out2 = e2.ssf_run(rule, nsteps, nodes=nodes, fluct=fl, fluct_per_replica=per_rep, T=T, steps_per_T=spT, trace_every=tr)
+    assert np.array_equal(e2.get_spins(), S) and np.array_equal(out2["flips"], out["flips"])
+
+
+def test_checkerboard_order_needs_a_lattice(ctx, synth):
+    L = _lib()
+    n = 64
+    J = synth.sk_J(n, 3)
+    e = L.Ensemble(L.Model.dense(ctx, J, np.zeros(n)), 2)
+    e.set_spins(synth.spins(1, 2, n))
+    with pytest.raises(L.IsbError) as ei:
+        e.ssf_run(L.RULE_GLAUBER, 10, order=L.ORDER_CHECKERBOARD, T=np.ones(1), steps_per_T=10)
+    assert ei.value.code == L.ERR_UNSUPPORTED
+
+
+def test_checkerboard_order_samples_the_exact_mean_energy(ctx, synth):
+    """Two-colour sweeps of the 32 x 32 ferromagnet at T = 2.269 (Metropolis, in-kernel noise) give Kaufman's exact
+    finite-lattice mean energy: the order changes the trajectory, not the stationary distribution (tolerance: 5 standard
+    errors of the replica scatter + 0.2 % for the residual equilibration bias at the critical point)."""
+    from exact_ising import mean_energy
+    L = _lib()
+    Ls, T, R = 32, 2.269, 2048
+    n = Ls * Ls
+    A = _lattice(synth, Ls, "ferro", 1)
+    e = L.Ensemble(L.Model.sparse(ctx, A, np.zeros(n)), R)
+    e.set_spins(synth.spins(5, R, n))
+    e.ssf_run(L.RULE_METROPOLIS, 2000 * n, order=L.ORDER_CHECKERBOARD, seed=11, T=np.array([T]), steps_per_T=2000 * n)
+    out = e.ssf_run(L.RULE_METROPOLIS, 500 * n, order=L.ORDER_CHECKERBOARD, seed=11, step_offset=2000 * n, T=np.array([T]),
+                    steps_per_T=500 * n, trace_every=10 * n)
+    Em = out["E"].mean(0)
+    exact = mean_energy(Ls, T)
+    err = Em.std() / np.sqrt(R)
+    assert abs(Em.mean() - exact) < 5 * err + 2e-3 * abs(exact), (Em.mean(), exact, err)
