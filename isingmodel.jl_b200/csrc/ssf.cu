@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "handles.hpp"
 #include "ssf_kernel.cuh"
@@ -272,6 +273,7 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
     bool tma = getenv("ISB_SSF_NOTMA") == nullptr;
     int NG = (int)((ctx->smem_optin - 2048) / ((size_t)SSF_G * rowb));
     NG = std::min(NG, 8);
+    if (const char *env_ng = getenv("ISB_SSF_NG")) NG = std::max(1, std::min(NG, atoi(env_ng)));   // fewer ring slots = more L1 (A/B runs)
     if (NG < 2) tma = false;
     const size_t smem = tma ? (size_t)NG * SSF_G * rowb + (size_t)(3 * NG + 2) * sizeof(uint64_t) + 16 : 0;
     // thread-block clusters: one multicast J-row stream per cluster of `cl` CTAs (L2 -> SM traffic / cl)
@@ -324,17 +326,92 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
     p.od_ratio = 0.8f;
     if (const char *env_od = getenv("ISB_SSF_OD_RATIO")) p.od_ratio = (float)atof(env_od);
 
+    p.fluct_pitch = nsteps;
     const bool list = order != ISB_ORDER_SEQUENTIAL;
     const int threads = 32 * (nw + 1);
-    cudaError_t ce;
-    if (hd)
-        ce = launch_ssf_dd(p, npl, list, tma, cl, ctas, threads, smem, ctx->stream);
-    else
-        ce = launch_ssf_ff(p, npl, list, tma, cl, ctas, threads, smem, ctx->stream);
+    // one launch over the steps [t0, t0 + len) of the run: every per-step input is offset on the host, the kernel sees a
+    // run of `len` steps (t0 is a multiple of steps_per_T and of trace_every, see below)
+    auto launch = [&](int64_t t0, int64_t len, bool use_tma) -> cudaError_t {
+        SsfParams q = p;
+        q.nsteps = len;
+        q.step_offset = step_offset + (uint64_t)t0;
+        if (list) {
+            q.nodes = d_nodes + t0;
+        } else {
+            q.start = (int)(((int64_t)start + t0) % m->n);
+        }
+        if (d_fluct) q.fluct = d_fluct + t0;                 // (shared: step t0; per replica: [r][t0], pitch = whole run)
+        q.Tsched = d_T + t0 / steps_per_T;
+        if (trace_every > 0) {
+            const int64_t i0 = t0 / trace_every;
+            if (d_E) q.out_E = d_E + i0 * e->R;
+            if (d_M) q.out_M = d_M + i0 * e->R;
+            if (d_S) q.out_S = d_S + i0 * e->R * (int64_t)m->n;
+        }
+        const size_t sm = use_tma ? smem : 0;
+        return hd ? launch_ssf_dd(q, npl, list, use_tma, use_tma ? cl : 1, ctas, threads, sm, ctx->stream)
+                  : launch_ssf_ff(q, npl, list, use_tma, use_tma ? cl : 1, ctas, threads, sm, ctx->stream);
+    };
+    // Adaptive delivery across launches.  The streaming kernel (TMA ring, adaptive epochs) wins while more than about one
+    // flip in five is accepted; below that the plain kernel — every chain reads the rows of its own flips from L2, no
+    // producer warp, no epoch synchronisation between the chains of a CTA — is up to 1.7x faster per sweep (C2 schedule,
+    // profiles/r2aq_c2_delivery_profile.txt).  Sequential sweeps longer than two segments are therefore run segment by
+    // segment, each in the mode the previous segment's acceptance calls for; the fields stay cached on the device between
+    // launches and the trajectory does not depend on the segmentation (noise, schedule and traces are indexed by the
+    // step of the run).  ISB_SSF_SEGMENT=0 keeps one launch.
+    int64_t unit = steps_per_T;
+    if (trace_every > 0) {   // least common multiple of the schedule period and the trace period
+        int64_t a = unit, b = trace_every;
+        while (b) {
+            const int64_t c = a % b;
+            a = b;
+            b = c;
+        }
+        unit = unit / a * trace_every;
+    }
+    int64_t seg = std::max<int64_t>((int64_t)50 * m->n, (int64_t)1 << 16);
+    seg = (seg + unit - 1) / unit * unit;
+    bool segment = tma && !list && cl == 1 && unit > 0 && nsteps > 2 * seg && (double)e->R * m->n >= 1e5;
+    if (const char *env_sg = getenv("ISB_SSF_SEGMENT")) segment = segment && atoi(env_sg) != 0;
+    double thr = 0.2;      // accepted flips per attempt above which the streaming kernel is the faster one
+    if (const char *env_th = getenv("ISB_SSF_SEG_THR")) thr = atof(env_th);
+    cudaError_t ce = cudaSuccess;
+    if (!segment) {
+        ce = launch(0, nsteps, tma);
+        e->last_launches += 1;
+    } else {
+        std::vector<unsigned long long> fl((size_t)e->R), tot((size_t)e->R, 0ull);
+        bool use_tma = true;
+        int stable = 0;
+        for (int64_t t0 = 0; t0 < nsteps && ce == cudaSuccess;) {
+            const int64_t len = std::min(seg, nsteps - t0);
+            ce = launch(t0, len, use_tma);
+            e->last_launches += 1;
+            if (ce != cudaSuccess) break;
+            ce = cudaMemcpyAsync(fl.data(), e->d_flips, fl.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+            if (ce != cudaSuccess) break;
+            double sum = 0.0;
+            for (size_t r = 0; r < fl.size(); ++r) {
+                tot[r] += fl[r];
+                sum += (double)fl[r];
+            }
+            // (the decision lags one segment behind: in an anneal the acceptance of the next segment is lower still)
+            const bool next_tma = sum / ((double)len * e->R) > thr;
+            stable = next_tma == use_tma ? stable + 1 : 0;
+            use_tma = next_tma;
+            // a settled cold regime: fewer, longer launches.  Hot segments stay short — an anneal leaves them, and a long
+            // streamed segment that has gone cold costs more than the extra launches
+            if (!use_tma && stable >= 2) seg = std::min<int64_t>(seg * 2, (int64_t)1 << 40);
+            t0 += len;
+        }
+        if (ce == cudaSuccess)   // the flip counts of the whole run, where the caller reads them
+            ce = cudaMemcpyAsync(e->d_flips, tot.data(), tot.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    }
     if (ce != cudaSuccess)
         return fail(ctx, ISB_ERR_CUDA, "ssf_kernel launch failed: %s (grid %d x %d threads, %zu B smem, cluster %d)",
                     cudaGetErrorString(ce), ctas, threads, smem, cl);
-    e->last_launches += 1;
     e->steps_since_refresh += nsteps;
     return ISB_OK;
 }

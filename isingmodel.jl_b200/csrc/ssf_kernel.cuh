@@ -28,7 +28,10 @@
 
 namespace isb {
 
-constexpr int SSF_G = 8;  // rows of J per ring slot
+#ifndef ISB_SSF_G
+#define ISB_SSF_G 8
+#endif
+constexpr int SSF_G = ISB_SSF_G;  // rows of J per ring slot (a power of two; 8 measured best: A/B builds with -DISB_SSF_G=2|4|16)
 
 struct SsfParams {
     const void *J;  // permuted couplings [npad][ldj] (double or float)
@@ -45,6 +48,7 @@ struct SsfParams {
     const int32_t *nodes;
     int fluct_mode;
     const double *fluct;
+    int64_t fluct_pitch;   // per-replica fluctuations: steps per replica of the whole run (= nsteps unless the run is segmented)
     uint64_t seed, step_offset;
     const double *Tsched;
     const double *tscale;  // per-replica temperature factors [R] or NULL
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                 } else if (p.fluct_mode == 1) {
                     f = __ldg(&p.fluct[tl]);
                 } else {
-                    f = __ldg(&p.fluct[(int64_t)r * p.nsteps + tl]);
+                    f = __ldg(&p.fluct[(int64_t)r * p.fluct_pitch + tl]);
                 }
             }
             const double ftl = __dmul_rn(f, Tl);
@@ -548,7 +552,7 @@ __global__ void __launch_bounds__(SsfCfg<HT, NPL>::kMaxThreads, 1) ssf_kernel(co
                         } else if (p.fluct_mode == 1) {
                             f_batch = __ldg(&p.fluct[tl]);
                         } else {
-                            f_batch = __ldg(&p.fluct[(int64_t)r * p.nsteps + tl]);
+                            f_batch = __ldg(&p.fluct[(int64_t)r * p.fluct_pitch + tl]);
                         }
                     }
                 }
