@@ -442,10 +442,15 @@ def run_c2(rt, args, steps, warmup, cpu=True):
     line["roofline"] = {
         "bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
         "traffic": traffic, "kernel": "isb::ssf_kernel", "kernel_ms": 1e3 * kern_s,
-        "peak_source": f"shared-memory pipe, 128 B/clk/SM x {rt.sms} SMs x {sm_mhz:.0f} MHz (clock sampled in the timed region)",
-        "accounting": f"shared-memory bytes the chains read: accepted flips ({flips:.4g}/launch) x N x {bJ} B (one J row per "
-                      "accepted flip per chain, 128-bit conflict-free LDS); ring writes of the streamed epochs not counted",
+        "peak_source": f"shared-memory / L1 data path, 128 B/clk/SM x {rt.sms} SMs x {sm_mhz:.0f} MHz (clock sampled in the timed region)",
+        "accounting": f"row bytes the chains read through the SM's shared-memory / L1 data path: accepted flips ({flips:.4g} per "
+                      f"anneal) x N x {bJ} B (one J row per accepted flip per chain: 128-bit LDS from the ring while the streaming "
+                      "kernel runs, 128-bit loads that hit L1 / L2 once the plain kernel has taken over); ring writes of the "
+                      "streamed epochs not counted",
         "accept_rate": flips / upd_step,
+        "launches_per_anneal": float(np.mean([s["launches"] for s in stats])),
+        "traffic_note": "DRAM bytes of ONE launch of the sweep kernel (ncu); an anneal is run as several launches (streaming kernel "
+                        "while hot, plain kernel once cold), each of which reads the cached fields and spins once",
         "hbm_accounting": {"note": "SURVEY §8d per-chain figure (flips x N x b_J) against the measured HBM copy rate: > 1 because "
                                    "one smem copy of a row serves all chains of a CTA; DRAM traffic is ~46 MB per launch, so "
                                    "the HBM roof (and the >= 60 % HBM target) is moot for this design",

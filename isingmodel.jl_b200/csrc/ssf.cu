@@ -370,8 +370,13 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
         unit = unit / a * trace_every;
     }
     int64_t seg = std::max<int64_t>((int64_t)50 * m->n, (int64_t)1 << 16);
+    double min_work = 1e5;   // replicas x sites below which a launch is too short to be worth splitting
+    if (const char *env_sm = getenv("ISB_SSF_SEG_MIN")) {   // tests: segment length in steps, any problem size
+        seg = std::max<int64_t>(1, atoll(env_sm));
+        min_work = 0.0;
+    }
     seg = (seg + unit - 1) / unit * unit;
-    bool segment = tma && !list && cl == 1 && unit > 0 && nsteps > 2 * seg && (double)e->R * m->n >= 1e5;
+    bool segment = tma && !list && cl == 1 && unit > 0 && nsteps > 2 * seg && (double)e->R * m->n >= min_work;
     if (const char *env_sg = getenv("ISB_SSF_SEGMENT")) segment = segment && atoi(env_sg) != 0;
     double thr = 0.2;      // accepted flips per attempt above which the streaming kernel is the faster one
     if (const char *env_th = getenv("ISB_SSF_SEG_THR")) thr = atof(env_th);

@@ -159,6 +159,44 @@ def test_ssf_batched_bit_exact(ctx, orc, synth, N, kind, rule, order, prec, R, n
     assert np.array_equal(e.magnetization(), S.sum(1).astype(np.float64))
 
 
+@pytest.mark.parametrize("thr", ["0.2", "0", "2"])
+@pytest.mark.parametrize("rule,per_rep", [(1, True), (2, False)])
+def test_ssf_segmented_run_equals_the_oracle(ctx, orc, synth, monkeypatch, thr, rule, per_rep):
+    """Long sequential sweeps are run segment by segment, each launch with the streaming or the plain kernel according
+    to the previous segment's acceptance (csrc/ssf.cu).  Forced here at a small size (3 sweeps per segment; threshold
+    0.2 = the product's rule, 0 = always streaming, 2 = plain after the first segment): spins, flip counts and traces
+    must equal the oracle's single run — noise, schedule entries, first site and trace slots are all indexed by the
+    step of the whole run — and the single-launch run of the library."""
+    L = _lib()
+    N, R, sweeps, start = 96, 70, 41, 37
+    nsteps = sweeps * N + 29                                  # the last segment is ragged
+    J, h = synth.sk_J(N, 71), synth.gaussian(72, N) * 0.2
+    S0 = synth.spins(73, R, N)
+    gen = synth.logistic if rule == 1 else synth.exponential
+    fl = gen(74, (R, nsteps) if per_rep else nsteps)
+    T = synth.geometric_schedule(2.5, 0.05, sweeps + 1)       # hot to cold: both kernels get their turn at thr = 0.2
+    tr = 2 * N
+    runs = {}
+    for seg in ("1", "0"):
+        monkeypatch.setenv("ISB_SSF_SEGMENT", seg)
+        monkeypatch.setenv("ISB_SSF_SEG_MIN", str(3 * N))
+        monkeypatch.setenv("ISB_SSF_SEG_THR", thr)
+        e = L.Ensemble(L.Model.dense(ctx, J, h, L.PREC_F64), R)
+        e.set_spins(S0)
+        out = e.ssf_run(rule, nsteps, start=start, fluct=fl, fluct_per_replica=per_rep, T=T, steps_per_T=N, trace_every=tr,
+                        want_S=True)
+        runs[seg] = (e.get_spins(), out, e.last_stats()["launches"])
+    S, out, launches = runs["1"]
+    assert launches >= runs["0"][2] + 4                       # it really was segmented (cold segments double in length)
+    assert np.array_equal(S, runs["0"][0]) and np.array_equal(out["flips"], runs["0"][1]["flips"])
+    assert np.array_equal(out["E"], runs["0"][1]["E"]) and np.array_equal(out["S"], runs["0"][1]["S"])
+    for r in (0, 1, R // 2, R - 1):
+        s, flips, E, M = orc.ssf_run(rule, J, h, S0[r], nsteps, start=start, fluct=fl[r] if per_rep else fl, T=T,
+                                     steps_per_T=N, trace_every=tr)
+        assert np.array_equal(s, S[r]) and flips == out["flips"][r], f"replica {r}"
+        assert np.array_equal(M, out["M"][:, r]) and _close(out["E"][:, r], E)
+
+
 def test_ssf_continuation_and_field_cache(ctx, orc, synth):
     """Two runs back to back == one run (cached local fields stay valid); set_spins invalidates them."""
     L = _lib()
