@@ -12,6 +12,8 @@
 
 namespace isb {
 
+int ssf_cold_chains(const isb_ctx *ctx, int npad);                            // ssf_cold.cu
+cudaError_t launch_ssf_cold(const SsfParams &p, int chains, cudaStream_t st);
 cudaError_t launch_ssf_dd(const SsfParams &p, int npl, bool list, bool tma, int cl, int grid, int threads,
                           size_t smem, cudaStream_t st);
 cudaError_t launch_ssf_ff(const SsfParams &p, int npl, bool list, bool tma, int cl, int grid, int threads,
@@ -331,7 +333,12 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
     const int threads = 32 * (nw + 1);
     // one launch over the steps [t0, t0 + len) of the run: every per-step input is offset on the host, the kernel sees a
     // run of `len` steps (t0 is a multiple of steps_per_T and of trace_every, see below)
-    auto launch = [&](int64_t t0, int64_t len, bool use_tma) -> cudaError_t {
+    // mode 2: streaming kernel (TMA ring); 1: plain kernel (rows on demand, fields in registers); 0: cold kernel (fields in
+    // shared memory, 28 chains per SM: ssf_cold.cu)
+    const int cold_chains = (hd && !jf && !list && trace_every == 0 && p.guard == 0.0 && p.tie_eps == 0.0)
+                                ? ssf_cold_chains(ctx, m->npad) : 0;
+    auto launch = [&](int64_t t0, int64_t len, int mode) -> cudaError_t {
+        const bool use_tma = mode == 2;
         SsfParams q = p;
         q.nsteps = len;
         q.step_offset = step_offset + (uint64_t)t0;
@@ -348,6 +355,7 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
             if (d_M) q.out_M = d_M + i0 * e->R;
             if (d_S) q.out_S = d_S + i0 * e->R * (int64_t)m->n;
         }
+        if (mode == 0) return launch_ssf_cold(q, cold_chains, ctx->stream);
         const size_t sm = use_tma ? smem : 0;
         return hd ? launch_ssf_dd(q, npl, list, use_tma, use_tma ? cl : 1, ctas, threads, sm, ctx->stream)
                   : launch_ssf_ff(q, npl, list, use_tma, use_tma ? cl : 1, ctas, threads, sm, ctx->stream);
@@ -381,16 +389,27 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
     double thr = 0.2;      // accepted flips per attempt above which the streaming kernel is the faster one
     if (const char *env_th = getenv("ISB_SSF_SEG_THR")) thr = atof(env_th);
     cudaError_t ce = cudaSuccess;
-    if (!segment) {
-        ce = launch(0, nsteps, tma);
+    double thr_cold = 0.03;   // ... below which the shared-memory-field kernel is the fastest (one wave of 28 chains per SM)
+    if (const char *env_tc = getenv("ISB_SSF_COLD_THR")) thr_cold = atof(env_tc);
+    if (cold_chains < 16) thr_cold = -1.0;
+    int forced = -1;          // ISB_SSF_MODE = 0 | 1 | 2: one launch of that kernel (A/B runs and tests)
+    if (const char *env_md = getenv("ISB_SSF_MODE")) {
+        forced = atoi(env_md);
+        if (forced < 0 || forced > 2 || (forced == 0 && cold_chains < 1) || (forced == 2 && !tma)) forced = -1;
+    }
+    if (forced >= 0) {
+        ce = launch(0, nsteps, forced);
+        e->last_launches += 1;
+    } else if (!segment) {
+        ce = launch(0, nsteps, tma ? 2 : 1);
         e->last_launches += 1;
     } else {
         std::vector<unsigned long long> fl((size_t)e->R), tot((size_t)e->R, 0ull);
-        bool use_tma = true;
+        int mode = 2;
         int stable = 0;
         for (int64_t t0 = 0; t0 < nsteps && ce == cudaSuccess;) {
             const int64_t len = std::min(seg, nsteps - t0);
-            ce = launch(t0, len, use_tma);
+            ce = launch(t0, len, mode);
             e->last_launches += 1;
             if (ce != cudaSuccess) break;
             ce = cudaMemcpyAsync(fl.data(), e->d_flips, fl.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
@@ -402,12 +421,13 @@ int ssf_run_device(isb_ens *e, int rule, int64_t nsteps, int order, const int32_
                 sum += (double)fl[r];
             }
             // (the decision lags one segment behind: in an anneal the acceptance of the next segment is lower still)
-            const bool next_tma = sum / ((double)len * e->R) > thr;
-            stable = next_tma == use_tma ? stable + 1 : 0;
-            use_tma = next_tma;
+            const double acc = sum / ((double)len * e->R);
+            const int next = acc > thr ? 2 : (acc > thr_cold ? 1 : 0);
+            stable = next == mode ? stable + 1 : 0;
+            mode = next;
             // a settled cold regime: fewer, longer launches.  Hot segments stay short — an anneal leaves them, and a long
             // streamed segment that has gone cold costs more than the extra launches
-            if (!use_tma && stable >= 2) seg = std::min<int64_t>(seg * 2, (int64_t)1 << 40);
+            if (mode == 0 && stable >= 2) seg = std::min<int64_t>(seg * 2, (int64_t)1 << 40);
             t0 += len;
         }
         if (ce == cudaSuccess)   // the flip counts of the whole run, where the caller reads them

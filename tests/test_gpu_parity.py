@@ -197,6 +197,42 @@ def test_ssf_segmented_run_equals_the_oracle(ctx, orc, synth, monkeypatch, thr, 
         assert np.array_equal(M, out["M"][:, r]) and _close(out["E"][:, r], E)
 
 
+@pytest.mark.parametrize("rule,per_rep,start", [(1, True, 5), (2, False, 0), (0, False, 77)])
+@pytest.mark.parametrize("thr,thr_cold", [("0.2", "0.04"), ("2", "2"), ("0.5", "0.25")])
+def test_ssf_cold_kernel_in_segmented_runs(ctx, orc, synth, monkeypatch, thr, thr_cold, rule, per_rep, start):
+    """The third kernel of a segmented run (csrc/ssf_cold.cu: fields in shared memory, 28 chains per SM), chosen when the
+    previous segment accepted few flips and the run has no traces: thresholds of the product, "cold from the second
+    segment on", and a mix that alternates streaming / plain / cold launches.  The cached fields pass from kernel to
+    kernel, so every replica must still equal the oracle's single run bit for bit."""
+    L = _lib()
+    N, R, sweeps = 128, 90, 37
+    nsteps = sweeps * N + 51
+    J, h = synth.sk_J(N, 81), synth.gaussian(82, N) * 0.2
+    S0 = synth.spins(83, R, N)
+    gen = synth.logistic if rule == 1 else synth.exponential
+    fl = None if rule == 0 else gen(84, (R, nsteps) if per_rep else nsteps)
+    T = synth.geometric_schedule(3.0, 0.03, sweeps + 1)
+    monkeypatch.setenv("ISB_SSF_SEG_MIN", str(3 * N))
+    monkeypatch.setenv("ISB_SSF_SEG_THR", thr)
+    monkeypatch.setenv("ISB_SSF_COLD_THR", thr_cold)
+    e = L.Ensemble(L.Model.dense(ctx, J, h, L.PREC_F64), R)
+    e.set_spins(S0)
+    out = e.ssf_run(rule, nsteps, start=start, fluct=fl, fluct_per_replica=per_rep, T=T, steps_per_T=N)
+    S = e.get_spins()
+    assert e.last_stats()["launches"] >= 5 or rule == 0      # (Hopfield runs have no schedule to cut at: one launch)
+    assert _close(e.energy()[:4], np.array([orc.energy(J, h, S[r]) for r in range(4)]))
+    for r in (0, 1, R // 2, R - 1):
+        s, flips, _, _ = orc.ssf_run(rule, J, h, S0[r], nsteps, start=start,
+                                     fluct=None if fl is None else (fl[r] if per_rep else fl), T=T, steps_per_T=N)
+        assert np.array_equal(s, S[r]) and flips == out["flips"][r], f"replica {r}"
+    # and the run continues from the cached fields the cold kernel left behind
+    e.ssf_run(rule, 5 * N, start=(start + nsteps) % N, fluct=None if fl is None else fl[..., :5 * N], fluct_per_replica=per_rep,
+              T=T[:5], steps_per_T=N)
+    s, _, _, _ = orc.ssf_run(rule, J, h, S[0], 5 * N, start=(start + nsteps) % N,
+                             fluct=None if fl is None else (fl[0, :5 * N] if per_rep else fl[:5 * N]), T=T[:5], steps_per_T=N)
+    assert np.array_equal(s, e.get_spins()[0])
+
+
 def test_ssf_continuation_and_field_cache(ctx, orc, synth):
     """Two runs back to back == one run (cached local fields stay valid); set_spins invalidates them."""
     L = _lib()
