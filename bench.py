@@ -441,7 +441,8 @@ def run_c2(rt, args, steps, warmup, cpu=True):
     line = base_line(upd_step * steps * rt.world / t_dev, rt.world, steps, warmup, 1e3 * t_dev / steps, prec_name, c2_config(args))
     line["roofline"] = {
         "bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
-        "traffic": traffic, "kernel": "isb::ssf_kernel", "kernel_ms": 1e3 * kern_s,
+        "traffic": traffic, "kernel": "isb::ssf_kernel (streaming and plain instantiations) + isb::ssf_cold_kernel, one per segment of the anneal",
+        "kernel_ms": 1e3 * kern_s,
         "peak_source": f"shared-memory / L1 data path, 128 B/clk/SM x {rt.sms} SMs x {sm_mhz:.0f} MHz (clock sampled in the timed region)",
         "accounting": f"row bytes the chains read through the SM's shared-memory / L1 data path: accepted flips ({flips:.4g} per "
                       f"anneal) x N x {bJ} B (one J row per accepted flip per chain: 128-bit LDS from the ring while the streaming "
