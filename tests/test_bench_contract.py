@@ -31,3 +31,17 @@ def test_reference_arm_other_ranks_stay_silent():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env)
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_tensor_roofline_denominator_follows_the_timed_region():
+    """MEASURED_PEAKS.json holds a burst and a sustained cuBLAS bf16 rate; bench.py divides by the burst rate for a short
+    timed region and by the sustained rate for regions of 2 s and more, and always reports both fractions."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    pk = {"tc_burst": 1617.1, "tc_sustained": 1355.9, "src": "test"}
+    p_short, s_short = b.tensor_peak(pk, 0.4)
+    p_long, s_long = b.tensor_peak(pk, 2.5)
+    assert p_short == 1617.1 and "BURST" in s_short
+    assert p_long == 1355.9 and "SUSTAINED" in s_long

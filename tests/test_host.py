@@ -97,3 +97,39 @@ def test_sparse_input_validation(pkg):
     with pytest.warns(UserWarning, match="diagonal"):
         ss = SS.SpinSystem([1, -1], sp.csc_matrix(np.array([[4.0, 1], [1, 9.0]])), np.zeros(2))
     assert not ss.couplingCoefficients.diagonal().any()
+
+
+def test_spin_validation_fast_path(pkg):
+    """The int8 fast path of the spin check (one pass over the bytes: +1 = 0x01 and -1 = 0xFF are the only bytes x with
+    (x + 1) & 0xFD == 0) accepts and rejects exactly what the general Float64 path does."""
+    chk = pkg.SpinSystems._checked_spins
+    good = np.array([[1, -1, -1, 1]], dtype=np.int8)
+    assert chk(good, (1, 4), "spins").dtype == np.int8
+    for bad in (0, 2, -2, 3, -3, 127, -128, 64, -127, 126):
+        a = good.copy()
+        a[0, 2] = bad
+        with pytest.raises(ValueError, match=r"\+1 / -1"):
+            chk(a, (1, 4), "spins")
+        with pytest.raises(ValueError, match=r"\+1 / -1"):
+            chk(a.astype(np.float64), (1, 4), "spins")
+    assert np.array_equal(chk(np.array([1.0, -1.0]), (1, 2), "spins"), [[1, -1]])
+    with pytest.raises(ValueError, match="wrong shape"):
+        chk(good, (1, 5), "spins")
+
+
+def test_checkerboard_site_list(synth):
+    """ISB_ORDER_CHECKERBOARD's site list: a permutation of the sites, the (x + y) even ones first, ascending within a
+    colour; no two sites of a colour are lattice neighbours (which is why the kernel may decide them concurrently)."""
+    for L in (4, 32, 64):
+        nodes = synth.checkerboard_nodes(L)
+        n = L * L
+        assert sorted(nodes.tolist()) == list(range(n))
+        x, y = nodes % L, nodes // L
+        colour = (x + y) & 1
+        assert np.all(colour[: n // 2] == 0) and np.all(colour[n // 2:] == 1)
+        assert np.all(np.diff(nodes[: n // 2]) > 0) and np.all(np.diff(nodes[n // 2:]) > 0)
+        first = set(nodes[: n // 2].tolist())
+        for i in nodes[: n // 2][:: max(1, n // 64)]:
+            xi, yi = i % L, i // L
+            for nb in (((xi + 1) % L) + yi * L, ((xi - 1) % L) + yi * L, xi + ((yi + 1) % L) * L, xi + ((yi - 1) % L) * L):
+                assert nb not in first
