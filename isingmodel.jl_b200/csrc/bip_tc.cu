@@ -1315,8 +1315,10 @@ static int prec_terms(int prec) {
 static bool prec_is_i8(int prec) { return prec == ISB_PREC_I8X2 || prec == ISB_PREC_I8X3 || prec == ISB_PREC_I8X4; }
 
 // Units per tile of the stacked int8 layout (fixed when the model is built: it is part of the storage order).  The MMA
-// takes N = P * bn <= 256 columns; a tile costs its N columns of tensor time plus a fixed part (the A tile is read once
-// per K block whatever N is, the accumulator hand-over), so minimise tiles x (N + 32) over the multiples of 16.
+// takes N = P * bn <= 256 columns; a tile costs its N columns of tensor time plus a fixed part — the A tile is read once
+// per K block whatever N is, the accumulator hand-over, and above all the per-tile code of the sampling warps (measured
+// on config 4: 512 hidden units as 7 tiles of 80 beat 8 tiles of 64 by 3 % although they pad the layer to 560) — so
+// minimise tiles x (N + 160) over the multiples of 16.
 static int i8_pick_bn(int nout, int P) {
     if (const char *env = getenv("ISB_I8_BN")) {
         const int v = atoi(env);
@@ -1325,7 +1327,7 @@ static int i8_pick_bn(int nout, int P) {
     int best = 16;
     long best_cost = 0;
     for (int bn = 16; bn * P <= TC_BN_MAX; bn += 16) {
-        const long cost = (long)((nout + bn - 1) / bn) * (bn * P + 32);
+        const long cost = (long)((nout + bn - 1) / bn) * (bn * P + 160);
         if (best_cost == 0 || cost <= best_cost) {
             best = bn;
             best_cost = cost;
